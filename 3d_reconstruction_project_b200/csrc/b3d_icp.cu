@@ -1,0 +1,735 @@
+// b3d_icp.cu -- K4: registration_icp / registration_generalized_icp.
+// One kernel per ICP pass fuses: transform of the source point, nearest-neighbour correspondence search in the hashed
+// target grid, residual / Jacobian evaluation, the 29-value normal-equation reduction (warp shuffles -> block -> the
+// last block sums the per-block partials in a fixed order, no data-path atomics), the 6x6 LDL^T solve (or the
+// Umeyama step for point-to-point), the transform update and the convergence test. The loop state lives on the
+// device; the host only enqueues passes. A batch of P independent pairs runs in the same launches (grid.y = pair).
+#include "b3d_icp.cuh"
+#include "b3d_search.cuh"
+
+#include <cmath>
+#include <cstring>
+
+namespace b3d {
+
+namespace {
+
+constexpr int kIcpBlock = 128;
+
+// ---- small dense helpers (device) ----------------------------------------------------------------------------------
+__device__ void mat4_mul(const double* A, const double* B, double* C) {
+    double R[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0;
+            for (int k = 0; k < 4; ++k) s += A[4 * i + k] * B[4 * k + j];
+            R[4 * i + j] = s;
+        }
+    for (int i = 0; i < 16; ++i) C[i] = R[i];
+}
+__device__ void mat4_identity(double* T) {
+    for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+}
+// TransformVector6dToMatrix4d: R = Rz(x2) Ry(x1) Rx(x0), t = x[3..5]
+__device__ void vec6_to_mat4(const double* x, double* T) {
+    const double ca = cos(x[0]), sa = sin(x[0]);
+    const double cb = cos(x[1]), sb = sin(x[1]);
+    const double cg = cos(x[2]), sg = sin(x[2]);
+    T[0] = cg * cb; T[1] = cg * sb * sa - sg * ca; T[2] = cg * sb * ca + sg * sa; T[3] = x[3];
+    T[4] = sg * cb; T[5] = sg * sb * sa + cg * ca; T[6] = sg * sb * ca - cg * sa; T[7] = x[4];
+    T[8] = -sb;     T[9] = cb * sa;                T[10] = cb * ca;               T[11] = x[5];
+    T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
+}
+// 6x6 symmetric solve by LDL^T without pivoting; false if a pivot is not positive / finite (identity update)
+__device__ bool solve6(const double* A, const double* b, double* x) {
+    double L[36], D[6];
+    for (int i = 0; i < 36; ++i) L[i] = 0;
+    for (int j = 0; j < 6; ++j) {
+        double d = A[6 * j + j];
+        for (int k = 0; k < j; ++k) d -= L[6 * j + k] * L[6 * j + k] * D[k];
+        if (!(d > 0) || !isfinite(d)) return false;
+        D[j] = d;
+        L[6 * j + j] = 1;
+        for (int i = j + 1; i < 6; ++i) {
+            double s = A[6 * i + j];
+            for (int k = 0; k < j; ++k) s -= L[6 * i + k] * L[6 * j + k] * D[k];
+            L[6 * i + j] = s / d;
+        }
+    }
+    double y[6];
+    for (int i = 0; i < 6; ++i) {
+        double s = b[i];
+        for (int k = 0; k < i; ++k) s -= L[6 * i + k] * y[k];
+        y[i] = s;
+    }
+    for (int i = 0; i < 6; ++i) y[i] /= D[i];
+    for (int i = 5; i >= 0; --i) {
+        double s = y[i];
+        for (int k = i + 1; k < 6; ++k) s -= L[6 * k + i] * x[k];
+        x[i] = s;
+    }
+    for (int i = 0; i < 6; ++i)
+        if (!isfinite(x[i])) return false;
+    return true;
+}
+// symmetric 3x3 Jacobi eigen-decomposition: A = V diag(w) V^T
+__device__ void jacobi_eig3(const double* A_in, double* w, double* V) {
+    double A[9];
+    for (int i = 0; i < 9; ++i) { A[i] = A_in[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        const double offd = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
+        if (offd == 0) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                const double apq = A[3 * p + q];
+                if (apq == 0) continue;
+                const double theta = (A[3 * q + q] - A[3 * p + p]) / (2 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+                const double c = 1 / sqrt(t * t + 1), s = t * c;
+                for (int k = 0; k < 3; ++k) {
+                    const double akp = A[3 * k + p], akq = A[3 * k + q];
+                    A[3 * k + p] = c * akp - s * akq;
+                    A[3 * k + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double apk = A[3 * p + k], aqk = A[3 * q + k];
+                    A[3 * p + k] = c * apk - s * aqk;
+                    A[3 * q + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double vkp = V[3 * k + p], vkq = V[3 * k + q];
+                    V[3 * k + p] = c * vkp - s * vkq;
+                    V[3 * k + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    w[0] = A[0]; w[1] = A[4]; w[2] = A[8];
+}
+__device__ double det3(const double* M) {
+    return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+}
+// Eigen::umeyama(src, dst, with_scaling = false): R = U S V^T of Sigma = cov(dst, src), t = mu_d - R mu_s
+__device__ void umeyama_from_moments(const double* mu_s, const double* mu_d, const double* Sigma, double* T) {
+    double StS[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += Sigma[3 * k + i] * Sigma[3 * k + j];
+            StS[3 * i + j] = s;
+        }
+    double w[3], V[9];
+    jacobi_eig3(StS, w, V);
+    int ord[3] = {0, 1, 2};
+    // sort eigenvalues descending (3 elements)
+    if (w[ord[0]] < w[ord[1]]) { int t = ord[0]; ord[0] = ord[1]; ord[1] = t; }
+    if (w[ord[1]] < w[ord[2]]) { int t = ord[1]; ord[1] = ord[2]; ord[2] = t; }
+    if (w[ord[0]] < w[ord[1]]) { int t = ord[0]; ord[0] = ord[1]; ord[1] = t; }
+    double Vs[9], U[9];
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) Vs[3 * r + c] = V[3 * r + ord[c]];
+    for (int c = 0; c < 2; ++c) {
+        double u[3];
+        for (int r = 0; r < 3; ++r) u[r] = Sigma[3 * r] * Vs[c] + Sigma[3 * r + 1] * Vs[3 + c] + Sigma[3 * r + 2] * Vs[6 + c];
+        const double nrm = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        if (nrm > 0)
+            for (int r = 0; r < 3; ++r) U[3 * r + c] = u[r] / nrm;
+        else
+            for (int r = 0; r < 3; ++r) U[3 * r + c] = (r == c) ? 1.0 : 0.0;
+    }
+    {
+        double u[3];
+        for (int r = 0; r < 3; ++r) u[r] = Sigma[3 * r] * Vs[2] + Sigma[3 * r + 1] * Vs[3 + 2] + Sigma[3 * r + 2] * Vs[6 + 2];
+        const double cx = U[3 * 1 + 0] * U[3 * 2 + 1] - U[3 * 2 + 0] * U[3 * 1 + 1];
+        const double cy = U[3 * 2 + 0] * U[3 * 0 + 1] - U[3 * 0 + 0] * U[3 * 2 + 1];
+        const double cz = U[3 * 0 + 0] * U[3 * 1 + 1] - U[3 * 1 + 0] * U[3 * 0 + 1];
+        const double sgn = (u[0] * cx + u[1] * cy + u[2] * cz) < 0 ? -1.0 : 1.0;
+        U[2] = sgn * cx; U[5] = sgn * cy; U[8] = sgn * cz;
+    }
+    double S[3] = {1, 1, 1};
+    if (det3(U) * det3(Vs) < 0) S[2] = -1;
+    double R[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += U[3 * i + k] * S[k] * Vs[3 * j + k];
+            R[3 * i + j] = s;
+        }
+    mat4_identity(T);
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) T[4 * i + j] = R[3 * i + j];
+        T[4 * i + 3] = mu_d[i] - (R[3 * i] * mu_s[0] + R[3 * i + 1] * mu_s[1] + R[3 * i + 2] * mu_s[2]);
+    }
+}
+// (M^-1)^(1/2) of a symmetric positive-definite 3x3 (GICP weight)
+__device__ void inv_sqrt_sym3(const double* M, double* W) {
+    double w[3], V[9];
+    jacobi_eig3(M, w, V);
+    double s[3];
+    for (int i = 0; i < 3; ++i) s[i] = 1.0 / sqrt(w[i]);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double a = 0;
+            for (int k = 0; k < 3; ++k) a += V[3 * i + k] * s[k] * V[3 * j + k];
+            W[3 * i + j] = a;
+        }
+}
+
+// ---- reduction of kIcpSums doubles over a block: result valid in thread 0 ------------------------------------------
+__device__ __forceinline__ void block_reduce_sums(double* a, double (*sm)[kIcpSums]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < kIcpSums; ++j) {
+        double v = a[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        a[j] = v;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < kIcpSums; ++j) sm[warp][j] = a[j];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kIcpBlock / 32; ++w)
+#pragma unroll
+            for (int j = 0; j < kIcpSums; ++j) a[j] += sm[w][j];
+    }
+}
+
+// ---- end of a pass: fitness / rmse / convergence / update (one thread per pair) -------------------------------------
+__device__ void icp_finalize_pair(int kind, const double* a, double ns, double rel_fitness, double rel_rmse, int max_iter, IcpPairState* st) {
+    const double nc = a[27];
+    const double fitness = (nc == 0 || ns == 0) ? 0.0 : nc / ns;
+    const double rmse = nc == 0 ? 0.0 : sqrt(a[28] / nc);
+    st->fitness = fitness;
+    st->rmse = rmse;
+    st->n_corr = (long long)nc;
+    const int k = st->iter;
+    if (k > 0 && fabs(st->prev_fitness - fitness) < rel_fitness && fabs(st->prev_rmse - rmse) < rel_rmse) {
+        st->done = 1;
+        st->converged = 1;
+        return;
+    }
+    if (k >= max_iter) {
+        st->done = 1;
+        return;
+    }
+    double U[16];
+    mat4_identity(U);
+    if (nc > 0) {
+        if (kind == B3D_ICP_POINT_TO_POINT) {
+            const double mu_s[3] = {a[0] / nc, a[1] / nc, a[2] / nc}, mu_d[3] = {a[3] / nc, a[4] / nc, a[5] / nc};
+            double Sigma[9];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) Sigma[3 * r + c] = a[6 + 3 * r + c] / nc - mu_d[r] * mu_s[c];
+            umeyama_from_moments(mu_s, mu_d, Sigma, U);
+        } else {
+            double A[36], b[6], x[6];
+            int t = 0;
+            for (int u = 0; u < 6; ++u)
+                for (int v = u; v < 6; ++v) { A[6 * u + v] = a[t]; A[6 * v + u] = a[t]; ++t; }
+            for (int u = 0; u < 6; ++u) b[u] = -a[21 + u];
+            if (solve6(A, b, x)) vec6_to_mat4(x, U);
+        }
+    }
+    double Tn[16];
+    mat4_mul(U, st->T, Tn);
+    for (int i = 0; i < 16; ++i) st->T[i] = Tn[i];
+    st->prev_fitness = fitness;
+    st->prev_rmse = rmse;
+    st->iter = k + 1;
+}
+
+struct IcpKernelArgs {
+    int kind;
+    const double* src;
+    const double* src_cov;
+    const int32_t* src_off;
+    const int64_t* ns_global;
+    GridView<double> grid;
+    const int32_t* tgt_off;
+    const double* tgt_nrm_sorted;
+    const double* tgt_cov_sorted;
+    double r2;
+    int rmax;
+    double rel_fitness, rel_rmse;
+    int max_iter;
+    IcpPairState* state;
+    double* partial;
+    double* sums;
+    int32_t* corr;
+    int fused;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(kIcpBlock) icp_pass_kernel(IcpKernelArgs A) {
+    const int pair = blockIdx.y;
+    IcpPairState* st = A.state + pair;
+    if (st->done) return;
+    __shared__ double sT[16];
+    __shared__ double sm[kIcpBlock / 32][kIcpSums];
+    __shared__ int s_last;
+    if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
+    __syncthreads();
+    const int32_t s0 = A.src_off[pair], s1 = A.src_off[pair + 1];
+    const int32_t t0 = A.tgt_off[pair];
+    double a[kIcpSums];
+#pragma unroll
+    for (int j = 0; j < kIcpSums; ++j) a[j] = 0.0;
+    for (int32_t i = s0 + blockIdx.x * kIcpBlock + threadIdx.x; i < s1; i += gridDim.x * kIcpBlock) {
+        const double x = A.src[3 * (int64_t)i], y = A.src[3 * (int64_t)i + 1], z = A.src[3 * (int64_t)i + 2];
+        // PointCloud::Transform: (T [p,1]).xyz / w
+        const double w = sT[12] * x + sT[13] * y + sT[14] * z + sT[15];
+        const double px = (sT[0] * x + sT[1] * y + sT[2] * z + sT[3]) / w;
+        const double py = (sT[4] * x + sT[5] * y + sT[6] * z + sT[7]) / w;
+        const double pz = (sT[8] * x + sT[9] * y + sT[10] * z + sT[11]) / w;
+        double d2;
+        int idx;
+        const int pos = nn_within_query<double>(A.grid, pair, px, py, pz, A.r2, A.rmax, &d2, &idx);
+        if (A.corr != nullptr) A.corr[i] = pos >= 0 ? idx - t0 : -1;
+        if (pos < 0) continue;
+        const double4 q = ld_point(A.grid.pts + pos);
+        a[27] += 1.0;
+        a[28] += d2;
+        if (KIND == B3D_ICP_POINT_TO_POINT) {
+            a[0] += px; a[1] += py; a[2] += pz;
+            a[3] += q.x; a[4] += q.y; a[5] += q.z;
+            const double qq[3] = {q.x, q.y, q.z}, pp[3] = {px, py, pz};
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) a[6 + 3 * r + c] += qq[r] * pp[c];
+        } else if (KIND == B3D_ICP_POINT_TO_PLANE) {
+            const double* nq = A.tgt_nrm_sorted + 3 * (int64_t)pos;
+            const double n0 = __ldg(nq), n1 = __ldg(nq + 1), n2 = __ldg(nq + 2);
+            const double r = (px - q.x) * n0 + (py - q.y) * n1 + (pz - q.z) * n2;
+            const double J[6] = {py * n2 - pz * n1, pz * n0 - px * n2, px * n1 - py * n0, n0, n1, n2};
+            int t = 0;
+#pragma unroll
+            for (int u = 0; u < 6; ++u)
+#pragma unroll
+                for (int v = u; v < 6; ++v) a[t++] += J[u] * J[v];
+#pragma unroll
+            for (int u = 0; u < 6; ++u) a[21 + u] += J[u] * r;
+        } else {
+            // generalized ICP: M = C_t + R C_s R^T, W = (M^-1)^(1/2), rows r_k = W_k (p - q), J = W [ -[p]x | I ]
+            const double* Ct = A.tgt_cov_sorted + 9 * (int64_t)pos;
+            const double* Cs = A.src_cov + 9 * (int64_t)i;
+            double RC[9], M[9], W[9];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) RC[3 * r + c] = sT[4 * r] * Cs[c] + sT[4 * r + 1] * Cs[3 + c] + sT[4 * r + 2] * Cs[6 + c];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    M[3 * r + c] = __ldg(Ct + 3 * r + c) + (RC[3 * r] * sT[4 * c] + RC[3 * r + 1] * sT[4 * c + 1] + RC[3 * r + 2] * sT[4 * c + 2]);
+            inv_sqrt_sym3(M, W);
+            const double d[3] = {px - q.x, py - q.y, pz - q.z};
+            const double Sk[9] = {0, pz, -py, -pz, 0, px, py, -px, 0};
+#pragma unroll
+            for (int row = 0; row < 3; ++row) {
+                double J[6];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) J[c] = W[3 * row] * Sk[c] + W[3 * row + 1] * Sk[3 + c] + W[3 * row + 2] * Sk[6 + c];
+                J[3] = W[3 * row]; J[4] = W[3 * row + 1]; J[5] = W[3 * row + 2];
+                const double r = W[3 * row] * d[0] + W[3 * row + 1] * d[1] + W[3 * row + 2] * d[2];
+                int t = 0;
+#pragma unroll
+                for (int u = 0; u < 6; ++u)
+#pragma unroll
+                    for (int v = u; v < 6; ++v) a[t++] += J[u] * J[v];
+#pragma unroll
+                for (int u = 0; u < 6; ++u) a[21 + u] += J[u] * r;
+            }
+        }
+    }
+    block_reduce_sums(a, sm);
+    double* part = A.partial + ((int64_t)pair * gridDim.x + blockIdx.x) * kIcpSums;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < kIcpSums; ++j) part[j] = a[j];
+        __threadfence();
+        const unsigned int t = atomicAdd(&st->ticket, 1u);
+        s_last = (t == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // last block of this pair: second pass over the per-block partials, fixed order (rows strided by thread, then tree)
+    __threadfence();
+#pragma unroll
+    for (int j = 0; j < kIcpSums; ++j) a[j] = 0.0;
+    const double* base = A.partial + (int64_t)pair * gridDim.x * kIcpSums;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kIcpBlock) {
+#pragma unroll
+        for (int j = 0; j < kIcpSums; ++j) a[j] += __ldcg(base + (int64_t)b * kIcpSums + j);
+    }
+    __syncthreads();
+    block_reduce_sums(a, sm);
+    if (threadIdx.x == 0) {
+        st->ticket = 0;
+        double* out = A.sums + (int64_t)pair * kIcpSums;
+#pragma unroll
+        for (int j = 0; j < kIcpSums; ++j) out[j] = a[j];
+        if (A.fused) {
+            const double ns = A.ns_global ? (double)A.ns_global[pair] : (double)(s1 - s0);
+            icp_finalize_pair(A.kind, a, ns, A.rel_fitness, A.rel_rmse, A.max_iter, st);
+        }
+    }
+}
+
+__global__ void icp_finalize_kernel(int kind, const double* __restrict__ sums, const int32_t* __restrict__ src_off, const int64_t* __restrict__ ns_global,
+                                    double rel_fitness, double rel_rmse, int max_iter, IcpPairState* state, int P) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= P) return;
+    IcpPairState* st = state + pair;
+    if (st->done) return;
+    double a[kIcpSums];
+    for (int j = 0; j < kIcpSums; ++j) a[j] = sums[(int64_t)pair * kIcpSums + j];
+    const double ns = ns_global ? (double)ns_global[pair] : (double)(src_off[pair + 1] - src_off[pair]);
+    icp_finalize_pair(kind, a, ns, rel_fitness, rel_rmse, max_iter, st);
+}
+
+__global__ void icp_init_state_kernel(IcpPairState* state, const double* __restrict__ init, int P) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= P) return;
+    IcpPairState s;
+    for (int i = 0; i < 16; ++i) s.T[i] = init ? init[16 * pair + i] : ((i % 5 == 0) ? 1.0 : 0.0);
+    s.fitness = s.rmse = s.prev_fitness = s.prev_rmse = 0.0;
+    s.n_corr = 0;
+    s.iter = 0;
+    s.done = 0;
+    s.converged = 0;
+    s.ticket = 0;
+    state[pair] = s;
+}
+
+// dst[pos] = src[original index of sorted position pos] (cols doubles per row)
+__global__ void __launch_bounds__(256) gather_by_sorted_kernel(const double4* __restrict__ pts, int32_t n, const double* __restrict__ src, int cols,
+                                                               double* __restrict__ dst) {
+    const int64_t total = (int64_t)n * cols;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pos = t / cols;
+        const int c = (int)(t - pos * cols);
+        const int64_t oi = (int64_t)__double_as_longlong(pts[pos].w);
+        dst[t] = src[oi * cols + c];
+    }
+}
+
+__global__ void __launch_bounds__(256) transform_kernel(const double* __restrict__ T16, double* __restrict__ xyz, int64_t n, double* __restrict__ nrm,
+                                                        double* __restrict__ cov) {
+    __shared__ double T[16];
+    if (threadIdx.x < 16) T[threadIdx.x] = T16[threadIdx.x];
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        const double nx = T[0] * x + T[1] * y + T[2] * z + T[3];
+        const double ny = T[4] * x + T[5] * y + T[6] * z + T[7];
+        const double nz = T[8] * x + T[9] * y + T[10] * z + T[11];
+        const double w = T[12] * x + T[13] * y + T[14] * z + T[15];
+        xyz[3 * i] = nx / w; xyz[3 * i + 1] = ny / w; xyz[3 * i + 2] = nz / w;
+        if (nrm != nullptr) {
+            const double a = nrm[3 * i], b = nrm[3 * i + 1], c = nrm[3 * i + 2];
+            nrm[3 * i] = T[0] * a + T[1] * b + T[2] * c;
+            nrm[3 * i + 1] = T[4] * a + T[5] * b + T[6] * c;
+            nrm[3 * i + 2] = T[8] * a + T[9] * b + T[10] * c;
+        }
+        if (cov != nullptr) {
+            double* C = cov + 9 * i;
+            double Cin[9], RC[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) Cin[k] = C[k];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c2 = 0; c2 < 3; ++c2) RC[3 * r + c2] = T[4 * r] * Cin[c2] + T[4 * r + 1] * Cin[3 + c2] + T[4 * r + 2] * Cin[6 + c2];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c2 = 0; c2 < 3; ++c2) C[3 * r + c2] = RC[3 * r] * T[4 * c2] + RC[3 * r + 1] * T[4 * c2 + 1] + RC[3 * r + 2] * T[4 * c2 + 2];
+        }
+    }
+}
+
+}  // namespace
+
+int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWork* w) {
+    const int P = pb.P;
+    int64_t longest = 0;
+    for (int p = 0; p < P; ++p) longest = std::max<int64_t>(longest, pb.src_off_h[p + 1] - pb.src_off_h[p]);
+    int blocks = (int)std::max<int64_t>(1, (longest + kIcpBlock - 1) / kIcpBlock);
+    const int cap = std::max(1, ctx->sm_count * 16 / P);
+    w->blocks = std::min(blocks, cap);
+    B3D_TRY(w->state.alloc(ctx, P));
+    B3D_TRY(w->partial.alloc(ctx, (size_t)P * w->blocks * kIcpSums));
+    B3D_TRY(w->sums.alloc(ctx, (size_t)P * kIcpSums));
+    DevBuf<double> init_d;
+    if (init_h) {
+        B3D_TRY(init_d.alloc(ctx, (size_t)P * 16));
+        B3D_TRY(ctx->upload(init_d.p, init_h, (size_t)P * 16 * sizeof(double)));
+    }
+    B3D_LAUNCH(ctx, icp_init_state_kernel, (P + 127) / 128, 128, 0, w->state.p, init_h ? init_d.p : (const double*)nullptr, P);
+    const Grid<double>& g = *pb.tgt_grid;
+    const int32_t nt = (int32_t)g.sort.n;
+    if (pb.kind == B3D_ICP_POINT_TO_PLANE) {
+        B3D_TRY(w->tgt_nrm_sorted.alloc(ctx, (size_t)nt * 3));
+        B3D_LAUNCH(ctx, gather_by_sorted_kernel, ctx->grid_for((int64_t)nt * 3, 256, 1, 8), 256, 0, g.pts.p, nt, pb.tgt_normals, 3, w->tgt_nrm_sorted.p);
+    } else if (pb.kind == B3D_ICP_GENERALIZED) {
+        B3D_TRY(w->tgt_cov_sorted.alloc(ctx, (size_t)nt * 9));
+        B3D_LAUNCH(ctx, gather_by_sorted_kernel, ctx->grid_for((int64_t)nt * 9, 256, 1, 8), 256, 0, g.pts.p, nt, pb.tgt_cov, 9, w->tgt_cov_sorted.p);
+    }
+    return B3D_OK;
+}
+
+static IcpKernelArgs make_args(const IcpProblem& pb, IcpWork* w, int32_t* corr, bool fused) {
+    IcpKernelArgs A;
+    A.kind = pb.kind;
+    A.src = pb.src;
+    A.src_cov = pb.src_cov;
+    A.src_off = pb.src_off;
+    A.ns_global = pb.ns_global;
+    A.grid = pb.tgt_grid->view();
+    A.tgt_off = pb.tgt_off;
+    A.tgt_nrm_sorted = w->tgt_nrm_sorted.p;
+    A.tgt_cov_sorted = w->tgt_cov_sorted.p;
+    A.r2 = pb.max_dist * pb.max_dist;
+    A.rmax = pb.rmax;
+    A.rel_fitness = pb.rel_fitness;
+    A.rel_rmse = pb.rel_rmse;
+    A.max_iter = pb.max_iter;
+    A.state = w->state.p;
+    A.partial = w->partial.p;
+    A.sums = w->sums.p;
+    A.corr = corr;
+    A.fused = fused ? 1 : 0;
+    return A;
+}
+
+int icp_pass(b3d_ctx* ctx, const IcpProblem& pb, IcpWork* w, int32_t* corr, bool fused) {
+    IcpKernelArgs A = make_args(pb, w, corr, fused);
+    const dim3 grid(w->blocks, pb.P);
+    if (pb.kind == B3D_ICP_POINT_TO_POINT) {
+        B3D_LAUNCH(ctx, icp_pass_kernel<B3D_ICP_POINT_TO_POINT>, grid, kIcpBlock, 0, A);
+    } else if (pb.kind == B3D_ICP_POINT_TO_PLANE) {
+        B3D_LAUNCH(ctx, icp_pass_kernel<B3D_ICP_POINT_TO_PLANE>, grid, kIcpBlock, 0, A);
+    } else {
+        B3D_LAUNCH(ctx, icp_pass_kernel<B3D_ICP_GENERALIZED>, grid, kIcpBlock, 0, A);
+    }
+    return B3D_OK;
+}
+
+int icp_finalize_from_sums(b3d_ctx* ctx, const IcpProblem& pb, IcpWork* w) {
+    B3D_LAUNCH(ctx, icp_finalize_kernel, (pb.P + 127) / 128, 128, 0, pb.kind, w->sums.p, pb.src_off, pb.ns_global, pb.rel_fitness, pb.rel_rmse,
+               pb.max_iter, w->state.p, pb.P);
+    return B3D_OK;
+}
+
+int icp_run(b3d_ctx* ctx, const IcpProblem& pb, IcpWork* w, int32_t* corr) {
+    // max_iter updates need max_iter + 1 correspondence passes; finished pairs return at once
+    for (int k = 0; k <= pb.max_iter; ++k) B3D_TRY(icp_pass(ctx, pb, w, corr, true));
+    return B3D_OK;
+}
+
+int icp_results(b3d_ctx* ctx, const IcpProblem& pb, IcpWork* w, b3d_icp_result* results_h) {
+    std::vector<IcpPairState> st(pb.P);
+    B3D_TRY(ctx->download(st.data(), w->state.p, (size_t)pb.P * sizeof(IcpPairState)));
+    for (int p = 0; p < pb.P; ++p) {
+        b3d_icp_result& r = results_h[p];
+        memcpy(r.transformation, st[p].T, sizeof(r.transformation));
+        r.fitness = st[p].fitness;
+        r.inlier_rmse = st[p].rmse;
+        r.iterations = st[p].iter;
+        r.converged = st[p].converged;
+        r.n_correspondences = st[p].n_corr;
+    }
+    return B3D_OK;
+}
+
+}  // namespace b3d
+
+using namespace b3d;
+
+struct b3d_icp_state {
+    IcpProblem pb;
+    IcpWork work;
+    Grid<double> grid;
+    DevBuf<int32_t> src_off, tgt_off;
+    Segments tgt_seg;
+    DevBuf<int32_t> corr;
+    bool pending_sums = false;
+};
+
+static int validate_icp(int kind, const double* src, int64_t ns, const double* src_cov, const double* tgt, int64_t nt, const double* tgt_normals,
+                        const double* tgt_cov, double max_dist, int max_iter) {
+    B3D_REQUIRE(kind >= 0 && kind <= 2, "unknown ICP kind %d", kind);
+    B3D_REQUIRE(max_dist > 0.0, "Invalid max_correspondence_distance.");
+    B3D_REQUIRE(ns >= 0 && nt >= 0 && max_iter >= 0, "negative size");
+    B3D_REQUIRE(ns == 0 || src != nullptr, "source is NULL");
+    B3D_REQUIRE(nt == 0 || tgt != nullptr, "target is NULL");
+    if (kind == B3D_ICP_POINT_TO_PLANE)
+        B3D_REQUIRE(nt == 0 || tgt_normals != nullptr,
+                    "TransformationEstimationPointToPlane and TransformationEstimationColoredICP require pre-computed normal vectors for target "
+                    "PointCloud.");
+    if (kind == B3D_ICP_GENERALIZED) B3D_REQUIRE((ns == 0 || src_cov) && (nt == 0 || tgt_cov), "GeneralizedICP requires covariances.");
+    return B3D_OK;
+}
+
+static void empty_result(const double* init_h, b3d_icp_result* r) {
+    for (int i = 0; i < 16; ++i) r->transformation[i] = init_h ? init_h[i] : ((i % 5 == 0) ? 1.0 : 0.0);
+    r->fitness = 0;
+    r->inlier_rmse = 0;
+    r->iterations = 0;
+    r->converged = 0;
+    r->n_correspondences = 0;
+}
+
+// builds the single-pair problem (target grid included) inside st
+static int setup_single(b3d_ctx* ctx, b3d_icp_state* st, int kind, const double* src, int64_t ns_local, const double* src_cov, const double* tgt,
+                        int64_t nt, const double* tgt_normals, const double* tgt_cov, double max_dist, const double* init_h, double rel_fitness,
+                        double rel_rmse, int max_iter) {
+    B3D_TRY(single_segment(ctx, nt, &st->tgt_off, &st->tgt_seg));
+    Segments sseg;
+    B3D_TRY(single_segment(ctx, ns_local, &st->src_off, &sseg));
+    int rmax = 1;
+    B3D_TRY(build_search_grid<double>(ctx, tgt, st->tgt_seg, 8, max_dist, &st->grid, &rmax));
+    IcpProblem& pb = st->pb;
+    pb.kind = kind;
+    pb.P = 1;
+    pb.src = src;
+    pb.src_cov = src_cov;
+    pb.src_off = st->src_off.p;
+    pb.src_off_h = sseg.off_h;
+    pb.tgt_grid = &st->grid;
+    pb.tgt_off = st->tgt_off.p;
+    pb.tgt_normals = tgt_normals;
+    pb.tgt_cov = tgt_cov;
+    pb.max_dist = max_dist;
+    pb.rmax = rmax;
+    pb.rel_fitness = rel_fitness;
+    pb.rel_rmse = rel_rmse;
+    pb.max_iter = max_iter;
+    return icp_prepare(ctx, pb, init_h, &st->work);
+}
+
+extern "C" {
+
+int b3d_transform_f64(b3d_ctx* ctx, const double* T_h, double* xyz, int64_t n, double* normals, double* cov) {
+    B3D_REQUIRE(ctx != nullptr && T_h != nullptr, "b3d_transform_f64: NULL argument");
+    B3D_REQUIRE(n >= 0, "negative point count");
+    if (n == 0) return B3D_OK;
+    B3D_REQUIRE(xyz != nullptr, "b3d_transform_f64: NULL buffer");
+    B3D_TRY(ctx->bind());
+    DevBuf<double> T;
+    B3D_TRY(T.alloc(ctx, 16));
+    B3D_TRY(ctx->upload(T.p, T_h, 16 * sizeof(double)));
+    B3D_LAUNCH(ctx, transform_kernel, ctx->grid_for(n, 256, 1, 8), 256, 0, T.p, xyz, n, normals, cov);
+    return B3D_OK;
+}
+
+int b3d_icp_correspondences(b3d_ctx* ctx, const double* src, int64_t ns, const double* tgt, int64_t nt, const double* T_h, double max_dist,
+                            int32_t* corr, double* stats_h) {
+    B3D_REQUIRE(ctx != nullptr, "ctx is NULL");
+    B3D_TRY(validate_icp(B3D_ICP_POINT_TO_POINT, src, ns, nullptr, tgt, nt, nullptr, nullptr, max_dist, 0));
+    if (stats_h) stats_h[0] = stats_h[1] = 0.0;
+    if (ns == 0) return B3D_OK;
+    B3D_TRY(ctx->bind());
+    if (nt == 0) {
+        if (corr) B3D_CUDA(cudaMemsetAsync(corr, 0xff, (size_t)ns * sizeof(int32_t), ctx->stream));
+        return B3D_OK;
+    }
+    b3d_icp_state st;
+    B3D_TRY(setup_single(ctx, &st, B3D_ICP_POINT_TO_POINT, src, ns, nullptr, tgt, nt, nullptr, nullptr, max_dist, T_h, 1e-6, 1e-6, 0));
+    B3D_TRY(icp_pass(ctx, st.pb, &st.work, corr, false));
+    double sums[kIcpSums];
+    B3D_TRY(ctx->download(sums, st.work.sums.p, sizeof(sums)));
+    if (stats_h) {
+        stats_h[0] = sums[27];
+        stats_h[1] = sums[28];
+    }
+    return B3D_OK;
+}
+
+int b3d_icp(b3d_ctx* ctx, int kind, const double* src, int64_t ns, const double* src_cov, const double* tgt, int64_t nt, const double* tgt_normals,
+            const double* tgt_cov, double max_dist, const double* init_h, double rel_fitness, double rel_rmse, int max_iter,
+            b3d_icp_result* result_h, int32_t* corr) {
+    B3D_REQUIRE(ctx != nullptr && result_h != nullptr, "b3d_icp: NULL argument");
+    B3D_TRY(validate_icp(kind, src, ns, src_cov, tgt, nt, tgt_normals, tgt_cov, max_dist, max_iter));
+    empty_result(init_h, result_h);
+    if (ns == 0) return B3D_OK;
+    B3D_TRY(ctx->bind());
+    if (nt == 0) {
+        if (corr) B3D_CUDA(cudaMemsetAsync(corr, 0xff, (size_t)ns * sizeof(int32_t), ctx->stream));
+        return ctx->sync();
+    }
+    b3d_icp_state st;
+    B3D_TRY(setup_single(ctx, &st, kind, src, ns, src_cov, tgt, nt, tgt_normals, tgt_cov, max_dist, init_h, rel_fitness, rel_rmse, max_iter));
+    B3D_TRY(icp_run(ctx, st.pb, &st.work, corr));
+    return icp_results(ctx, st.pb, &st.work, result_h);
+}
+
+int b3d_icp_begin(b3d_ctx* ctx, int kind, const double* src, int64_t ns_local, int64_t ns_total, const double* src_cov, const double* tgt,
+                  int64_t nt, const double* tgt_normals, const double* tgt_cov, double max_dist, const double* init_h, double rel_fitness,
+                  double rel_rmse, int max_iter, b3d_icp_state** out) {
+    B3D_REQUIRE(ctx != nullptr && out != nullptr, "b3d_icp_begin: NULL argument");
+    *out = nullptr;
+    B3D_TRY(validate_icp(kind, src, ns_local, src_cov, tgt, nt, tgt_normals, tgt_cov, max_dist, max_iter));
+    B3D_REQUIRE(nt > 0, "b3d_icp_begin: empty target");
+    B3D_REQUIRE(ns_total >= ns_local, "b3d_icp_begin: ns_total < ns_local");
+    B3D_TRY(ctx->bind());
+    b3d_icp_state* st = new b3d_icp_state();
+    int rc = setup_single(ctx, st, kind, src, ns_local, src_cov, tgt, nt, tgt_normals, tgt_cov, max_dist, init_h, rel_fitness, rel_rmse, max_iter);
+    if (rc == B3D_OK) rc = st->work.ns_global.alloc(ctx, 1);
+    if (rc == B3D_OK) rc = ctx->upload(st->work.ns_global.p, &ns_total, sizeof(int64_t));
+    if (rc == B3D_OK) rc = st->corr.alloc(ctx, (size_t)std::max<int64_t>(ns_local, 1));
+    if (rc != B3D_OK) {
+        delete st;
+        return rc;
+    }
+    st->pb.ns_global = st->work.ns_global.p;
+    *out = st;
+    return B3D_OK;
+}
+
+int b3d_icp_accumulate(b3d_ctx* ctx, b3d_icp_state* st, double** sums_dev_out) {
+    B3D_REQUIRE(ctx != nullptr && st != nullptr && sums_dev_out != nullptr, "b3d_icp_accumulate: NULL argument");
+    B3D_TRY(ctx->bind());
+    if (st->pb.src_off_h[1] > 0) {
+        B3D_TRY(icp_pass(ctx, st->pb, &st->work, st->corr.p, false));
+    } else {
+        B3D_CUDA(cudaMemsetAsync(st->work.sums.p, 0, kIcpSums * sizeof(double), ctx->stream));
+    }
+    st->pending_sums = true;
+    *sums_dev_out = st->work.sums.p;
+    return B3D_OK;
+}
+
+int b3d_icp_update(b3d_ctx* ctx, b3d_icp_state* st, int* done_h) {
+    B3D_REQUIRE(ctx != nullptr && st != nullptr, "b3d_icp_update: NULL argument");
+    if (!st->pending_sums) return set_error(B3D_E_STATE, "b3d_icp_update called without a preceding b3d_icp_accumulate");
+    B3D_TRY(ctx->bind());
+    B3D_TRY(icp_finalize_from_sums(ctx, st->pb, &st->work));
+    st->pending_sums = false;
+    if (done_h) {
+        IcpPairState s;
+        B3D_TRY(ctx->download(&s, st->work.state.p, sizeof(s)));
+        *done_h = s.done;
+    }
+    return B3D_OK;
+}
+
+int b3d_icp_finish(b3d_ctx* ctx, b3d_icp_state* st, b3d_icp_result* result_h, int32_t* corr) {
+    B3D_REQUIRE(ctx != nullptr && st != nullptr, "b3d_icp_finish: NULL argument");
+    B3D_TRY(ctx->bind());
+    int rc = B3D_OK;
+    if (corr && st->pb.src_off_h[1] > 0)
+        rc = cudaMemcpyAsync(corr, st->corr.p, (size_t)st->pb.src_off_h[1] * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream) == cudaSuccess
+                 ? B3D_OK
+                 : set_error(B3D_E_CUDA, "copy of the correspondence set failed");
+    if (rc == B3D_OK && result_h) rc = icp_results(ctx, st->pb, &st->work, result_h);
+    if (rc == B3D_OK) rc = ctx->sync();
+    delete st;
+    return rc;
+}
+
+}  // extern "C"

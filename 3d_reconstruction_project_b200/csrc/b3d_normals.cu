@@ -1,0 +1,531 @@
+// b3d_normals.cu -- K3: neighbourhood covariances + closed-form symmetric eigen-solve (normals), GICP covariances,
+// and the two outlier filters that share the same neighbour search.
+#include "b3d_common.cuh"
+#include "b3d_scan.cuh"
+#include "b3d_search.cuh"
+
+#include <cmath>
+
+namespace b3d {
+
+// ---- cell-size policy -------------------------------------------------------------------------------------------
+// radius searches: cell slightly above the radius (so that ring 1 always suffices); k-nearest searches: cells holding
+// about k/2 points each (surface model: occupancy ~ cell^2). One trial build measures the occupancy; at most two
+// rebuilds follow.
+template <typename T>
+int build_search_grid(b3d_ctx* ctx, const T* xyz, const Segments& seg, int k, double radius, Grid<T>* out, int* rmax_out) {
+    std::vector<double> bounds;
+    B3D_TRY(compute_bounds<T>(ctx, xyz, seg, &bounds));
+    const int64_t n = seg.total();
+    double ext[3] = {0, 0, 0};
+    for (int b = 0; b < seg.B; ++b) {
+        if (seg.off_h[b + 1] == seg.off_h[b]) continue;
+        for (int d = 0; d < 3; ++d) {
+            double e = bounds[(size_t)b * 6 + 3 + d] - bounds[(size_t)b * 6 + d];
+            if (!std::isfinite(e)) return set_error(B3D_E_INVALID, "non-finite coordinates in the cloud");
+            ext[d] = std::max(ext[d], e);
+        }
+    }
+    const double target = std::max(2.0, 0.5 * (double)std::max(k, 1));
+    double cell;
+    if (radius > 0) {
+        cell = radius * 1.001;
+    } else {
+        double area = std::max(std::max(ext[0] * ext[1], ext[1] * ext[2]), ext[0] * ext[2]);
+        double per_cloud = std::max<double>(1.0, (double)n / std::max(1, seg.B));
+        double spacing = std::sqrt(area / per_cloud);
+        cell = spacing * std::sqrt(target);
+        double longest = std::max(std::max(ext[0], ext[1]), ext[2]);
+        if (!(cell > 0)) cell = longest > 0 ? longest / 64.0 : 1.0;
+    }
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        B3D_TRY(grid_build<T>(ctx, xyz, seg, cell, &bounds, out));
+        const double occ = (double)n / (double)std::max<int64_t>(1, out->sort.n_runs);
+        if (attempt == 2) break;
+        if (radius > 0) {
+            // far too many candidates per cell for the k wanted: shrink towards the k-nearest scale
+            if (occ > 4.0 * target) {
+                double next = cell * std::sqrt(target / occ);
+                if (next < cell / 1.5) { cell = next; continue; }
+            }
+            break;
+        }
+        if (occ < 0.5 * target || occ > 2.5 * target) {
+            double f = std::sqrt(target / occ);
+            f = std::min(std::max(f, 0.125), 8.0);
+            // a cloud much smaller than k cannot reach the target occupancy: stop once one cell spans it
+            double longest = std::max(std::max(ext[0], ext[1]), ext[2]);
+            if (f > 1.0 && cell > longest && longest > 0) break;
+            cell *= f;
+            continue;
+        }
+        break;
+    }
+    if (rmax_out) *rmax_out = radius > 0 ? rings_for_radius(radius, cell) : kMaxRing;
+    return B3D_OK;
+}
+template int build_search_grid<float>(b3d_ctx*, const float*, const Segments&, int, double, Grid<float>*, int*);
+template int build_search_grid<double>(b3d_ctx*, const double*, const Segments&, int, double, Grid<double>*, int*);
+
+namespace {
+
+// ---- normals ------------------------------------------------------------------------------------------------------
+// One thread per point, walked in sorted (cell) order so that neighbouring threads touch the same cells.
+// LEGACY (T = double): raw-moment covariance in neighbour order, /n            
+// TENSOR (T = float) : two-pass centred covariance in double, /(n-1), eigen in float
+template <typename T, int KMAX, bool TENSOR>
+__global__ void __launch_bounds__(128) normals_kernel(GridView<T> g, const uint64_t* __restrict__ keys, const int32_t* __restrict__ off, int k,
+                                                      bool use_radius, T r2, int rmax, const T* __restrict__ prior, T* __restrict__ normals) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= g.n) return;
+    const typename PointT<T>::vec4 q = ld_point(g.pts + pos);
+    const int cloud = (int)(keys[pos] >> g.shift);
+    TopK<T, KMAX> tk;
+    knn_hybrid_query<T, KMAX>(g, off, cloud, q.x, q.y, q.z, k, use_radius, r2, rmax, tk);
+    const int c = tk.n;
+    Sym3<T> C{T(1), T(0), T(0), T(1), T(0), T(1)};
+    if (c >= 3) {
+        if (!TENSOR) {
+            double cu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int j = 0; j < c; ++j) {
+                const typename PointT<T>::vec4 p = ld_point(g.pts + tk.pos[j]);
+                const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
+                cu[0] += x; cu[1] += y; cu[2] += z;
+                cu[3] += x * x; cu[4] += x * y; cu[5] += x * z;
+                cu[6] += y * y; cu[7] += y * z; cu[8] += z * z;
+            }
+            const double cn = (double)c;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) cu[j] /= cn;
+            C.a00 = (T)(cu[3] - cu[0] * cu[0]);
+            C.a11 = (T)(cu[6] - cu[1] * cu[1]);
+            C.a22 = (T)(cu[8] - cu[2] * cu[2]);
+            C.a01 = (T)(cu[4] - cu[0] * cu[1]);
+            C.a02 = (T)(cu[5] - cu[0] * cu[2]);
+            C.a12 = (T)(cu[7] - cu[1] * cu[2]);
+        } else {
+            double ce[3] = {0, 0, 0};
+            for (int j = 0; j < c; ++j) {
+                const typename PointT<T>::vec4 p = ld_point(g.pts + tk.pos[j]);
+                ce[0] += (double)p.x; ce[1] += (double)p.y; ce[2] += (double)p.z;
+            }
+            ce[0] /= c; ce[1] /= c; ce[2] /= c;
+            double cu[6] = {0, 0, 0, 0, 0, 0};
+            for (int j = 0; j < c; ++j) {
+                const typename PointT<T>::vec4 p = ld_point(g.pts + tk.pos[j]);
+                const double x = (double)p.x - ce[0], y = (double)p.y - ce[1], z = (double)p.z - ce[2];
+                cu[0] += x * x; cu[1] += y * y; cu[2] += z * z; cu[3] += x * y; cu[4] += x * z; cu[5] += y * z;
+            }
+            const double nf = (double)(c - 1);
+            C.a00 = (T)(cu[0] / nf); C.a11 = (T)(cu[1] / nf); C.a22 = (T)(cu[2] / nf);
+            C.a01 = (T)(cu[3] / nf); C.a02 = (T)(cu[4] / nf); C.a12 = (T)(cu[5] / nf);
+        }
+    }
+    Vec3<T> nrm = sym3_smallest_eigvec<T>(C);
+    const int64_t oi = point_index(q);
+    if (!TENSOR) {
+        const T len = b3d_sqrt(nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z);
+        if (prior != nullptr) {
+            const T ox = prior[3 * oi], oy = prior[3 * oi + 1], oz = prior[3 * oi + 2];
+            if (len == T(0)) nrm = {ox, oy, oz};
+            else if (nrm.x * ox + nrm.y * oy + nrm.z * oz < T(0)) nrm = {-nrm.x, -nrm.y, -nrm.z};
+        } else if (len == T(0)) {
+            nrm = {T(0), T(0), T(1)};
+        }
+    } else {
+        if (nrm.x == T(0) && nrm.y == T(0) && nrm.z == T(0)) nrm = {T(0), T(0), T(1)};
+    }
+    normals[3 * oi] = nrm.x;
+    normals[3 * oi + 1] = nrm.y;
+    normals[3 * oi + 2] = nrm.z;
+}
+
+// ---- k nearest export (b3d_knn_hybrid): arbitrary queries against a grid -------------------------------------------
+template <typename T, int KMAX>
+__global__ void __launch_bounds__(128) knn_export_kernel(GridView<T> g, const int32_t* __restrict__ off, const T* __restrict__ queries, int64_t nq,
+                                                         int k, bool use_radius, T r2, int rmax, int32_t* __restrict__ idx, T* __restrict__ d2,
+                                                         int32_t* __restrict__ cnt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    TopK<T, KMAX> tk;
+    knn_hybrid_query<T, KMAX>(g, off, 0, queries[3 * i], queries[3 * i + 1], queries[3 * i + 2], k, use_radius, r2, rmax, tk);
+    for (int j = 0; j < k; ++j) {
+        idx[i * k + j] = j < tk.n ? point_index(ld_point(g.pts + tk.pos[j])) : -1;
+        if (d2 != nullptr) d2[i * k + j] = j < tk.n ? tk.d2[j] : T(0);
+    }
+    if (cnt != nullptr) cnt[i] = tk.n;
+}
+
+// ---- statistical outlier: mean distance to the nb nearest (self included) -------------------------------------------
+template <int KMAX>
+__global__ void __launch_bounds__(128) knn_mean_distance_kernel(GridView<double> g, const int32_t* __restrict__ off, int nb, int rmax,
+                                                                double* __restrict__ avg) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= g.n) return;
+    const double4 q = ld_point(g.pts + pos);
+    TopK<double, KMAX> tk;
+    knn_hybrid_query<double, KMAX>(g, off, 0, q.x, q.y, q.z, nb, false, 0.0, rmax, tk);
+    double mean = -1.0;
+    if (tk.n > 0) {
+        double s = 0;
+        for (int j = 0; j < tk.n; ++j) s += sqrt(tk.d2[j]);
+        mean = s / (double)tk.n;
+    }
+    avg[point_index(q)] = mean;
+}
+
+// deterministic two-stage reductions over avg[]: stage 1 -> per-block partial {sum, count}; stage 2 (one block)
+constexpr int kRedBlocks = 512;
+__global__ void __launch_bounds__(256) stat_sum_kernel(const double* __restrict__ avg, int64_t n, const double* __restrict__ mean_in,
+                                                       double* __restrict__ partial) {
+    // mean_in == NULL: sum of valid avg and their count; else: sum of squared deviations from *mean_in
+    const double mu = mean_in ? mean_in[0] : 0.0;
+    double s = 0, c = 0;
+    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * chunk, hi = min(n, lo + chunk);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const double a = avg[i];
+        if (a > 0) {
+            s += mean_in ? (a - mu) * (a - mu) : a;
+            c += 1.0;
+        }
+    }
+    __shared__ double sh[2][256];
+    sh[0][threadIdx.x] = s;
+    sh[1][threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = sh[0][0];
+        partial[2 * blockIdx.x + 1] = sh[1][0];
+    }
+}
+// stats: [0] mean, [1] valid count, [2] threshold
+__global__ void stat_final_kernel(const double* __restrict__ partial, int nblocks, int stage, double std_ratio, double* __restrict__ stats) {
+    if (threadIdx.x != 0) return;
+    double s = 0, c = 0;
+    for (int b = 0; b < nblocks; ++b) {
+        s += partial[2 * b];
+        c += partial[2 * b + 1];
+    }
+    if (stage == 0) {
+        stats[0] = c > 0 ? s / c : 0.0;
+        stats[1] = c;
+    } else {
+        const double sd = sqrt(s / (stats[1] - 1.0));
+        stats[2] = stats[0] + std_ratio * sd;
+    }
+}
+__global__ void __launch_bounds__(256) stat_keep_kernel(const double* __restrict__ avg, int64_t n, const double* __restrict__ stats,
+                                                        uint8_t* __restrict__ keep) {
+    const double thr = stats[2];
+    const bool any = stats[1] > 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = avg[i];
+        keep[i] = (any && a > 0 && a < thr) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(128) radius_count_kernel(GridView<double> g, double r2, int rmax, int nb_points, uint8_t* __restrict__ keep) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= g.n) return;
+    const double4 q = ld_point(g.pts + pos);
+    const int c = count_within_query<double>(g, 0, q.x, q.y, q.z, r2, rmax);
+    keep[point_index(q)] = c > nb_points ? 1 : 0;
+}
+
+struct KeepPred {
+    const uint8_t* keep;
+    __device__ __forceinline__ bool operator()(int64_t i) const { return keep[i] != 0; }
+};
+struct KeepEmit {
+    int64_t* out;
+    __device__ __forceinline__ void operator()(int64_t i, int64_t slot) const {
+        if (out != nullptr) out[slot] = i;
+    }
+};
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const double* __restrict__ src, const int64_t* __restrict__ idx, int64_t n, int cols,
+                                                          double* __restrict__ dst) {
+    const int64_t total = n * cols;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / cols;
+        const int c = (int)(t - r * cols);
+        dst[t] = src[idx[r] * cols + c];
+    }
+}
+
+// GICP: C = R diag(eps,1,1) R^T with R the rotation taking e1 onto the normal
+__global__ void __launch_bounds__(256) cov_from_normals_kernel(const double* __restrict__ normals, int64_t n, double eps, double* __restrict__ cov) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x0 = normals[3 * i], x1 = normals[3 * i + 1], x2 = normals[3 * i + 2];
+        double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        const double c = x0;
+        if (!(c < -0.99)) {
+            const double v[3] = {0.0, -x2, x1};
+            const double sv[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
+            const double f = 1.0 / (1.0 + c);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+                    double s2 = 0;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) s2 += sv[3 * r + k] * sv[3 * k + cc];
+                    R[3 * r + cc] = (r == cc ? 1.0 : 0.0) + sv[3 * r + cc] + s2 * f;
+                }
+        }
+        const double D[3] = {eps, 1.0, 1.0};
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) {
+                double s = 0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) s += R[3 * r + k] * D[k] * R[3 * cc + k];
+                cov[9 * i + 3 * r + cc] = s;
+            }
+    }
+}
+
+}  // namespace
+
+// normals for a batch of clouds (written by ORIGINAL point index). radius <= 0: pure k nearest.
+template <typename T, bool TENSOR>
+int estimate_normals_batch(b3d_ctx* ctx, const T* xyz, const Segments& seg, int max_nn, double radius, const T* prior, T* normals,
+                           Grid<T>* reuse_grid, int reuse_rmax) {
+    B3D_REQUIRE(max_nn >= 1 && max_nn <= 64, "max_nn must be in [1, 64] (got %d)", max_nn);
+    Grid<T> local;
+    Grid<T>* grid = reuse_grid;
+    int rmax = reuse_rmax;
+    if (!grid) {
+        grid = &local;
+        B3D_TRY(build_search_grid<T>(ctx, xyz, seg, max_nn, radius, grid, &rmax));
+    }
+    const bool use_radius = radius > 0;
+    const T r = (T)radius;
+    const T r2 = r * r;
+    const int n = (int)grid->sort.n;
+    const int blocks = (n + 127) / 128;
+    if (max_nn <= 32) {
+        B3D_LAUNCH(ctx, (normals_kernel<T, 32, TENSOR>), blocks, 128, 0, grid->view(), grid->sort.keys.p, seg.off, max_nn, use_radius, r2, rmax, prior,
+                   normals);
+    } else {
+        B3D_LAUNCH(ctx, (normals_kernel<T, 64, TENSOR>), blocks, 128, 0, grid->view(), grid->sort.keys.p, seg.off, max_nn, use_radius, r2, rmax, prior,
+                   normals);
+    }
+    return B3D_OK;
+}
+template int estimate_normals_batch<double, false>(b3d_ctx*, const double*, const Segments&, int, double, const double*, double*, Grid<double>*, int);
+template int estimate_normals_batch<float, false>(b3d_ctx*, const float*, const Segments&, int, double, const float*, float*, Grid<float>*, int);
+template int estimate_normals_batch<float, true>(b3d_ctx*, const float*, const Segments&, int, double, const float*, float*, Grid<float>*, int);
+
+}  // namespace b3d
+
+using namespace b3d;
+
+struct b3d_grid {
+    int is_f64 = 1;
+    Grid<double> gd;
+    Grid<float> gf;
+    DevBuf<int32_t> off;
+    Segments seg;
+    int rmax_hint = kMaxRing;
+    double radius_hint = 0;
+};
+
+extern "C" {
+
+int b3d_estimate_normals_legacy(b3d_ctx* ctx, const double* xyz, int64_t n, int max_nn, double radius, const double* prior, double* normals) {
+    B3D_REQUIRE(ctx != nullptr, "ctx is NULL");
+    B3D_REQUIRE(n >= 0, "negative point count");
+    if (n == 0) return B3D_OK;
+    B3D_REQUIRE(xyz && normals, "b3d_estimate_normals_legacy: NULL buffer");
+    B3D_TRY(ctx->bind());
+    DevBuf<int32_t> off;
+    Segments seg;
+    B3D_TRY(single_segment(ctx, n, &off, &seg));
+    return estimate_normals_batch<double, false>(ctx, xyz, seg, max_nn, radius, prior, normals, nullptr, 0);
+}
+
+int b3d_estimate_normals_tensor(b3d_ctx* ctx, const float* xyz, int64_t n, int max_nn, float radius, float* normals) {
+    B3D_REQUIRE(ctx != nullptr, "ctx is NULL");
+    B3D_REQUIRE(n >= 0, "negative point count");
+    if (n == 0) return B3D_OK;
+    B3D_REQUIRE(xyz && normals, "b3d_estimate_normals_tensor: NULL buffer");
+    B3D_TRY(ctx->bind());
+    DevBuf<int32_t> off;
+    Segments seg;
+    B3D_TRY(single_segment(ctx, n, &off, &seg));
+    return estimate_normals_batch<float, true>(ctx, xyz, seg, max_nn, (double)radius, nullptr, normals, nullptr, 0);
+}
+
+int b3d_covariances_from_normals(b3d_ctx* ctx, const double* normals, int64_t n, double eps, double* cov) {
+    B3D_REQUIRE(ctx != nullptr, "ctx is NULL");
+    B3D_REQUIRE(n >= 0, "negative point count");
+    if (n == 0) return B3D_OK;
+    B3D_REQUIRE(normals && cov, "b3d_covariances_from_normals: NULL buffer");
+    B3D_TRY(ctx->bind());
+    B3D_LAUNCH(ctx, cov_from_normals_kernel, ctx->grid_for(n, 256, 1, 8), 256, 0, normals, n, eps, cov);
+    return B3D_OK;
+}
+
+static int finish_keep(b3d_ctx* ctx, const uint8_t* keep, int64_t n, int64_t* kept_idx, int64_t* n_kept_h) {
+    DevBuf<int64_t> total;
+    B3D_TRY(total.alloc(ctx, 1));
+    B3D_TRY(compact(ctx, KeepPred{keep}, KeepEmit{kept_idx}, n, total.p));
+    return ctx->download(n_kept_h, total.p, sizeof(int64_t));
+}
+
+int b3d_statistical_outlier(b3d_ctx* ctx, const double* xyz, int64_t n, int nb_neighbors, double std_ratio, uint8_t* keep, int64_t* kept_idx,
+                            int64_t* n_kept_h) {
+    B3D_REQUIRE(ctx != nullptr, "ctx is NULL");
+    B3D_REQUIRE(n_kept_h != nullptr, "n_kept_h is NULL");
+    *n_kept_h = 0;
+    B3D_REQUIRE(nb_neighbors >= 1 && std_ratio > 0.0,
+                "Illegal input parameters, the number of neighbors and standard deviation ratio must be positive.");
+    B3D_REQUIRE(nb_neighbors <= 64, "nb_neighbors must be <= 64 (got %d)", nb_neighbors);
+    B3D_REQUIRE(n >= 0, "negative point count");
+    if (n == 0) return B3D_OK;
+    B3D_REQUIRE(xyz && keep, "b3d_statistical_outlier: NULL buffer");
+    B3D_TRY(ctx->bind());
+    DevBuf<int32_t> off;
+    Segments seg;
+    B3D_TRY(single_segment(ctx, n, &off, &seg));
+    Grid<double> grid;
+    int rmax = kMaxRing;
+    B3D_TRY(build_search_grid<double>(ctx, xyz, seg, nb_neighbors, 0.0, &grid, &rmax));
+    DevBuf<double> avg, partial, stats;
+    B3D_TRY(avg.alloc(ctx, n));
+    B3D_TRY(partial.alloc(ctx, 2 * kRedBlocks));
+    B3D_TRY(stats.alloc(ctx, 4));
+    const int blocks = (int)((n + 127) / 128);
+    if (nb_neighbors <= 32) {
+        B3D_LAUNCH(ctx, knn_mean_distance_kernel<32>, blocks, 128, 0, grid.view(), seg.off, nb_neighbors, rmax, avg.p);
+    } else {
+        B3D_LAUNCH(ctx, knn_mean_distance_kernel<64>, blocks, 128, 0, grid.view(), seg.off, nb_neighbors, rmax, avg.p);
+    }
+    B3D_LAUNCH(ctx, stat_sum_kernel, kRedBlocks, 256, 0, avg.p, n, (const double*)nullptr, partial.p);
+    B3D_LAUNCH(ctx, stat_final_kernel, 1, 32, 0, partial.p, kRedBlocks, 0, std_ratio, stats.p);
+    B3D_LAUNCH(ctx, stat_sum_kernel, kRedBlocks, 256, 0, avg.p, n, (const double*)stats.p, partial.p);
+    B3D_LAUNCH(ctx, stat_final_kernel, 1, 32, 0, partial.p, kRedBlocks, 1, std_ratio, stats.p);
+    B3D_LAUNCH(ctx, stat_keep_kernel, ctx->grid_for(n, 256, 1, 8), 256, 0, avg.p, n, stats.p, keep);
+    return finish_keep(ctx, keep, n, kept_idx, n_kept_h);
+}
+
+int b3d_radius_outlier(b3d_ctx* ctx, const double* xyz, int64_t n, int nb_points, double radius, uint8_t* keep, int64_t* kept_idx,
+                       int64_t* n_kept_h) {
+    B3D_REQUIRE(ctx != nullptr, "ctx is NULL");
+    B3D_REQUIRE(n_kept_h != nullptr, "n_kept_h is NULL");
+    *n_kept_h = 0;
+    B3D_REQUIRE(nb_points >= 1 && radius > 0.0, "Illegal input parameters, number of points and radius must be positive.");
+    B3D_REQUIRE(n >= 0, "negative point count");
+    if (n == 0) return B3D_OK;
+    B3D_REQUIRE(xyz && keep, "b3d_radius_outlier: NULL buffer");
+    B3D_TRY(ctx->bind());
+    DevBuf<int32_t> off;
+    Segments seg;
+    B3D_TRY(single_segment(ctx, n, &off, &seg));
+    Grid<double> grid;
+    const double cell = radius * 1.001;
+    B3D_TRY(grid_build<double>(ctx, xyz, seg, cell, nullptr, &grid));
+    const int rmax = rings_for_radius(radius, cell);
+    B3D_LAUNCH(ctx, radius_count_kernel, (int)((n + 127) / 128), 128, 0, grid.view(), radius * radius, rmax, nb_points, keep);
+    return finish_keep(ctx, keep, n, kept_idx, n_kept_h);
+}
+
+int b3d_gather_rows_f64(b3d_ctx* ctx, const double* src, const int64_t* kept_idx, int64_t n_kept, int cols, double* dst) {
+    B3D_REQUIRE(ctx != nullptr, "ctx is NULL");
+    B3D_REQUIRE(n_kept >= 0 && cols >= 1, "b3d_gather_rows_f64: bad sizes");
+    if (n_kept == 0) return B3D_OK;
+    B3D_REQUIRE(src && kept_idx && dst, "b3d_gather_rows_f64: NULL buffer");
+    B3D_TRY(ctx->bind());
+    B3D_LAUNCH(ctx, gather_rows_kernel, ctx->grid_for(n_kept * cols, 256, 1, 8), 256, 0, src, kept_idx, n_kept, cols, dst);
+    return B3D_OK;
+}
+
+// ---- explicit grid objects (b3d_grid_build / b3d_knn_hybrid) ---------------------------------------------------------
+int b3d_grid_build(b3d_ctx* ctx, const void* xyz, int64_t n, int is_f64, double cell_size, int k_hint, double radius_hint, b3d_grid** out) {
+    B3D_REQUIRE(ctx != nullptr && out != nullptr, "b3d_grid_build: NULL argument");
+    *out = nullptr;
+    B3D_REQUIRE(n > 0, "b3d_grid_build: empty cloud");
+    B3D_REQUIRE(xyz != nullptr, "b3d_grid_build: NULL buffer");
+    B3D_TRY(ctx->bind());
+    b3d_grid* g = new b3d_grid();
+    g->is_f64 = is_f64 ? 1 : 0;
+    g->radius_hint = radius_hint;
+    int rc = single_segment(ctx, n, &g->off, &g->seg);
+    if (rc == B3D_OK) {
+        if (cell_size > 0) {
+            rc = is_f64 ? grid_build<double>(ctx, (const double*)xyz, g->seg, cell_size, nullptr, &g->gd)
+                        : grid_build<float>(ctx, (const float*)xyz, g->seg, cell_size, nullptr, &g->gf);
+        } else {
+            rc = is_f64 ? build_search_grid<double>(ctx, (const double*)xyz, g->seg, k_hint, radius_hint, &g->gd, &g->rmax_hint)
+                        : build_search_grid<float>(ctx, (const float*)xyz, g->seg, k_hint, radius_hint, &g->gf, &g->rmax_hint);
+        }
+    }
+    if (rc != B3D_OK) {
+        delete g;
+        return rc;
+    }
+    *out = g;
+    return B3D_OK;
+}
+
+int b3d_grid_destroy(b3d_ctx* ctx, b3d_grid* grid) {
+    if (!grid) return B3D_OK;
+    if (ctx) ctx->bind();
+    delete grid;
+    return B3D_OK;
+}
+
+int b3d_grid_info(b3d_grid* grid, int64_t* n_h, int64_t* n_cells_h, double* cell_size_h) {
+    B3D_REQUIRE(grid != nullptr, "grid is NULL");
+    const SpatialSort& s = grid->is_f64 ? grid->gd.sort : grid->gf.sort;
+    if (n_h) *n_h = s.n;
+    if (n_cells_h) *n_cells_h = s.n_runs;
+    if (cell_size_h) *cell_size_h = grid->is_f64 ? grid->gd.cell : grid->gf.cell;
+    return B3D_OK;
+}
+
+int b3d_knn_hybrid(b3d_ctx* ctx, b3d_grid* grid, const void* queries, int64_t nq, int k, double radius, int32_t* idx, void* d2, int32_t* cnt) {
+    B3D_REQUIRE(ctx != nullptr && grid != nullptr, "b3d_knn_hybrid: NULL argument");
+    B3D_REQUIRE(k >= 1 && k <= 64, "k must be in [1, 64] (got %d)", k);
+    B3D_REQUIRE(nq >= 0, "negative query count");
+    if (nq == 0) return B3D_OK;
+    B3D_REQUIRE(queries && idx, "b3d_knn_hybrid: NULL buffer");
+    B3D_TRY(ctx->bind());
+    const bool use_radius = radius > 0;
+    const int blocks = (int)((nq + 127) / 128);
+    if (grid->is_f64) {
+        const int rmax = use_radius ? rings_for_radius(radius, grid->gd.cell) : kMaxRing;
+        const double r2 = radius * radius;
+        if (k <= 32) {
+            B3D_LAUNCH(ctx, (knn_export_kernel<double, 32>), blocks, 128, 0, grid->gd.view(), grid->seg.off, (const double*)queries, nq, k, use_radius, r2,
+                       rmax, idx, (double*)d2, cnt);
+        } else {
+            B3D_LAUNCH(ctx, (knn_export_kernel<double, 64>), blocks, 128, 0, grid->gd.view(), grid->seg.off, (const double*)queries, nq, k, use_radius, r2,
+                       rmax, idx, (double*)d2, cnt);
+        }
+    } else {
+        const int rmax = use_radius ? rings_for_radius(radius, grid->gf.cell) : kMaxRing;
+        const float r = (float)radius;
+        const float r2 = r * r;
+        if (k <= 32) {
+            B3D_LAUNCH(ctx, (knn_export_kernel<float, 32>), blocks, 128, 0, grid->gf.view(), grid->seg.off, (const float*)queries, nq, k, use_radius, r2,
+                       rmax, idx, (float*)d2, cnt);
+        } else {
+            B3D_LAUNCH(ctx, (knn_export_kernel<float, 64>), blocks, 128, 0, grid->gf.view(), grid->seg.off, (const float*)queries, nq, k, use_radius, r2,
+                       rmax, idx, (float*)d2, cnt);
+        }
+    }
+    return B3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,163 @@
+// b3d_pipeline.cu -- the whole front end + registration path for a BATCH of depth frame pairs, device resident:
+//   deproject (rs.pointcloud semantics, pointcloud_capture.py:35-38) -> tensor voxel_down_sample (:50) -> to_legacy (f64, :53)
+//   -> legacy hybrid normals on the targets (pointcloud_alignment.py:27-28) [+ sources and GICP covariances for kind 2]
+//   -> registration_icp / registration_generalized_icp (pointcloud_alignment.py:35-39, test/mini1.py:293-296, test/GICP1.py:99-102)
+// All 2P frames of the batch share every launch: one deprojection, one radix sort (cloud id in the key's top bits),
+// one hash grid, one normals launch, and P-wide ICP passes (grid.y = pair). Host synchronisations per batch: a handful
+// (bounds -> lattice, run count -> sizes, final results), independent of P.
+#include "b3d_common.cuh"
+#include "b3d_icp.cuh"
+#include "b3d_search.cuh"
+
+namespace b3d {
+
+int deproject_z16_batch(b3d_ctx* ctx, const uint16_t* depth, const uint8_t* bgr, int w, int h, int frames, float fx, float fy, float ppx,
+                        float ppy, float scale, float* xyz, float* rgb);
+template <typename T, typename IndexT>
+int voxel_downsample_batch(b3d_ctx* ctx, const T* xyz, const T* a0, const T* a1, const Segments& seg, double voxel, int flavour, T* o_xyz,
+                           T* o_a0, T* o_a1, IndexT* o_index, int32_t* o_count, SpatialSort* out_sort, const std::vector<double>* bounds_in);
+template <typename T, bool TENSOR>
+int estimate_normals_batch(b3d_ctx* ctx, const T* xyz, const Segments& seg, int max_nn, double radius, const T* prior, T* normals,
+                           Grid<T>* reuse_grid, int reuse_rmax);
+
+namespace {
+__global__ void __launch_bounds__(256) widen_kernel(const float* __restrict__ in, int64_t n, double* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
+}
+}  // namespace
+
+}  // namespace b3d
+
+using namespace b3d;
+
+extern "C" {
+
+int b3d_register_depth_pairs(b3d_ctx* ctx, const b3d_pair_params* pr, const uint16_t* depth_src, const uint16_t* depth_tgt, int n_pairs,
+                             int device_inputs, b3d_pair_result* results_h) {
+    B3D_REQUIRE(ctx != nullptr && pr != nullptr && results_h != nullptr, "b3d_register_depth_pairs: NULL argument");
+    B3D_REQUIRE(n_pairs >= 1, "b3d_register_depth_pairs: n_pairs must be >= 1");
+    B3D_REQUIRE(pr->w > 0 && pr->h > 0, "b3d_register_depth_pairs: empty image");
+    B3D_REQUIRE(depth_src && depth_tgt, "b3d_register_depth_pairs: NULL depth buffer");
+    B3D_REQUIRE(pr->voxel_size > 0.0f, "voxel_size must be positive.");
+    B3D_REQUIRE(pr->icp_max_dist > 0.0, "Invalid max_correspondence_distance.");
+    B3D_REQUIRE(pr->icp_kind >= 0 && pr->icp_kind <= 2, "unknown ICP kind %d", pr->icp_kind);
+    B3D_REQUIRE(pr->normals_max_nn >= 1 && pr->normals_max_nn <= 64, "normals_max_nn must be in [1, 64]");
+    B3D_REQUIRE(pr->icp_max_iter >= 0, "negative icp_max_iter");
+    B3D_REQUIRE(pr->fx != 0.0f && pr->fy != 0.0f, "zero focal length");
+    B3D_TRY(ctx->bind());
+    const int P = n_pairs, F = 2 * P;
+    const int64_t N = (int64_t)pr->w * pr->h;
+    B3D_REQUIRE(N * F < (int64_t)INT32_MAX, "batch of %d frames x %lld pixels exceeds 2^31-1 points", F, (long long)N);
+
+    // 1. depth rasters -> device (e2e leg) -> float32 points, sources first then targets
+    DevBuf<uint16_t> depth_d;
+    const uint16_t* d_src = depth_src;
+    const uint16_t* d_tgt = depth_tgt;
+    if (!device_inputs) {
+        B3D_TRY(depth_d.alloc(ctx, (size_t)(N * F)));
+        B3D_CUDA(cudaMemcpyAsync(depth_d.p, depth_src, (size_t)(N * P) * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+        B3D_CUDA(cudaMemcpyAsync(depth_d.p + N * P, depth_tgt, (size_t)(N * P) * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+        d_src = depth_d.p;
+        d_tgt = depth_d.p + N * P;
+    }
+    DevBuf<float> xyz;
+    B3D_TRY(xyz.alloc(ctx, (size_t)(3 * N * F)));
+    B3D_TRY(deproject_z16_batch(ctx, d_src, nullptr, pr->w, pr->h, P, pr->fx, pr->fy, pr->ppx, pr->ppy, pr->depth_scale, xyz.p, nullptr));
+    B3D_TRY(deproject_z16_batch(ctx, d_tgt, nullptr, pr->w, pr->h, P, pr->fx, pr->fy, pr->ppx, pr->ppy, pr->depth_scale, xyz.p + 3 * N * P, nullptr));
+
+    // 2. tensor voxel down-sampling of all 2P frames in one sort
+    std::vector<int32_t> raw_off(F + 1);
+    for (int f = 0; f <= F; ++f) raw_off[f] = (int32_t)(f * N);
+    DevBuf<int32_t> raw_off_d;
+    Segments raw_seg;
+    B3D_TRY(upload_segments(ctx, raw_off, &raw_off_d, &raw_seg));
+    DevBuf<float> vox;
+    B3D_TRY(vox.alloc(ctx, (size_t)(3 * N * F)));
+    SpatialSort vs;
+    B3D_TRY((voxel_downsample_batch<float, int64_t>(ctx, xyz.p, nullptr, nullptr, raw_seg, (double)pr->voxel_size, kLatTensorVoxel, vox.p, nullptr,
+                                                     nullptr, nullptr, nullptr, &vs, nullptr)));
+    xyz.release();
+    const int64_t M = vs.n_runs;
+    const std::vector<int32_t>& voff = vs.run_off_h;  // [F+1] offsets of the down-sampled clouds
+    const int32_t Ms = voff[P], Mt = (int32_t)M - voff[P];
+
+    // 3. to_legacy: float32 -> float64 (exact)
+    DevBuf<double> vox64;
+    B3D_TRY(vox64.alloc(ctx, (size_t)(3 * M)));
+    B3D_LAUNCH(ctx, widen_kernel, ctx->grid_for(3 * M, 256, 1, 8), 256, 0, vox.p, 3 * M, vox64.p);
+    vox.release();
+    const double* src_pts = vox64.p;
+    const double* tgt_pts = vox64.p + 3 * (int64_t)voff[P];
+    std::vector<int32_t> soff(P + 1), toff(P + 1);
+    for (int p = 0; p <= P; ++p) {
+        soff[p] = voff[p];
+        toff[p] = voff[P + p] - voff[P];
+    }
+    DevBuf<int32_t> soff_d, toff_d;
+    Segments sseg, tseg;
+    B3D_TRY(upload_segments(ctx, soff, &soff_d, &sseg));
+    B3D_TRY(upload_segments(ctx, toff, &toff_d, &tseg));
+
+    // 4. target grid (shared by the normals and by the ICP correspondence search when the ring count allows)
+    Grid<double> tgrid;
+    int n_rmax = 1;
+    B3D_TRY(build_search_grid<double>(ctx, tgt_pts, tseg, pr->normals_max_nn, pr->normals_radius, &tgrid, &n_rmax));
+    DevBuf<double> tnrm;
+    B3D_TRY(tnrm.alloc(ctx, (size_t)(3 * (int64_t)Mt)));
+    B3D_TRY((estimate_normals_batch<double, false>(ctx, tgt_pts, tseg, pr->normals_max_nn, pr->normals_radius, nullptr, tnrm.p, &tgrid, n_rmax)));
+    Grid<double> icp_grid_own;
+    const Grid<double>* icp_grid = &tgrid;
+    int icp_rmax = rings_for_radius(pr->icp_max_dist, tgrid.cell);
+    if (icp_rmax > 3) {
+        B3D_TRY(build_search_grid<double>(ctx, tgt_pts, tseg, 8, pr->icp_max_dist, &icp_grid_own, &icp_rmax));
+        icp_grid = &icp_grid_own;
+    }
+
+    // 5. generalized ICP needs covariances on both sides (from normals, eps = 1e-3)
+    DevBuf<double> snrm, scov, tcov;
+    if (pr->icp_kind == B3D_ICP_GENERALIZED) {
+        B3D_TRY(snrm.alloc(ctx, (size_t)(3 * (int64_t)Ms)));
+        if (Ms > 0) B3D_TRY((estimate_normals_batch<double, false>(ctx, src_pts, sseg, pr->normals_max_nn, pr->normals_radius, nullptr, snrm.p, nullptr, 0)));
+        B3D_TRY(scov.alloc(ctx, (size_t)(9 * (int64_t)Ms)));
+        B3D_TRY(tcov.alloc(ctx, (size_t)(9 * (int64_t)Mt)));
+        B3D_TRY(b3d_covariances_from_normals(ctx, snrm.p, Ms, 1e-3, scov.p));
+        B3D_TRY(b3d_covariances_from_normals(ctx, tnrm.p, Mt, 1e-3, tcov.p));
+    }
+
+    // 6. batched ICP
+    IcpProblem pb;
+    pb.kind = pr->icp_kind;
+    pb.P = P;
+    pb.src = src_pts;
+    pb.src_cov = scov.p;
+    pb.src_off = soff_d.p;
+    pb.src_off_h = soff;
+    pb.tgt_grid = icp_grid;
+    pb.tgt_off = toff_d.p;
+    pb.tgt_normals = tnrm.p;
+    pb.tgt_cov = tcov.p;
+    pb.max_dist = pr->icp_max_dist;
+    pb.rmax = icp_rmax;
+    pb.rel_fitness = pr->icp_rel_fitness;
+    pb.rel_rmse = pr->icp_rel_rmse;
+    pb.max_iter = pr->icp_max_iter;
+    IcpWork work;
+    B3D_TRY(icp_prepare(ctx, pb, nullptr, &work));
+    B3D_TRY(icp_run(ctx, pb, &work, nullptr));
+    std::vector<b3d_icp_result> res(P);
+    B3D_TRY(icp_results(ctx, pb, &work, res.data()));
+    for (int p = 0; p < P; ++p) {
+        results_h[p].icp = res[p];
+        results_h[p].n_raw = 2 * N;
+        results_h[p].m_source = soff[p + 1] - soff[p];
+        results_h[p].m_target = toff[p + 1] - toff[p];
+    }
+    return B3D_OK;
+}
+
+int b3d_register_depth_pair(b3d_ctx* ctx, const b3d_pair_params* params, const uint16_t* depth_src, const uint16_t* depth_tgt, int device_inputs,
+                            b3d_pair_result* result_h) {
+    return b3d_register_depth_pairs(ctx, params, depth_src, depth_tgt, 1, device_inputs, result_h);
+}
+
+}  // extern "C"

@@ -1,0 +1,97 @@
+"""o3d.pipelines.registration as used on the reference's path: registration_icp with the point-to-point
+(pointcloud_alignment.py:35-39) and point-to-plane (test/mini1.py:293-296, check2.py:151-154) estimators, and
+registration_generalized_icp (test/GICP1.py:99-102). The whole ICP loop runs on the device (b3d_icp)."""
+import numpy as np
+
+from . import _native as N
+from . import ops
+from .geometry import as_cloud
+
+
+class ICPConvergenceCriteria:
+    def __init__(self, relative_fitness=1e-6, relative_rmse=1e-6, max_iteration=30):
+        self.relative_fitness, self.relative_rmse, self.max_iteration = float(relative_fitness), float(relative_rmse), int(max_iteration)
+
+
+class TransformationEstimationPointToPoint:
+    kind = N.ICP_POINT_TO_POINT
+
+    def __init__(self, with_scaling=False):
+        if with_scaling:
+            raise RuntimeError("with_scaling=True is not on the reference's path and is not implemented")
+
+
+class TransformationEstimationPointToPlane:
+    kind = N.ICP_POINT_TO_PLANE
+
+
+class TransformationEstimationForGeneralizedICP:
+    kind = N.ICP_GENERALIZED
+
+    def __init__(self, epsilon=1e-3):
+        self.epsilon = float(epsilon)
+
+
+class RegistrationResult:
+    def __init__(self, d):
+        self.transformation = d["transformation"]
+        self.fitness = d["fitness"]
+        self.inlier_rmse = d["inlier_rmse"]
+        self.iterations = d["iterations"]
+        self.converged = d["converged"]
+        corr = d.get("corr")
+        if corr is None:
+            self.correspondence_set = np.zeros((0, 2), np.int32)
+        else:
+            src = np.nonzero(corr >= 0)[0].astype(np.int32)
+            self.correspondence_set = np.stack([src, corr[src]], axis=1)
+
+    def __repr__(self):
+        return (f"RegistrationResult with fitness={self.fitness:e}, inlier_rmse={self.inlier_rmse:e}, and correspondence_set size of "
+                f"{len(self.correspondence_set)}\nAccess transformation to get result.")
+
+
+def _run(source, target, max_correspondence_distance, init, estimation, criteria):
+    source, target = as_cloud(source), as_cloud(target)
+    if max_correspondence_distance <= 0:
+        raise RuntimeError("Invalid max_correspondence_distance.")
+    criteria = criteria or ICPConvergenceCriteria()
+    init = np.eye(4) if init is None else np.asarray(init, dtype=np.float64).reshape(4, 4)
+    kind = estimation.kind
+    kw = {}
+    if kind == N.ICP_POINT_TO_PLANE:
+        if not target.has_normals():
+            raise RuntimeError("TransformationEstimationPointToPlane and TransformationEstimationColoredICP require pre-computed normal vectors "
+                               "for target PointCloud.")
+        kw["tgt_normals"] = np.asarray(target.normals)
+    if kind == N.ICP_GENERALIZED:
+        eps = estimation.epsilon
+        for c in (source, target):
+            if not c.has_covariances():
+                c.estimate_covariances_from_normals(eps)
+        kw["src_cov"] = source.covariances.reshape(-1, 9)
+        kw["tgt_cov"] = target.covariances.reshape(-1, 9)
+    if not source.has_points() or not target.has_points():
+        return RegistrationResult(dict(transformation=init.copy(), fitness=0.0, inlier_rmse=0.0, iterations=0, converged=False, corr=None))
+    d = ops.icp(kind, np.asarray(source.points), np.asarray(target.points), max_correspondence_distance, init=init,
+                rel_fitness=criteria.relative_fitness, rel_rmse=criteria.relative_rmse, max_iter=criteria.max_iteration, device=source.device, **kw)
+    return RegistrationResult(d)
+
+
+def registration_icp(source, target, max_correspondence_distance, init=None, estimation_method=None, criteria=None):
+    return _run(source, target, max_correspondence_distance, init, estimation_method or TransformationEstimationPointToPoint(), criteria)
+
+
+def registration_generalized_icp(source, target, max_correspondence_distance, init=None, estimation_method=None, criteria=None):
+    return _run(source, target, max_correspondence_distance, init, estimation_method or TransformationEstimationForGeneralizedICP(), criteria)
+
+
+def evaluate_registration(source, target, max_correspondence_distance, transformation=None):
+    source, target = as_cloud(source), as_cloud(target)
+    T = np.eye(4) if transformation is None else np.asarray(transformation, dtype=np.float64)
+    ns = len(source.points)
+    if ns == 0 or len(target.points) == 0:
+        return RegistrationResult(dict(transformation=T, fitness=0.0, inlier_rmse=0.0, iterations=0, converged=False, corr=None))
+    corr, n, s = ops.correspondences(np.asarray(source.points), np.asarray(target.points), T, max_correspondence_distance, device=source.device)
+    return RegistrationResult(dict(transformation=T, fitness=(n / ns if n else 0.0), inlier_rmse=(np.sqrt(s / n) if n else 0.0), iterations=0,
+                                   converged=False, corr=corr))

@@ -1,0 +1,367 @@
+"""GPU parity tests: every entry point of the C ABI (through the ctypes binding) against the CPU oracle on the same
+seeded inputs, and against the reference's own golden fixtures. Bar: bit-exact for integer / index / ordered-sum work,
+stated tolerances for floating-point solves (transform 1e-5 rad / 1e-5 m, rmse / fitness 1e-4, normals 1e-9 bulk)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from util import DEPTH_SCALE, GOLDEN, INTR, golden_cloud, lexorder, rot_err, small_rigid, surface_cloud
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import b200recon
+    from b200recon import ops as _ops
+    return _ops
+
+
+# ---- K1 ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(480, 640), (480, 848), (5, 7), (1, 1), (3, 4)])
+def test_deproject_z16_bit_exact(ops, shape):
+    rng = np.random.default_rng(1)
+    depth = rng.integers(0, 65536, size=shape, dtype=np.uint16)
+    depth[rng.random(shape) < 0.1] = 0
+    color = rng.integers(0, 256, size=shape + (3,), dtype=np.uint8)
+    args = (616.6349, 616.3090, 312.5787, 242.2195, 0.001)
+    ref = oracle.deproject_z16(depth, *args)
+    out = ops.deproject_z16(depth, *args)
+    assert out.dtype == np.float32 and np.array_equal(out, ref)
+    out2, rgb = ops.deproject_z16(depth, *args, color_bgr=color)
+    assert np.array_equal(out2, ref)
+    assert np.array_equal(rgb, (color.reshape(-1, 3) / 255.0).astype(np.float32))
+
+
+def test_deproject_z16_all_zero_and_max(ops):
+    for v in (0, 65535):
+        depth = np.full((8, 12), v, np.uint16)
+        assert np.array_equal(ops.deproject_z16(depth, 424.0, 424.0, 424.0, 240.0, 0.001), oracle.deproject_z16(depth, 424.0, 424.0, 424.0, 240.0, 0.001))
+
+
+@pytest.mark.parametrize("name", ["output84_00008", "output_00008"])
+def test_deproject_rgbd_golden_inputs(ops, name):
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    color = d["color_rgb"]
+    rx, rc = oracle.deproject_rgbd(d["depth"], color, INTR["fx"], INTR["fy"], INTR["ppx"], INTR["ppy"], depth_scale=DEPTH_SCALE)
+    gx, gc = ops.deproject_rgbd(d["depth"], color, INTR["fx"], INTR["fy"], INTR["ppx"], INTR["ppy"], depth_scale=DEPTH_SCALE)
+    assert gx.shape == rx.shape and np.array_equal(gx, rx) and np.array_equal(gc, rc)
+
+
+def test_deproject_rgbd_edge_cases(ops):
+    rng = np.random.default_rng(3)
+    depth = rng.integers(0, 5000, size=(37, 53), dtype=np.uint16)
+    for flip in (True, False):
+        rx, _ = oracle.deproject_rgbd(depth, None, 500.0, 510.0, 26.0, 18.0, 1000.0, 3.0, flip)
+        gx, gc = ops.deproject_rgbd(depth, None, 500.0, 510.0, 26.0, 18.0, 1000.0, 3.0, flip)
+        assert gc is None and np.array_equal(gx, rx)
+    empty = np.zeros((16, 16), np.uint16)
+    gx, _ = ops.deproject_rgbd(empty, None, 500.0, 500.0, 8.0, 8.0)
+    assert gx.shape == (0, 3)
+    # a raster larger than one scan tile, all valid
+    big = np.full((300, 300), 1234, np.uint16)
+    rx, _ = oracle.deproject_rgbd(big, None, 500.0, 500.0, 150.0, 150.0)
+    gx, _ = ops.deproject_rgbd(big, None, 500.0, 500.0, 150.0, 150.0)
+    assert np.array_equal(gx, rx)
+
+
+def test_reproject_disparity_golden(ops):
+    d = np.load(os.path.join(GOLDEN, "disparity_cv2.npz"))
+    out = ops.reproject_disparity(d["disp16"], d["Q"])
+    fin = np.isfinite(d["xyz"])
+    assert np.array_equal(np.isfinite(out), fin) and np.array_equal(out[fin], d["xyz"][fin])
+    rng = np.random.default_rng(2000)
+    disp = rng.integers(16, 2048, size=(245, 326), dtype=np.int16)
+    disp[rng.random(disp.shape) < 0.03] = -16
+    ref = oracle.reproject_disparity(disp, d["Q"])
+    out = ops.reproject_disparity(disp, d["Q"])
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+# ---- K2 ---------------------------------------------------------------------------------------------------------
+def _cmp_voxel_legacy(ops, pts, vs, colors=None, normals=None):
+    ref = oracle.voxel_legacy(pts, vs, colors=colors, normals=normals)
+    out = ops.voxel_down_sample_legacy(pts, vs, colors=colors, normals=normals)
+    assert out["points"].shape == ref["points"].shape
+    assert np.array_equal(out["index"], ref["index"])
+    assert np.array_equal(out["points"], ref["points"])
+    if colors is not None:
+        assert np.array_equal(out["colors"], ref["colors"])
+    if normals is not None:
+        assert np.array_equal(out["normals"], ref["normals"])
+    assert out["count"].sum() == len(pts)
+    return out
+
+
+@pytest.mark.parametrize("name", ["output84_00008", "output_00050"])
+def test_voxel_legacy_golden_replay(ops, name):
+    """depth PNG -> RGB-D deprojection -> legacy voxel 0.02 on the GPU reproduces the reference's PLY point set bit-exactly."""
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    color = d["color_rgb"] if "color_rgb" in d.files else None
+    xyz, rgb = ops.deproject_rgbd(d["depth"], color, INTR["fx"], INTR["fy"], INTR["ppx"], INTR["ppy"], depth_scale=DEPTH_SCALE)
+    out = _cmp_voxel_legacy(ops, xyz, 0.02, colors=rgb)
+    pts = out["points"]
+    if name.startswith("output_"):
+        keep, _ = ops.remove_statistical_outlier(pts, 20, 2.0)
+        pts = pts[keep]
+    gp = d["ply_points"]
+    assert len(pts) == len(gp)
+    assert np.array_equal(pts[lexorder(pts)], gp[lexorder(gp)])
+
+
+def test_voxel_legacy_random_and_attrs(ops):
+    rng = np.random.default_rng(5)
+    pts = rng.normal(0, 1, (200_000, 3))
+    cols, nrm = rng.random((200_000, 3)), rng.normal(0, 1, (200_000, 3))
+    _cmp_voxel_legacy(ops, pts, 0.05, colors=cols, normals=nrm)
+    _cmp_voxel_legacy(ops, pts, 0.05, normals=nrm)
+    # coarse voxels -> long runs (block-per-run path), and a voxel size larger than the whole cloud
+    _cmp_voxel_legacy(ops, pts, 1.0, colors=cols)
+    _cmp_voxel_legacy(ops, pts, 100.0, colors=cols, normals=nrm)
+
+
+def test_voxel_legacy_edge_cases(ops):
+    one = np.array([[1.5, -2.0, 3.0]])
+    _cmp_voxel_legacy(ops, one, 0.01)
+    same = np.repeat(one, 1000, axis=0)
+    out = _cmp_voxel_legacy(ops, same, 0.01)
+    assert len(out["points"]) == 1 and out["count"][0] == 1000
+    empty = ops.voxel_down_sample_legacy(np.zeros((0, 3)), 0.01)
+    assert empty["points"].shape == (0, 3)
+    with pytest.raises(RuntimeError, match="voxel_size <= 0"):
+        ops.voxel_down_sample_legacy(one, 0.0)
+    far = np.array([[0.0, 0.0, 0.0], [1e9, 0.0, 0.0]])
+    with pytest.raises(RuntimeError, match="voxel_size is too small"):
+        ops.voxel_down_sample_legacy(far, 1e-3)
+    with pytest.raises(RuntimeError, match="voxel_size is too small"):
+        oracle.voxel_legacy(far, 1e-3)
+
+
+def test_voxel_tensor_depth_frame_with_holes(ops):
+    """rs.pointcloud() output keeps zero-depth pixels as (0,0,0): one voxel swallows thousands of identical points."""
+    rng = np.random.default_rng(1000)
+    depth = rng.integers(500, 4000, size=(480, 848), dtype=np.uint16)
+    depth[rng.random(depth.shape) < 0.05] = 0
+    xyz = oracle.deproject_z16(depth, 424.0, 424.0, 424.0, 240.0, 0.001)
+    cols = rng.random(xyz.shape).astype(np.float32)
+    for vs in (0.005, 0.01, 0.05):
+        ref = oracle.voxel_tensor(xyz, vs, attr=cols)
+        out = ops.voxel_down_sample_tensor(xyz, vs, attr=cols)
+        assert np.array_equal(out["index"], ref["index"])
+        assert np.array_equal(out["points"], ref["points"])
+        assert np.array_equal(out["attr"], ref["attr"])
+
+
+def test_voxel_tensor_uniform_cube(ops):
+    """test/gpu-performance.py shape (uniform [0,1)^3, voxel 0.05) at 1 M points: runs of ~125 points each."""
+    rng = np.random.default_rng(5000)
+    pts = rng.random((1_000_000, 3), dtype=np.float32)
+    ref = oracle.voxel_tensor(pts, 0.05)
+    out = ops.voxel_down_sample_tensor(pts, 0.05)
+    assert np.array_equal(out["index"], ref["index"]) and np.array_equal(out["points"], ref["points"])
+    neg = (pts - 0.5).astype(np.float32)
+    ref = oracle.voxel_tensor(neg, 0.013)
+    out = ops.voxel_down_sample_tensor(neg, 0.013)
+    assert np.array_equal(out["index"], ref["index"]) and np.array_equal(out["points"], ref["points"])
+    with pytest.raises(RuntimeError, match="voxel_size must be positive"):
+        ops.voxel_down_sample_tensor(pts[:10], 0.0)
+
+
+# ---- neighbour search -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("k,radius", [(30, 0.02), (20, 0.0), (1, 0.0), (50, 0.05), (64, 0.03)])
+def test_knn_indices_bit_exact(ops, dtype, k, radius):
+    pts = surface_cloud(40_000, seed=7).astype(dtype)
+    q = np.concatenate([pts[::7], (pts[:500] + 0.003).astype(dtype)])
+    ri, rd, rc = oracle.knn(pts, q, k, radius)
+    gi, gd, gc = ops.knn(pts, q, k, radius)
+    assert np.array_equal(gc, rc)
+    assert np.array_equal(gi, ri)
+    assert np.array_equal(gd, rd)
+
+
+def test_knn_ties_and_isolated_points(ops):
+    """Raw lattices produce exact distance ties (tie-break: smaller index); far-away points force the whole-cloud scan."""
+    g = np.stack(np.meshgrid(np.arange(20.0), np.arange(20.0), np.arange(5.0), indexing="ij"), -1).reshape(-1, 3) * 0.01
+    pts = np.concatenate([g, [[5.0, 5.0, 5.0], [-3.0, 0.0, 0.0]]])
+    for k, r in ((7, 0.0), (27, 0.015), (10, 0.0101)):
+        ri, rd, rc = oracle.knn(pts, pts, k, r)
+        gi, gd, gc = ops.knn(pts, pts, k, r)
+        assert np.array_equal(gc, rc) and np.array_equal(gi, ri) and np.array_equal(gd, rd)
+    few = pts[:5]
+    ri, rd, rc = oracle.knn(few, few, 30, 0.0)
+    gi, gd, gc = ops.knn(few, few, 30, 0.0)
+    assert np.array_equal(gc, rc) and np.array_equal(gi, ri)
+
+
+# ---- K3 ---------------------------------------------------------------------------------------------------------
+def _normal_diff(a, b):
+    return np.abs(a - b).max(axis=1)
+
+
+@pytest.mark.parametrize("name,k", [("output84_00060", 20), ("output_00094", 30)])
+def test_normals_legacy_golden(ops, name, k):
+    pts, gn = golden_cloud(name)
+    ref = oracle.normals_legacy(pts, k, 0.04)
+    out = ops.estimate_normals_legacy(pts, k, 0.04)
+    d = _normal_diff(out, ref)
+    # same neighbour order and summation order as the oracle; only libm (acos/cos) last-ulp differences remain, amplified on
+    # near-degenerate neighbourhoods
+    assert np.quantile(d, 0.999) < 1e-9 and (d > 1e-6).sum() <= 3, (np.quantile(d, 0.999), d.max())
+    dg = _normal_diff(out, gn)
+    assert np.quantile(dg, 0.999) < 1e-9 and (dg > 1e-9).sum() <= 8
+
+
+def test_normals_legacy_variants(ops):
+    pts = surface_cloud(60_000, seed=11)
+    for k, r in ((30, 0.02), (30, 0.0), (10, 0.004), (64, 0.05)):
+        ref = oracle.normals_legacy(pts, k, r)
+        out = ops.estimate_normals_legacy(pts, k, r)
+        d = _normal_diff(out, ref)
+        assert np.quantile(d, 0.999) < 1e-9 and (d > 1e-6).sum() <= 3, (k, r, d.max())
+    prior = np.tile([0.0, 0.0, -1.0], (len(pts), 1))
+    ref = oracle.normals_legacy(pts, 30, 0.02, prior=prior)
+    out = ops.estimate_normals_legacy(pts, 30, 0.02, prior=prior)
+    assert np.quantile(_normal_diff(out, ref), 0.999) < 1e-9
+    assert (out[:, 2] <= 1e-12).mean() > 0.99
+    # fewer than 3 neighbours -> (0,0,1); collinear points -> degenerate covariance handled like the oracle
+    iso = np.array([[0.0, 0, 0], [10.0, 0, 0], [0, 10.0, 0]])
+    assert np.array_equal(ops.estimate_normals_legacy(iso, 30, 0.5), oracle.normals_legacy(iso, 30, 0.5))
+    line = np.column_stack([np.linspace(0, 1, 50), np.zeros(50), np.zeros(50)])
+    assert np.allclose(ops.estimate_normals_legacy(line, 10, 0.0), oracle.normals_legacy(line, 10, 0.0), atol=1e-12)
+
+
+def test_normals_tensor(ops):
+    pts = surface_cloud(60_000, seed=13).astype(np.float32)
+    for k, r in ((50, 0.05), (30, 0.01)):
+        ref = oracle.normals_tensor(pts, k, r)
+        out = ops.estimate_normals_tensor(pts, k, r)
+        d = _normal_diff(out, ref)
+        # float32 eigen-solve: libm differences show at 1e-6 relative; stated tolerance 1e-4 on 99.9 %, sign-consistent
+        assert np.quantile(d, 0.999) < 1e-4, np.quantile(d, 0.999)
+        assert (np.sum(out * ref, axis=1) > 0.99).mean() > 0.999
+
+
+def test_covariances_from_normals(ops):
+    rng = np.random.default_rng(17)
+    n = rng.normal(0, 1, (5000, 3))
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    n[0] = [-1.0, 0, 0]
+    n[1] = [1.0, 0, 0]
+    assert np.allclose(ops.covariances_from_normals(n, 1e-3), oracle.covariances_from_normals(n, 1e-3), rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("nb,ratio", [(20, 2.0), (30, 1.2)])
+def test_statistical_outlier_kept_set(ops, nb, ratio):
+    pts, _ = golden_cloud("output84_00008")
+    rng = np.random.default_rng(19)
+    pts = np.concatenate([pts, rng.uniform(-2, 2, (300, 3))])
+    rk, _ = oracle.statistical_outlier(pts, nb, ratio)
+    gk, gi = ops.remove_statistical_outlier(pts, nb, ratio)
+    assert np.array_equal(gk, rk)
+    assert np.array_equal(gi, np.nonzero(rk)[0])
+    with pytest.raises(RuntimeError, match="Illegal input parameters"):
+        ops.remove_statistical_outlier(pts, 0, 1.0)
+
+
+def test_radius_outlier_kept_set(ops):
+    pts, _ = golden_cloud("output_00050")
+    for nbp, r in ((16, 0.05), (4, 0.03), (1, 0.02)):
+        rk = oracle.radius_outlier(pts, nbp, r)
+        gk, gi = ops.remove_radius_outlier(pts, nbp, r)
+        assert np.array_equal(gk, rk) and np.array_equal(gi, np.nonzero(rk)[0])
+    with pytest.raises(RuntimeError, match="Illegal input parameters"):
+        ops.remove_radius_outlier(pts, 3, 0.0)
+
+
+# ---- K4 ---------------------------------------------------------------------------------------------------------
+def test_transform_bit_exact(ops):
+    rng = np.random.default_rng(23)
+    p, n = rng.normal(0, 1, (10_000, 3)), rng.normal(0, 1, (10_000, 3))
+    c = rng.normal(0, 1, (10_000, 9))
+    T = small_rigid()
+    rp, rn, rc = oracle.transform(T, p, n, c)
+    gp, gn, gc = ops.transform(T, p, n, c)
+    assert np.array_equal(gp, rp) and np.array_equal(gn, rn) and np.array_equal(gc, rc)
+
+
+@pytest.mark.parametrize("dmax", [0.02, 0.008, 0.1])
+def test_correspondence_indices_bit_exact(ops, dmax):
+    tgt, _ = golden_cloud("output_00094")
+    T = small_rigid()
+    src = oracle.transform(np.linalg.inv(T), tgt)[0][::2]
+    for Tq in (None, T, small_rigid(0.03, 0.02, -0.01, (0.01, 0.0, -0.01))):
+        rc, rn, rs = oracle.correspondences(src, tgt, Tq, dmax)
+        gc, gn, gs = ops.correspondences(src, tgt, Tq, dmax)
+        assert np.array_equal(gc, rc)
+        assert gn == rn and abs(gs - rs) <= 1e-12 * max(1.0, abs(rs))
+
+
+def test_correspondences_with_exact_ties(ops):
+    g = np.stack(np.meshgrid(np.arange(30.0), np.arange(30.0), indexing="ij"), -1).reshape(-1, 2) * 0.01
+    tgt = np.column_stack([g, np.zeros(len(g))])
+    src = tgt + np.array([0.005, 0.005, 0.0])  # equidistant from four targets
+    rc, rn, _ = oracle.correspondences(src, tgt, None, 0.02)
+    gc, gn, _ = ops.correspondences(src, tgt, None, 0.02)
+    assert np.array_equal(gc, rc) and gn == rn
+
+
+def _check_icp(res, ref, T_true=None):
+    assert rot_err(res["transformation"][:3, :3], ref["transformation"][:3, :3]) < 1e-5
+    assert np.linalg.norm(res["transformation"][:3, 3] - ref["transformation"][:3, 3]) < 1e-5
+    assert abs(res["fitness"] - ref["fitness"]) < 1e-4 and abs(res["inlier_rmse"] - ref["inlier_rmse"]) < 1e-4
+    if T_true is not None:
+        assert rot_err(res["transformation"][:3, :3], T_true[:3, :3]) < 1e-5
+        assert np.linalg.norm(res["transformation"][:3, 3] - T_true[:3, 3]) < 1e-5
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_icp_known_answer_and_oracle(ops, kind):
+    """BASELINE config 1 (substitute cloud): fixture cloud vs a known rigid transform of itself."""
+    tgt, nrm = golden_cloud("output_00094")
+    T = small_rigid()
+    src = oracle.transform(np.linalg.inv(T), tgt)[0]
+    kw = {}
+    if kind == 1:
+        kw["tgt_normals"] = nrm
+    if kind == 2:
+        tc = oracle.covariances_from_normals(nrm)
+        sn = oracle.transform(np.linalg.inv(T), tgt, nrm)[1]
+        kw.update(src_cov=oracle.covariances_from_normals(sn).reshape(-1, 9), tgt_cov=tc.reshape(-1, 9))
+    max_iter = 100 if kind == 0 else 30
+    ref = oracle.icp(kind, src, tgt, 0.02, max_iter=max_iter, **kw)
+    res = ops.icp(kind, src, tgt, 0.02, max_iter=max_iter, **kw)
+    _check_icp(res, ref, T)
+    assert res["fitness"] == 1.0 and res["inlier_rmse"] < 1e-4
+    assert abs(res["iterations"] - ref["iterations"]) <= 1
+    assert np.array_equal(res["corr"], ref["corr"])
+
+
+def test_icp_partial_overlap_with_init(ops):
+    tgt, nrm = golden_cloud("output_00050")
+    other, _ = golden_cloud("output_00008")
+    T = small_rigid(0.02, 0.01, -0.02, (0.01, 0.005, -0.008))
+    src = oracle.transform(np.linalg.inv(T), tgt)[0][::3]
+    src = np.concatenate([src, other[:800] + 5.0])  # far-away clutter: no correspondences
+    init = small_rigid(0.015, 0.0, -0.01, (0.005, 0.0, 0.0))
+    for max_iter in (0, 1, 30):
+        ref = oracle.icp(1, src, tgt, 0.015, T0=init, tgt_normals=nrm, max_iter=max_iter)
+        res = ops.icp(1, src, tgt, 0.015, init=init, tgt_normals=nrm, max_iter=max_iter)
+        _check_icp(res, ref)
+        assert res["iterations"] == ref["iterations"] and res["n_corr"] == ref["n_corr"]
+
+
+def test_icp_errors_and_empty(ops):
+    tgt, nrm = golden_cloud("output84_00008")
+    with pytest.raises(RuntimeError, match="Invalid max_correspondence_distance"):
+        ops.icp(0, tgt, tgt, 0.0)
+    with pytest.raises(RuntimeError, match="require pre-computed normal vectors"):
+        ops.icp(1, tgt, tgt, 0.02)
+    with pytest.raises(RuntimeError, match="requires covariances"):
+        ops.icp(2, tgt, tgt, 0.02)
+    r = ops.icp(0, np.zeros((0, 3)), tgt, 0.02)
+    assert r["fitness"] == 0 and r["inlier_rmse"] == 0 and np.array_equal(r["transformation"], np.eye(4))
+    r = ops.icp(0, tgt[:100] + 50.0, tgt, 0.02)  # nothing within range: identity, fitness 0
+    assert r["fitness"] == 0 and r["n_corr"] == 0 and np.array_equal(r["transformation"], np.eye(4))

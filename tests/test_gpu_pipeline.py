@@ -1,0 +1,179 @@
+"""GPU tests of the whole path: the batched frame-pair pipeline (b3d_register_depth_pairs) against the oracle chain, the
+reference-facing classes, and the step-wise (sharded) ICP."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from util import GOLDEN, golden_cloud, rot_err, small_rigid
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def b3():
+    import b200recon
+    return b200recon
+
+
+def oracle_pair(src_depth, tgt_depth, cam, voxel=0.005, k=30, radius=0.01, kind=1, dmax=0.02, max_iter=30):
+    """CPU restatement of the pipeline: pointcloud_capture.py:35-53 then pointcloud_alignment.py:27-39 (estimator per kind)."""
+    a = (cam["fx"], cam["fy"], cam["ppx"], cam["ppy"], cam["depth_scale"])
+    vs = oracle.voxel_tensor(oracle.deproject_z16(src_depth, *a), voxel)["points"].astype(np.float64)
+    vt = oracle.voxel_tensor(oracle.deproject_z16(tgt_depth, *a), voxel)["points"].astype(np.float64)
+    nt = oracle.normals_legacy(vt, k, radius)
+    kw = dict(tgt_normals=nt)
+    if kind == 2:
+        ns = oracle.normals_legacy(vs, k, radius)
+        kw = dict(src_cov=oracle.covariances_from_normals(ns).reshape(-1, 9), tgt_cov=oracle.covariances_from_normals(nt).reshape(-1, 9))
+    r = oracle.icp(kind, vs, vt, dmax, max_iter=max_iter, **kw)
+    r.update(m_source=len(vs), m_target=len(vt))
+    return r
+
+
+SMALL_CAM = dict(w=212, h=120, fx=106.0, fy=106.0, ppx=106.0, ppy=60.0, depth_scale=0.001)
+
+
+def _pairs(n, cam):
+    from b200recon import synth
+    return synth.depth_pairs(n, base_seed=3000, cam=cam)
+
+
+@pytest.mark.parametrize("kind", [1, 0, 2])
+def test_pair_pipeline_vs_oracle_small(b3, kind):
+    from b200recon import ops
+    src, tgt, T_true = _pairs(3, SMALL_CAM)
+    voxel, radius, dmax = 0.02, 0.05, 0.05
+    params = ops.make_pair_params(**SMALL_CAM, voxel_size=voxel, normals_max_nn=30, normals_radius=radius, icp_kind=kind, icp_max_dist=dmax, icp_max_iter=30)
+    batch = ops.register_depth_pairs(src, tgt, params)
+    assert len(batch) == 3
+    for i in range(3):
+        ref = oracle_pair(src[i], tgt[i], SMALL_CAM, voxel, 30, radius, kind, dmax, 30)
+        r = batch[i]
+        assert r["m_source"] == ref["m_source"] and r["m_target"] == ref["m_target"]
+        assert r["n_raw"] == 2 * SMALL_CAM["w"] * SMALL_CAM["h"]
+        assert rot_err(r["transformation"][:3, :3], ref["transformation"][:3, :3]) < 1e-5
+        assert np.linalg.norm(r["transformation"][:3, 3] - ref["transformation"][:3, 3]) < 1e-5
+        assert abs(r["fitness"] - ref["fitness"]) < 1e-4 and abs(r["inlier_rmse"] - ref["inlier_rmse"]) < 1e-4
+        # every pair of the batch equals the single-pair call bit for bit (same kernels, same order of operations)
+        single = ops.register_depth_pairs(src[i], tgt[i], params)[0]
+        assert np.array_equal(single["transformation"], r["transformation"])
+        assert single["fitness"] == r["fitness"] and single["inlier_rmse"] == r["inlier_rmse"] and single["iterations"] == r["iterations"]
+
+
+def test_pair_pipeline_config2_full_size(b3):
+    """BASELINE config 2 at full size (848x480, voxel 5 mm, Hybrid(0.01, 30), point-to-plane, d_max 0.02, 30 iterations)."""
+    import torch
+    from b200recon import ops, synth
+    src, tgt, T_true = synth.depth_pairs(2, base_seed=1000)
+    params = ops.make_pair_params(**synth.D435)
+    host = ops.register_depth_pairs(src, tgt, params)
+    dev = ops.register_depth_pairs(torch.from_numpy(src.view(np.int16)).cuda(), torch.from_numpy(tgt.view(np.int16)).cuda(), params)
+    for i in range(2):
+        ref = oracle_pair(src[i], tgt[i], synth.D435)
+        for r in (host[i], dev[i]):
+            assert r["m_source"] == ref["m_source"] and r["m_target"] == ref["m_target"]
+            assert rot_err(r["transformation"][:3, :3], ref["transformation"][:3, :3]) < 1e-5
+            assert np.linalg.norm(r["transformation"][:3, 3] - ref["transformation"][:3, 3]) < 1e-5
+            assert abs(r["fitness"] - ref["fitness"]) < 1e-4 and abs(r["inlier_rmse"] - ref["inlier_rmse"]) < 1e-4
+        assert np.array_equal(host[i]["transformation"], dev[i]["transformation"])
+        # the registration recovers the camera motion of the synthetic pair to depth-quantisation accuracy
+        assert rot_err(host[i]["transformation"][:3, :3], T_true[i][:3, :3]) < 2e-3
+        assert np.linalg.norm(host[i]["transformation"][:3, 3] - T_true[i][:3, 3]) < 5e-3
+
+
+def test_capture_and_alignment_classes(b3):
+    """The reference's scan loop (main.py:34-49) over replayed fixture frames: capture -> align -> accumulate."""
+    from b200recon import synth
+    cam = SMALL_CAM
+    src, tgt, _ = _pairs(2, cam)
+    rng = np.random.default_rng(0)
+    frames = [(tgt[0], rng.integers(0, 256, (cam["h"], cam["w"], 3), dtype=np.uint8)), (src[0], rng.integers(0, 256, (cam["h"], cam["w"], 3), dtype=np.uint8)),
+              (None, None)]
+    intr = b3.realsense_pipeline.Intrinsics(cam["w"], cam["h"], cam["fx"], cam["fy"], cam["ppx"], cam["ppy"])
+    mgr = b3.RealSensePipeline(source=b3.ReplayPipeline(frames, intr, depth_scale=cam["depth_scale"]))
+    mgr.start_pipeline()
+    cap = b3.PointCloudCapture(voxel_size=0.02)
+    first = cap.capture_point_cloud(mgr.pipeline)
+    second = cap.capture_point_cloud(mgr.pipeline)
+    assert cap.capture_point_cloud(mgr.pipeline) is None  # missing frame -> None (pointcloud_capture.py:28-29)
+    a = (cam["fx"], cam["fy"], cam["ppx"], cam["ppy"], cam["depth_scale"])
+    ref = oracle.voxel_tensor(oracle.deproject_z16(tgt[0], *a), 0.02, attr=(frames[0][1].reshape(-1, 3) / 255.0).astype(np.float32))
+    assert np.array_equal(np.asarray(first.points), ref["points"].astype(np.float64))
+    assert np.array_equal(np.asarray(first.colors), ref["attr"].astype(np.float64))
+    combined = b3.PointCloud()
+    combined.points, combined.colors = first.points, first.colors
+    align = b3.PointCloudAlignment()
+    aligned = align.align_point_clouds(second, combined, threshold=0.05, voxel_size=0.03, max_iter=50)
+    # oracle chain of pointcloud_alignment.py:22-42
+    s = oracle.voxel_legacy(np.asarray(second.points), 0.03)["points"]
+    t = oracle.voxel_legacy(np.asarray(combined.points), 0.03)["points"]
+    r = oracle.icp(0, s, t, 0.05, max_iter=50)
+    assert rot_err(align.last_result.transformation[:3, :3], r["transformation"][:3, :3]) < 1e-5
+    assert np.linalg.norm(align.last_result.transformation[:3, 3] - r["transformation"][:3, 3]) < 1e-5
+    exp = oracle.transform(r["transformation"], s)[0]
+    assert np.abs(np.asarray(aligned.points) - exp).max() < 1e-5 and aligned.has_normals()
+    n0 = len(combined.points)
+    combined += aligned
+    assert len(combined.points) == n0 + len(aligned.points)
+
+
+def test_processing_and_normal_estimation_classes(b3, tmp_path):
+    """main.py:79-80: process_point_cloud(file) then NormalEstimation.estimate_normals."""
+    from b200recon import plyio
+    pts, nrm = golden_cloud("output84_00060")
+    rng = np.random.default_rng(1)
+    pcd = b3.PointCloud(pts)
+    pcd.colors = rng.random(pts.shape)
+    fn = str(tmp_path / "captured_data_on_the_fly.ply")
+    plyio.write_point_cloud(fn, pcd)
+    proc = b3.PointCloudProcessingWithCUDA(downsample_voxel_size=0.03)
+    out = proc.process_point_cloud(fn)
+    back = plyio.read_point_cloud(fn)
+    p32 = np.asarray(back.points).astype(np.float32)
+    v = oracle.voxel_tensor(p32, 0.03, attr=np.asarray(back.colors).astype(np.float32))
+    vp = v["points"].astype(np.float64)
+    k1, _ = oracle.statistical_outlier(vp, 30, 1.2)
+    vp1 = vp[k1]
+    # the reference's radius (0.01) is tuned to a 2.5 mm cloud; on this 3 cm cloud it removes everything, like Open3D would
+    k2 = oracle.radius_outlier(vp1, 16, 0.01)
+    assert len(out.points) == int(k2.sum())
+    stat_only, ind = b3.PointCloud(vp).remove_statistical_outlier(30, 1.2)
+    assert np.array_equal(np.asarray(stat_only.points), vp1) and ind == np.nonzero(k1)[0].tolist()
+    ne = b3.NormalEstimation()
+    with_n = ne.estimate_normals(b3.PointCloud(pts))
+    ref = oracle.normals_tensor(pts.astype(np.float32), 50, 0.05)
+    d = np.abs(np.asarray(with_n.normals) - ref.astype(np.float64)).max(axis=1)
+    assert np.quantile(d, 0.999) < 1e-4
+
+
+def test_stepwise_icp_two_shards_equal_single(b3):
+    """BASELINE config 5 mechanics on one GPU: the source split in two shards, the 29 sums added (what the all-reduce does),
+    every shard applying the same update -> same transform as the unsharded run (to summation-order rounding)."""
+    import torch
+    from b200recon import distributed as dist, ops
+    tgt, nrm = golden_cloud("output_00094")
+    T = small_rigid()
+    src = oracle.transform(np.linalg.inv(T), tgt)[0]
+    single = ops.icp(1, src, tgt, 0.02, tgt_normals=nrm, max_iter=30)
+    half = len(src) // 2
+    shards = [dist.ShardedICP(1, src[:half], len(src), tgt, 0.02, tgt_normals=nrm, max_iter=30),
+              dist.ShardedICP(1, src[half:], len(src), tgt, 0.02, tgt_normals=nrm, max_iter=30)]
+    for _ in range(40):
+        sums = [s.accumulate() for s in shards]
+        total = sums[0] + sums[1]
+        for s, t in zip(shards, sums):
+            t.copy_(total)
+        done = [s.update() for s in shards]
+        assert done[0] == done[1]
+        if done[0]:
+            break
+    res = [s.finish() for s in shards]
+    assert np.array_equal(res[0]["transformation"], res[1]["transformation"])
+    assert rot_err(res[0]["transformation"][:3, :3], single["transformation"][:3, :3]) < 1e-9
+    assert np.linalg.norm(res[0]["transformation"][:3, 3] - single["transformation"][:3, 3]) < 1e-9
+    assert res[0]["iterations"] == single["iterations"] and abs(res[0]["fitness"] - single["fitness"]) < 1e-12
+    corr = np.concatenate([res[0]["corr"], res[1]["corr"]])
+    assert np.array_equal(corr, single["corr"])
