@@ -7,6 +7,8 @@
 #include "b3d_icp.cuh"
 #include "b3d_search.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <cmath>
 #include <cstring>
 
@@ -174,30 +176,37 @@ __device__ void inv_sqrt_sym3(const double* M, double* W) {
         }
 }
 
-// ---- reduction of kIcpSums doubles over a block: result valid in thread 0 ------------------------------------------
-__device__ __forceinline__ void block_reduce_sums(double* a, double (*sm)[kIcpSums]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int j = 0; j < kIcpSums; ++j) {
-        double v = a[j];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        a[j] = v;
+// ---- per-warp reduction through shared memory ------------------------------------------------------------------------
+// Every lane stores the few values its contributions are products of (row: J0..J5, r, 1, d2 for the plane / generalized
+// estimators; p, q, 1, d2 for point-to-point). Output sum j is sum over lanes of row[P(j)] * row[Q(j)]; lane j walks the
+// 32 rows in lane order and keeps that one running total -- a thread never holds 29 accumulators across the search.
+constexpr int kIcpRow = 9;
+
+__device__ __forceinline__ void icp_sum_operands(int kind, int j, int& p, int& q) {
+    // row layouts: P2L / GICP: [J0 J1 J2 J3 J4 J5 r one d2]   P2P: [px py pz qx qy qz - one d2]
+    p = 7;
+    q = 7;  // default: one * one (j == 27, the correspondence count; also harmless for j >= 29)
+    if (j == 28) { p = 8; q = 7; return; }
+    if (j >= 27) return;
+    if (kind == B3D_ICP_POINT_TO_POINT) {
+        if (j < 6) { p = j; q = 7; }                               // sums of p and of q
+        else if (j < 15) { p = 3 + (j - 6) / 3; q = (j - 6) % 3; } // q_r * p_c
+        else { p = 6; q = 6; }                                      // unused slots: 0 * 0
+        return;
     }
-    if (lane == 0) {
-#pragma unroll
-        for (int j = 0; j < kIcpSums; ++j) sm[warp][j] = a[j];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < kIcpBlock / 32; ++w)
-#pragma unroll
-            for (int j = 0; j < kIcpSums; ++j) a[j] += sm[w][j];
+    if (j < 21) {
+        int u = 0, rem = j;
+        while (rem >= 6 - u) { rem -= 6 - u; ++u; }
+        p = u;
+        q = u + rem;
+    } else {
+        p = j - 21;
+        q = 6;
     }
 }
 
 // ---- end of a pass: fitness / rmse / convergence / update (one thread per pair) -------------------------------------
-__device__ void icp_finalize_pair(int kind, const double* a, double ns, double rel_fitness, double rel_rmse, int max_iter, IcpPairState* st) {
+__device__ __noinline__ void icp_finalize_pair(int kind, const double* a, double ns, double rel_fitness, double rel_rmse, int max_iter, IcpPairState* st) {
     const double nc = a[27];
     const double fitness = (nc == 0 || ns == 0) ? 0.0 : nc / ns;
     const double rmse = nc == 0 ? 0.0 : sqrt(a[28] / nc);
@@ -242,7 +251,7 @@ __device__ void icp_finalize_pair(int kind, const double* a, double ns, double r
 
 struct IcpKernelArgs {
     int kind;
-    const double* src;
+    const double4* src_sorted;
     const double* src_cov;
     const int32_t* src_off;
     const int64_t* ns_global;
@@ -261,121 +270,187 @@ struct IcpKernelArgs {
     int fused;
 };
 
+// Source points are visited in the order of the TARGET cell they fall into (sorted once per ICP run, icp_prepare), so the
+// 32 queries of a warp share their cells: the hash probes and candidate loads hit L1 and the lanes take similar paths.
+// Every lane produces its 29 contributions; a transpose-reduce leaves value j's warp total in lane j, which is the only
+// accumulator a thread keeps (instead of 29 live doubles across the search loop).
 template <int KIND>
-__global__ void __launch_bounds__(kIcpBlock) icp_pass_kernel(IcpKernelArgs A) {
+__global__ void __launch_bounds__(kIcpBlock, 4) icp_pass_kernel(IcpKernelArgs A) {
     const int pair = blockIdx.y;
     IcpPairState* st = A.state + pair;
     if (st->done) return;
     __shared__ double sT[16];
-    __shared__ double sm[kIcpBlock / 32][kIcpSums];
+    __shared__ double sm[kIcpBlock / 32][32];
+    __shared__ double srow[kIcpBlock / 32][32][kIcpRow];
     __shared__ int s_last;
     if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
     __syncthreads();
     const int32_t s0 = A.src_off[pair], s1 = A.src_off[pair + 1];
     const int32_t t0 = A.tgt_off[pair];
-    double a[kIcpSums];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int op_p, op_q;
+    icp_sum_operands(KIND, lane, op_p, op_q);
+    double (*rows)[kIcpRow] = srow[warp];
+    double acc = 0.0;  // lane j: running total of sum j
+    for (int32_t base = s0 + blockIdx.x * kIcpBlock + warp * 32; base < s1; base += gridDim.x * kIcpBlock) {
+        const int32_t i = base + lane;
+        double e[kIcpRow];
 #pragma unroll
-    for (int j = 0; j < kIcpSums; ++j) a[j] = 0.0;
-    for (int32_t i = s0 + blockIdx.x * kIcpBlock + threadIdx.x; i < s1; i += gridDim.x * kIcpBlock) {
-        const double x = A.src[3 * (int64_t)i], y = A.src[3 * (int64_t)i + 1], z = A.src[3 * (int64_t)i + 2];
-        // PointCloud::Transform: (T [p,1]).xyz / w
-        const double w = sT[12] * x + sT[13] * y + sT[14] * z + sT[15];
-        const double px = (sT[0] * x + sT[1] * y + sT[2] * z + sT[3]) / w;
-        const double py = (sT[4] * x + sT[5] * y + sT[6] * z + sT[7]) / w;
-        const double pz = (sT[8] * x + sT[9] * y + sT[10] * z + sT[11]) / w;
-        double d2;
-        int idx;
-        const int pos = nn_within_query<double>(A.grid, pair, px, py, pz, A.r2, A.rmax, &d2, &idx);
-        if (A.corr != nullptr) A.corr[i] = pos >= 0 ? idx - t0 : -1;
-        if (pos < 0) continue;
-        const double4 q = ld_point(A.grid.pts + pos);
-        a[27] += 1.0;
-        a[28] += d2;
-        if (KIND == B3D_ICP_POINT_TO_POINT) {
-            a[0] += px; a[1] += py; a[2] += pz;
-            a[3] += q.x; a[4] += q.y; a[5] += q.z;
-            const double qq[3] = {q.x, q.y, q.z}, pp[3] = {px, py, pz};
+        for (int j = 0; j < kIcpRow; ++j) e[j] = 0.0;
+        double W[9], gd[3], gp[3];  // generalized ICP only
+        bool matched = false;
+        if (i < s1) {
+            const double4 sp = ld_point(A.src_sorted + i);
+            const int oi = point_index(sp);  // original (batch-global) source index
+            const double x = sp.x, y = sp.y, z = sp.z;
+            // PointCloud::Transform: (T [p,1]).xyz / w
+            const double w = sT[12] * x + sT[13] * y + sT[14] * z + sT[15];
+            const double px = (sT[0] * x + sT[1] * y + sT[2] * z + sT[3]) / w;
+            const double py = (sT[4] * x + sT[5] * y + sT[6] * z + sT[7]) / w;
+            const double pz = (sT[8] * x + sT[9] * y + sT[10] * z + sT[11]) / w;
+            double d2;
+            int idx;
+            const int pos = nn_within_query<double>(A.grid, pair, px, py, pz, A.r2, A.rmax, &d2, &idx);
+            if (A.corr != nullptr) A.corr[oi] = pos >= 0 ? idx - t0 : -1;
+            if (pos >= 0) {
+                matched = true;
+                const double4 q = ld_point(A.grid.pts + pos);
+                e[7] = 1.0;
+                e[8] = d2;
+                if (KIND == B3D_ICP_POINT_TO_POINT) {
+                    e[0] = px; e[1] = py; e[2] = pz;
+                    e[3] = q.x; e[4] = q.y; e[5] = q.z;
+                } else if (KIND == B3D_ICP_POINT_TO_PLANE) {
+                    const double* nq = A.tgt_nrm_sorted + 3 * (int64_t)pos;
+                    const double n0 = __ldg(nq), n1 = __ldg(nq + 1), n2 = __ldg(nq + 2);
+                    e[0] = py * n2 - pz * n1; e[1] = pz * n0 - px * n2; e[2] = px * n1 - py * n0;
+                    e[3] = n0; e[4] = n1; e[5] = n2;
+                    e[6] = (px - q.x) * n0 + (py - q.y) * n1 + (pz - q.z) * n2;
+                } else {
+                    // generalized ICP: M = C_t + R C_s R^T, W = (M^-1)^(1/2), rows r_k = W_k (p - q), J = W [ -[p]x | I ]
+                    const double* Ct = A.tgt_cov_sorted + 9 * (int64_t)pos;
+                    const double* Cs = A.src_cov + 9 * (int64_t)oi;
+                    double RC[9], M[9];
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
+                    for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) a[6 + 3 * r + c] += qq[r] * pp[c];
-        } else if (KIND == B3D_ICP_POINT_TO_PLANE) {
-            const double* nq = A.tgt_nrm_sorted + 3 * (int64_t)pos;
-            const double n0 = __ldg(nq), n1 = __ldg(nq + 1), n2 = __ldg(nq + 2);
-            const double r = (px - q.x) * n0 + (py - q.y) * n1 + (pz - q.z) * n2;
-            const double J[6] = {py * n2 - pz * n1, pz * n0 - px * n2, px * n1 - py * n0, n0, n1, n2};
-            int t = 0;
+                        for (int c = 0; c < 3; ++c) RC[3 * r + c] = sT[4 * r] * Cs[c] + sT[4 * r + 1] * Cs[3 + c] + sT[4 * r + 2] * Cs[6 + c];
 #pragma unroll
-            for (int u = 0; u < 6; ++u)
+                    for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int v = u; v < 6; ++v) a[t++] += J[u] * J[v];
-#pragma unroll
-            for (int u = 0; u < 6; ++u) a[21 + u] += J[u] * r;
-        } else {
-            // generalized ICP: M = C_t + R C_s R^T, W = (M^-1)^(1/2), rows r_k = W_k (p - q), J = W [ -[p]x | I ]
-            const double* Ct = A.tgt_cov_sorted + 9 * (int64_t)pos;
-            const double* Cs = A.src_cov + 9 * (int64_t)i;
-            double RC[9], M[9], W[9];
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) RC[3 * r + c] = sT[4 * r] * Cs[c] + sT[4 * r + 1] * Cs[3 + c] + sT[4 * r + 2] * Cs[6 + c];
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    M[3 * r + c] = __ldg(Ct + 3 * r + c) + (RC[3 * r] * sT[4 * c] + RC[3 * r + 1] * sT[4 * c + 1] + RC[3 * r + 2] * sT[4 * c + 2]);
-            inv_sqrt_sym3(M, W);
-            const double d[3] = {px - q.x, py - q.y, pz - q.z};
-            const double Sk[9] = {0, pz, -py, -pz, 0, px, py, -px, 0};
-#pragma unroll
-            for (int row = 0; row < 3; ++row) {
-                double J[6];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) J[c] = W[3 * row] * Sk[c] + W[3 * row + 1] * Sk[3 + c] + W[3 * row + 2] * Sk[6 + c];
-                J[3] = W[3 * row]; J[4] = W[3 * row + 1]; J[5] = W[3 * row + 2];
-                const double r = W[3 * row] * d[0] + W[3 * row + 1] * d[1] + W[3 * row + 2] * d[2];
-                int t = 0;
-#pragma unroll
-                for (int u = 0; u < 6; ++u)
-#pragma unroll
-                    for (int v = u; v < 6; ++v) a[t++] += J[u] * J[v];
-#pragma unroll
-                for (int u = 0; u < 6; ++u) a[21 + u] += J[u] * r;
+                        for (int c = 0; c < 3; ++c)
+                            M[3 * r + c] = __ldg(Ct + 3 * r + c) + (RC[3 * r] * sT[4 * c] + RC[3 * r + 1] * sT[4 * c + 1] + RC[3 * r + 2] * sT[4 * c + 2]);
+                    inv_sqrt_sym3(M, W);
+                    gd[0] = px - q.x; gd[1] = py - q.y; gd[2] = pz - q.z;
+                    gp[0] = px; gp[1] = py; gp[2] = pz;
+                }
             }
         }
-    }
-    block_reduce_sums(a, sm);
-    double* part = A.partial + ((int64_t)pair * gridDim.x + blockIdx.x) * kIcpSums;
-    if (threadIdx.x == 0) {
+        const int n_rows = KIND == B3D_ICP_GENERALIZED ? 3 : 1;
+        for (int row = 0; row < n_rows; ++row) {
+            if (KIND == B3D_ICP_GENERALIZED) {
+                if (matched) {
+                    const double w0 = W[3 * row], w1 = W[3 * row + 1], w2 = W[3 * row + 2];
+                    // J = W_row [ -[p]x | I ],  -[p]x = [0 pz -py; -pz 0 px; py -px 0]
+                    e[0] = w1 * (-gp[2]) + w2 * gp[1];
+                    e[1] = w0 * gp[2] + w2 * (-gp[0]);
+                    e[2] = w0 * (-gp[1]) + w1 * gp[0];
+                    e[3] = w0; e[4] = w1; e[5] = w2;
+                    e[6] = w0 * gd[0] + w1 * gd[1] + w2 * gd[2];
+                    if (row > 0) { e[7] = 0.0; e[8] = 0.0; }
+                }
+            }
 #pragma unroll
-        for (int j = 0; j < kIcpSums; ++j) part[j] = a[j];
-        __threadfence();
+            for (int j = 0; j < kIcpRow; ++j) rows[lane][j] = e[j];
+            __syncwarp();
+            if (KIND == B3D_ICP_GENERALIZED && row > 0 && lane >= 27) {
+                // count and sum d2 are taken once per correspondence (row 0)
+            } else {
+#pragma unroll 8
+                for (int l = 0; l < 32; ++l) acc += rows[l][op_p] * rows[l][op_q];
+            }
+            __syncwarp();
+        }
+    }
+    // block: lane j of every warp holds sum j -> fixed-order sum over the warps -> per-block partial
+    sm[warp][lane] = acc;
+    __syncthreads();
+    double* part = A.partial + ((int64_t)pair * gridDim.x + blockIdx.x) * kIcpSums;
+    if (threadIdx.x < kIcpSums) {
+        double v = sm[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < kIcpBlock / 32; ++w) v += sm[w][threadIdx.x];
+        part[threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
         const unsigned int t = atomicAdd(&st->ticket, 1u);
         s_last = (t == gridDim.x - 1) ? 1 : 0;
     }
     __syncthreads();
     if (!s_last) return;
-    // last block of this pair: second pass over the per-block partials, fixed order (rows strided by thread, then tree)
+    // last block of this pair: second pass over the per-block partials in a fixed order (warp w takes blocks w, w+4, ...;
+    // lane j sums column j), no atomics on the data path
     __threadfence();
-#pragma unroll
-    for (int j = 0; j < kIcpSums; ++j) a[j] = 0.0;
     const double* base = A.partial + (int64_t)pair * gridDim.x * kIcpSums;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += kIcpBlock) {
+    double v = 0.0;
+    if (lane < kIcpSums)
+        for (int b = warp; b < (int)gridDim.x; b += kIcpBlock / 32) v += __ldcg(base + (int64_t)b * kIcpSums + lane);
+    sm[warp][lane] = v;
+    __syncthreads();
+    if (threadIdx.x < kIcpSums) {
+        double t = sm[0][threadIdx.x];
 #pragma unroll
-        for (int j = 0; j < kIcpSums; ++j) a[j] += __ldcg(base + (int64_t)b * kIcpSums + j);
+        for (int w = 1; w < kIcpBlock / 32; ++w) t += sm[w][threadIdx.x];
+        sm[0][threadIdx.x] = t;
+        A.sums[(int64_t)pair * kIcpSums + threadIdx.x] = t;
     }
     __syncthreads();
-    block_reduce_sums(a, sm);
     if (threadIdx.x == 0) {
         st->ticket = 0;
-        double* out = A.sums + (int64_t)pair * kIcpSums;
-#pragma unroll
-        for (int j = 0; j < kIcpSums; ++j) out[j] = a[j];
+#ifndef B3D_TEST_NO_FINALIZE
         if (A.fused) {
+            double a[kIcpSums];
+#pragma unroll
+            for (int j = 0; j < kIcpSums; ++j) a[j] = sm[0][j];
             const double ns = A.ns_global ? (double)A.ns_global[pair] : (double)(s1 - s0);
             icp_finalize_pair(A.kind, a, ns, A.rel_fitness, A.rel_rmse, A.max_iter, st);
         }
+#endif
+    }
+}
+
+// key of the target cell a (transformed) source point falls into; out-of-lattice points are clamped to a one-cell border
+__global__ void __launch_bounds__(256) icp_src_key_kernel(const double* __restrict__ src, const int32_t* __restrict__ src_off,
+                                                          const IcpPairState* __restrict__ state, const Lattice* __restrict__ lat, int shift,
+                                                          uint64_t* __restrict__ keys, uint32_t* __restrict__ order) {
+    const int pair = blockIdx.y;
+    const Lattice L = lat[pair];
+    const double* T = state[pair].T;
+    const int32_t s0 = src_off[pair], s1 = src_off[pair + 1];
+    for (int32_t i = s0 + blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += gridDim.x * blockDim.x) {
+        const double x = src[3 * (int64_t)i], y = src[3 * (int64_t)i + 1], z = src[3 * (int64_t)i + 2];
+        const double px = T[0] * x + T[1] * y + T[2] * z + T[3];
+        const double py = T[4] * x + T[5] * y + T[6] * z + T[7];
+        const double pz = T[8] * x + T[9] * y + T[10] * z + T[11];
+        const double lim = 1.0e9;
+        const double ux = fmin(fmax((px - L.ox) / L.cell, -lim), lim), uy = fmin(fmax((py - L.oy) / L.cell, -lim), lim),
+                     uz = fmin(fmax((pz - L.oz) / L.cell, -lim), lim);
+        long long cx = (long long)floor(ux) - L.kx0, cy = (long long)floor(uy) - L.ky0, cz = (long long)floor(uz) - L.kz0;
+        cx = min(max(cx, -1ll), (long long)L.nx) + 1;
+        cy = min(max(cy, -1ll), (long long)L.ny) + 1;
+        cz = min(max(cz, -1ll), (long long)L.nz) + 1;
+        keys[i] = ((unsigned long long)pair << shift) | (unsigned long long)((cx * (L.ny + 2) + cy) * (L.nz + 2) + cz);
+        order[i] = (uint32_t)i;
+    }
+}
+
+__global__ void __launch_bounds__(256) icp_gather_src_kernel(const double* __restrict__ src, const uint32_t* __restrict__ order, int32_t n,
+                                                             double4* __restrict__ out) {
+    for (int32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t i = order[j];
+        out[j] = make_double4(src[3 * (int64_t)i], src[3 * (int64_t)i + 1], src[3 * (int64_t)i + 2], __longlong_as_double((long long)i));
     }
 }
 
@@ -472,6 +547,41 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
     B3D_LAUNCH(ctx, icp_init_state_kernel, (P + 127) / 128, 128, 0, w->state.p, init_h ? init_d.p : (const double*)nullptr, P);
     const Grid<double>& g = *pb.tgt_grid;
     const int32_t nt = (int32_t)g.sort.n;
+    // order the source points by the target cell they start in (coherent warps in every pass)
+    {
+        const int32_t ns = pb.src_off_h[P];
+        unsigned __int128 max_cells = 1;
+        for (int p = 0; p < P; ++p) {
+            const Lattice& L = g.sort.lat_h[p];
+            unsigned __int128 t = (unsigned __int128)(L.nx + 2) * (unsigned __int128)(L.ny + 2) * (unsigned __int128)(L.nz + 2);
+            if (t > max_cells) max_cells = t;
+        }
+        int shift = 1;
+        while (shift < 100 && ((unsigned __int128)1 << shift) < max_cells) ++shift;
+        int pbits = 0;
+        while ((1ll << pbits) < P) ++pbits;
+        if (shift + pbits > 63) return set_error(B3D_E_RANGE, "ICP target lattice too large for 63-bit keys");
+        B3D_TRY(w->src_sorted.alloc(ctx, (size_t)std::max(ns, 1)));
+        if (ns > 0) {
+            DevBuf<uint64_t> k_in, k_out;
+            DevBuf<uint32_t> o_in, o_out;
+            B3D_TRY(k_in.alloc(ctx, ns));
+            B3D_TRY(k_out.alloc(ctx, ns));
+            B3D_TRY(o_in.alloc(ctx, ns));
+            B3D_TRY(o_out.alloc(ctx, ns));
+            const int kb = (int)std::min<int64_t>((longest + 255) / 256, std::max(1, ctx->sm_count * 16 / P));
+            B3D_LAUNCH(ctx, icp_src_key_kernel, dim3(std::max(1, kb), P), 256, 0, pb.src, pb.src_off, w->state.p, g.sort.lat.p, shift, k_in.p, o_in.p);
+            size_t tmp_bytes = 0;
+            B3D_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.p, k_out.p, o_in.p, o_out.p, ns, 0, shift + pbits, ctx->stream));
+            DevBuf<uint8_t> tmp;
+            B3D_TRY(tmp.alloc(ctx, tmp_bytes));
+            if (ctx->profiling) ctx->prof_begin("cub_radix_sort_pairs");
+            B3D_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k_in.p, k_out.p, o_in.p, o_out.p, ns, 0, shift + pbits, ctx->stream));
+            if (ctx->profiling) ctx->prof_end();
+            ctx->lib_launches += 1;
+            B3D_LAUNCH(ctx, icp_gather_src_kernel, ctx->grid_for(ns, 256, 1, 8), 256, 0, pb.src, o_out.p, ns, w->src_sorted.p);
+        }
+    }
     if (pb.kind == B3D_ICP_POINT_TO_PLANE) {
         B3D_TRY(w->tgt_nrm_sorted.alloc(ctx, (size_t)nt * 3));
         B3D_LAUNCH(ctx, gather_by_sorted_kernel, ctx->grid_for((int64_t)nt * 3, 256, 1, 8), 256, 0, g.pts.p, nt, pb.tgt_normals, 3, w->tgt_nrm_sorted.p);
@@ -485,7 +595,7 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
 static IcpKernelArgs make_args(const IcpProblem& pb, IcpWork* w, int32_t* corr, bool fused) {
     IcpKernelArgs A;
     A.kind = pb.kind;
-    A.src = pb.src;
+    A.src_sorted = w->src_sorted.p;
     A.src_cov = pb.src_cov;
     A.src_off = pb.src_off;
     A.ns_global = pb.ns_global;

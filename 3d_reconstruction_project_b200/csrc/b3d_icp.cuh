@@ -41,6 +41,7 @@ struct IcpWork {
     DevBuf<double> partial;      // [P][blocks][kIcpSums]
     DevBuf<double> sums;         // [P][kIcpSums]
     DevBuf<double> tgt_nrm_sorted, tgt_cov_sorted;
+    DevBuf<double4> src_sorted;  // source points in target-cell order, .w = original index
     DevBuf<int64_t> ns_global;
     int blocks = 1;
 };

@@ -108,7 +108,9 @@ int b3d_register_depth_pairs(b3d_ctx* ctx, const b3d_pair_params* pr, const uint
     Grid<double> icp_grid_own;
     const Grid<double>* icp_grid = &tgrid;
     int icp_rmax = rings_for_radius(pr->icp_max_dist, tgrid.cell);
-    if (icp_rmax > 3) {
+    // A source point without a partner walks every ring up to d_max; with cells of d_max that is 27 probes instead of
+    // (2 rmax + 1)^3, and one such lane holds back its whole warp, so the ICP search gets its own one-ring grid.
+    if (icp_rmax > 1) {
         B3D_TRY(build_search_grid<double>(ctx, tgt_pts, tseg, 8, pr->icp_max_dist, &icp_grid_own, &icp_rmax));
         icp_grid = &icp_grid_own;
     }

@@ -204,23 +204,75 @@ __device__ __forceinline__ void knn_hybrid_query(const GridView<T>& g, const int
     }
 }
 
-// nearest neighbour with d2 < r2 (ICP correspondence): returns sorted position or -1; ties by original index
+// nearest neighbour with d2 < r2 (ICP correspondence): returns sorted position or -1; ties by original index.
+// Home cell first; every further ring only enumerates the cells that the ball of the current best distance overlaps
+// (for a converged ICP that is 1-4 cells instead of 26), each still pruned by its own box distance.
 template <typename T>
 __device__ __forceinline__ int nn_within_query(const GridView<T>& g, int cloud, T qx, T qy, T qz, T r2, int rmax, T* d2_out, int* idx_out) {
     T best = r2;
     int best_pos = -1, best_idx = 0x7fffffff;
-    auto visit = [&](int p, const typename PointT<T>::vec4& pt) {
-        const T dx = qx - pt.x, dy = qy - pt.y, dz = qz - pt.z;
-        const T d2 = dist2<T>(dx, dy, dz);
-        if (best_pos < 0) {
-            if (d2 < best) { best = d2; best_pos = p; best_idx = point_index(pt); }
-        } else if (d2 <= best) {
-            const int idx = point_index(pt);
-            if (d2 < best || idx < best_idx) { best = d2; best_pos = p; best_idx = idx; }
+    const Lattice L = g.lat[cloud];
+    const double h = L.cell;
+    double ux = ((double)qx - L.ox) / h, uy = ((double)qy - L.oy) / h, uz = ((double)qz - L.oz) / h;
+    const double lim = 1.0e9;
+    ux = fmin(fmax(ux, -lim), lim);
+    uy = fmin(fmax(uy, -lim), lim);
+    uz = fmin(fmax(uz, -lim), lim);
+    const double fx0 = floor(ux), fy0 = floor(uy), fz0 = floor(uz);
+    const long long cx = (long long)fx0 - L.kx0, cy = (long long)fy0 - L.ky0, cz = (long long)fz0 - L.kz0;
+    const double fx = ux - fx0, fy = uy - fy0, fz = uz - fz0;
+    const double slack = 1.0 - SearchSlack<T>::rel;
+    const double h2 = h * h * slack;
+    const double face = fmin(fmin(fmin(fx, 1.0 - fx), fmin(fy, 1.0 - fy)), fmin(fz, 1.0 - fz));
+    const unsigned long long cloud_bits = (unsigned long long)cloud << g.shift;
+    auto scan_cell = [&](long long x, long long y, long long z) {
+        const unsigned long long key = cloud_bits | (unsigned long long)((x * L.ny + y) * L.nz + z);
+        int s, e;
+        if (!grid_lookup(g, key, s, e)) return;
+        for (int p = s; p < e; ++p) {
+            const typename PointT<T>::vec4 pt = ld_point(g.pts + p);
+            const T dx = qx - pt.x, dy = qy - pt.y, dz = qz - pt.z;
+            const T d2 = dist2<T>(dx, dy, dz);
+            if (best_pos < 0) {
+                if (d2 < best) { best = d2; best_pos = p; best_idx = point_index(pt); }
+            } else if (d2 <= best) {
+                const int idx = point_index(pt);
+                if (d2 < best || idx < best_idx) { best = d2; best_pos = p; best_idx = idx; }
+            }
         }
     };
-    auto thr = [&]() -> double { return (double)best; };
-    grid_walk<T>(g, cloud, qx, qy, qz, rmax, visit, thr);
+    if (cx >= 0 && cx < L.nx && cy >= 0 && cy < L.ny && cz >= 0 && cz < L.nz) scan_cell(cx, cy, cz);
+    for (int R = 1; R <= rmax; ++R) {
+        {
+            const double bound = (double)(R - 1) + face;
+            if ((double)best < bound * bound * h2) break;  // no unseen cell can hold a better (or tying) point
+        }
+        // cells overlapped by the ball of radius sqrt(best), in cell units, widened by the rounding slack
+        const double reach = sqrt((double)best) / h * (1.0 + 4.0 * SearchSlack<T>::rel) + 1e-12;
+        const int lox = max(-R, (int)floor(fx - reach)), hix = min(R, (int)floor(fx + reach));
+        const int loy = max(-R, (int)floor(fy - reach)), hiy = min(R, (int)floor(fy + reach));
+        const int loz = max(-R, (int)floor(fz - reach)), hiz = min(R, (int)floor(fz + reach));
+        for (int dx = lox; dx <= hix; ++dx) {
+            const long long x = cx + dx;
+            if (x < 0 || x >= L.nx) continue;
+            const double gx = dx > 0 ? (double)dx - fx : (dx < 0 ? fx - (double)dx - 1.0 : 0.0);
+            for (int dy = loy; dy <= hiy; ++dy) {
+                const long long y = cy + dy;
+                if (y < 0 || y >= L.ny) continue;
+                const double gy = dy > 0 ? (double)dy - fy : (dy < 0 ? fy - (double)dy - 1.0 : 0.0);
+                const double gxy2 = gx * gx + gy * gy;
+                const bool shell_xy = (dx == -R || dx == R || dy == -R || dy == R);
+                for (int dz = loz; dz <= hiz; ++dz) {
+                    if (!shell_xy && dz != -R && dz != R) continue;
+                    const long long z = cz + dz;
+                    if (z < 0 || z >= L.nz) continue;
+                    const double gz = dz > 0 ? (double)dz - fz : (dz < 0 ? fz - (double)dz - 1.0 : 0.0);
+                    if ((gxy2 + gz * gz) * h2 > (double)best) continue;
+                    scan_cell(x, y, z);
+                }
+            }
+        }
+    }
     *d2_out = best;
     *idx_out = best_idx;
     return best_pos;

@@ -102,7 +102,8 @@ def height_field_cloud(n_side, pitch=0.001, jitter=0.0002, seed=4000, z0=2.0):
 
 
 def rotation_angle(R):
-    return float(np.arccos(np.clip((np.trace(R) - 1.0) / 2.0, -1.0, 1.0)))
+    """Rotation angle in radians; chord form (arccos of the trace cannot resolve angles below ~1e-8)."""
+    return float(2.0 * np.arcsin(min(1.0, np.linalg.norm(R - np.eye(3)) / (2.0 * np.sqrt(2.0)))))
 
 
 def transform_error(Ta, Tb):

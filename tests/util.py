@@ -38,4 +38,5 @@ def small_rigid(rx=0.01, ry=-0.015, rz=0.02, t=(0.004, -0.003, 0.005)):
 
 
 def rot_err(Ra, Rb):
-    return float(np.arccos(np.clip((np.trace(Ra.T @ Rb) - 1) / 2, -1, 1)))
+    """Angle of Ra^T Rb in radians; chord form (arccos of the trace cannot resolve angles below ~1e-8)."""
+    return float(2.0 * np.arcsin(min(1.0, np.linalg.norm(Ra - Rb) / (2.0 * np.sqrt(2.0)))))
