@@ -6,17 +6,24 @@
 // device; the host only enqueues passes. A batch of P independent pairs runs in the same launches (grid.y = pair).
 #include "b3d_icp.cuh"
 #include "b3d_search.cuh"
+#include "b3d_scan.cuh"
+#include "b3d_stage.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace b3d {
 
+// debug counters of the staged search (enabled by the environment variable B3D_ICP_STATS=1; see b3d_debug_icp_stats)
+__device__ unsigned long long g_icp_stats[8];
+
 namespace {
 
 constexpr int kIcpBlock = 128;
+constexpr int kIcpMaxGroups = 1024;  // partial-sum groups (blocks) per pair
 
 // ---- small dense helpers (device) ----------------------------------------------------------------------------------
 __device__ void mat4_mul(const double* A, const double* B, double* C) {
@@ -252,6 +259,9 @@ __device__ __noinline__ void icp_finalize_pair(int kind, const double* a, double
 struct IcpKernelArgs {
     int kind;
     const double4* src_sorted;
+    const int32_t* chunk_start;  // [n_chunks + 1] first sorted source position of every warp chunk (<= 32 points, compact)
+    const int32_t* chunk_off;    // [P + 1] first chunk of every pair
+    int32_t n_chunks;
     const double* src_cov;
     const int32_t* src_off;
     const int64_t* ns_global;
@@ -268,6 +278,7 @@ struct IcpKernelArgs {
     double* sums;
     int32_t* corr;
     int fused;
+    int stats;  // count chunks / rounds / staged candidates into g_icp_stats
 };
 
 // Source points are visited in the order of the TARGET cell they fall into (sorted once per ICP run, icp_prepare), so the
@@ -282,6 +293,8 @@ __global__ void __launch_bounds__(kIcpBlock, 4) icp_pass_kernel(IcpKernelArgs A)
     __shared__ double sT[16];
     __shared__ double sm[kIcpBlock / 32][32];
     __shared__ double srow[kIcpBlock / 32][32][kIcpRow];
+    __shared__ float4 s_cand[kIcpBlock / 32][kStageCap];
+    __shared__ StageScratch s_stage[kIcpBlock / 32];
     __shared__ int s_last;
     if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
     __syncthreads();
@@ -292,25 +305,75 @@ __global__ void __launch_bounds__(kIcpBlock, 4) icp_pass_kernel(IcpKernelArgs A)
     icp_sum_operands(KIND, lane, op_p, op_q);
     double (*rows)[kIcpRow] = srow[warp];
     double acc = 0.0;  // lane j: running total of sum j
-    for (int32_t base = s0 + blockIdx.x * kIcpBlock + warp * 32; base < s1; base += gridDim.x * kIcpBlock) {
-        const int32_t i = base + lane;
+    // first-round reach of the staged search: a few times the previous pass's inlier rmse (most partners of a nearly
+    // converged pass are that close); lanes that are not certain after it trigger a second round at d_max
+    const double dmax = sqrt(A.r2);
+    double reach1 = dmax;
+    if (st->iter > 0) reach1 = fmin(dmax, fmax(3.0 * st->rmse, 0.2 * dmax));
+    float4* cand = s_cand[warp];
+    // this pair's range of warp chunks (chunks never straddle pairs) and its number of partial-sum groups: a function of
+    // the pair's own chunk count only, so a pair's result does not depend on what else is in the batch
+    const int32_t c0 = A.chunk_off[pair], c1 = A.chunk_off[pair + 1];
+    const int groups = max(1, min((c1 - c0 + kIcpBlock / 32 - 1) / (kIcpBlock / 32), kIcpMaxGroups));
+    if ((int)blockIdx.x >= groups) return;
+    for (int32_t c = c0 + blockIdx.x * (kIcpBlock / 32) + warp; c < c1; c += groups * (kIcpBlock / 32)) {
+        const int32_t i = A.chunk_start[c] + lane;
+        const int32_t chunk_end = A.chunk_start[c + 1];
         double e[kIcpRow];
 #pragma unroll
         for (int j = 0; j < kIcpRow; ++j) e[j] = 0.0;
         double W[9], gd[3], gp[3];  // generalized ICP only
         bool matched = false;
-        if (i < s1) {
+        const bool valid = i < chunk_end;
+        double px = 0, py = 0, pz = 0;
+        int oi = 0;
+        if (valid) {
             const double4 sp = ld_point(A.src_sorted + i);
-            const int oi = point_index(sp);  // original (batch-global) source index
+            oi = point_index(sp);  // original (batch-global) source index
             const double x = sp.x, y = sp.y, z = sp.z;
             // PointCloud::Transform: (T [p,1]).xyz / w
             const double w = sT[12] * x + sT[13] * y + sT[14] * z + sT[15];
-            const double px = (sT[0] * x + sT[1] * y + sT[2] * z + sT[3]) / w;
-            const double py = (sT[4] * x + sT[5] * y + sT[6] * z + sT[7]) / w;
-            const double pz = (sT[8] * x + sT[9] * y + sT[10] * z + sT[11]) / w;
-            double d2;
-            int idx;
-            const int pos = nn_within_query<double>(A.grid, pair, px, py, pz, A.r2, A.rmax, &d2, &idx);
+            px = (sT[0] * x + sT[1] * y + sT[2] * z + sT[3]) / w;
+            py = (sT[4] * x + sT[5] * y + sT[6] * z + sT[7]) / w;
+            pz = (sT[8] * x + sT[9] * y + sT[10] * z + sT[11]) / w;
+        }
+        // ---- correspondence: staged warp search (bit-identical to nn_within_query) ------------------------------
+        double d2 = 0.0;
+        int idx = 0, pos = -1;
+        {
+            const double big = 1.0e300;
+            const double bl[3] = {warp_min(valid ? px : big), warp_min(valid ? py : big), warp_min(valid ? pz : big)};
+            const double bh[3] = {warp_max(valid ? px : -big), warp_max(valid ? py : -big), warp_max(valid ? pz : -big)};
+            for (int round = 0; round < 2; ++round) {
+                const double reach = round == 0 ? reach1 : dmax;
+                if (round == 1 && !(reach1 < dmax)) break;
+                const double pad = reach * (1.0 + 1e-9) + 1e-12;
+                const double lo[3] = {bl[0] - pad, bl[1] - pad, bl[2] - pad}, hi[3] = {bh[0] + pad, bh[1] + pad, bh[2] + pad};
+                const double center[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
+                const float half_extent = (float)(0.5 * fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2])) * 1.0001f;
+                const int count = warp_stage_box(A.grid, pair, lo, hi, center, cand, &s_stage[warp]);
+                if (A.stats && lane == 0) {
+                    atomicAdd(&g_icp_stats[round == 0 ? 0 : 1], 1ull);
+                    if (count < 0) atomicAdd(&g_icp_stats[2], 1ull);
+                    else atomicAdd(&g_icp_stats[3], (unsigned long long)count);
+                    const double ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+                    atomicAdd(&g_icp_stats[4], (unsigned long long)(1.0e6 * ex * ey * ez));  // box volume in cm^3
+                    atomicAdd(&g_icp_stats[5], (unsigned long long)(1.0e4 * fmax(fmax(ex, ey), ez)));  // longest edge in 0.1 mm
+                }
+                if (count < 0) {
+                    // the box is too crowded for the staging buffer: per-lane walk of the grid
+                    if (valid) pos = nn_within_query<double>(A.grid, pair, px, py, pz, A.r2, A.rmax, &d2, &idx);
+                    break;
+                }
+                pos = -1;
+                if (valid) pos = staged_nearest(A.grid, cand, count, center, half_extent, px, py, pz, &d2, &idx);
+                __syncwarp();
+                const bool certain = !valid || !(reach < dmax) || (pos >= 0 && d2 <= reach * reach);
+                if (__all_sync(0xffffffffu, certain)) break;
+            }
+            if (pos >= 0 && !(d2 < A.r2)) pos = -1;
+        }
+        if (valid) {
             if (A.corr != nullptr) A.corr[oi] = pos >= 0 ? idx - t0 : -1;
             if (pos >= 0) {
                 matched = true;
@@ -386,7 +449,7 @@ __global__ void __launch_bounds__(kIcpBlock, 4) icp_pass_kernel(IcpKernelArgs A)
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int t = atomicAdd(&st->ticket, 1u);
-        s_last = (t == gridDim.x - 1) ? 1 : 0;
+        s_last = (t == (unsigned int)groups - 1u) ? 1 : 0;
     }
     __syncthreads();
     if (!s_last) return;
@@ -396,7 +459,7 @@ __global__ void __launch_bounds__(kIcpBlock, 4) icp_pass_kernel(IcpKernelArgs A)
     const double* base = A.partial + (int64_t)pair * gridDim.x * kIcpSums;
     double v = 0.0;
     if (lane < kIcpSums)
-        for (int b = warp; b < (int)gridDim.x; b += kIcpBlock / 32) v += __ldcg(base + (int64_t)b * kIcpSums + lane);
+        for (int b = warp; b < groups; b += kIcpBlock / 32) v += __ldcg(base + (int64_t)b * kIcpSums + lane);
     sm[warp][lane] = v;
     __syncthreads();
     if (threadIdx.x < kIcpSums) {
@@ -421,7 +484,18 @@ __global__ void __launch_bounds__(kIcpBlock, 4) icp_pass_kernel(IcpKernelArgs A)
     }
 }
 
-// key of the target cell a (transformed) source point falls into; out-of-lattice points are clamped to a one-cell border
+__device__ __forceinline__ unsigned long long spread3(unsigned long long v) {  // 21 bits -> every third bit
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x1f00000000ffffull;
+    v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+
+// Morton key of the (transformed) source point on a quarter-cell lattice of the pair's target grid: consecutive keys are
+// spatially compact, so the 32 queries of a warp fit a small box (and stay compact under the rigid updates of later passes).
 __global__ void __launch_bounds__(256) icp_src_key_kernel(const double* __restrict__ src, const int32_t* __restrict__ src_off,
                                                           const IcpPairState* __restrict__ state, const Lattice* __restrict__ lat, int shift,
                                                           uint64_t* __restrict__ keys, uint32_t* __restrict__ order) {
@@ -429,22 +503,52 @@ __global__ void __launch_bounds__(256) icp_src_key_kernel(const double* __restri
     const Lattice L = lat[pair];
     const double* T = state[pair].T;
     const int32_t s0 = src_off[pair], s1 = src_off[pair + 1];
+    const double q = L.cell * 0.25;
     for (int32_t i = s0 + blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += gridDim.x * blockDim.x) {
         const double x = src[3 * (int64_t)i], y = src[3 * (int64_t)i + 1], z = src[3 * (int64_t)i + 2];
         const double px = T[0] * x + T[1] * y + T[2] * z + T[3];
         const double py = T[4] * x + T[5] * y + T[6] * z + T[7];
         const double pz = T[8] * x + T[9] * y + T[10] * z + T[11];
-        const double lim = 1.0e9;
-        const double ux = fmin(fmax((px - L.ox) / L.cell, -lim), lim), uy = fmin(fmax((py - L.oy) / L.cell, -lim), lim),
-                     uz = fmin(fmax((pz - L.oz) / L.cell, -lim), lim);
-        long long cx = (long long)floor(ux) - L.kx0, cy = (long long)floor(uy) - L.ky0, cz = (long long)floor(uz) - L.kz0;
-        cx = min(max(cx, -1ll), (long long)L.nx) + 1;
-        cy = min(max(cy, -1ll), (long long)L.ny) + 1;
-        cz = min(max(cz, -1ll), (long long)L.nz) + 1;
-        keys[i] = ((unsigned long long)pair << shift) | (unsigned long long)((cx * (L.ny + 2) + cy) * (L.nz + 2) + cz);
+        const double hi = 2097151.0;  // 2^21 - 1
+        // one cell of margin below the lattice origin; everything farther out clamps to the border
+        const double ux = fmin(fmax(floor((px - L.ox) / q) + 4.0, 0.0), hi), uy = fmin(fmax(floor((py - L.oy) / q) + 4.0, 0.0), hi),
+                     uz = fmin(fmax(floor((pz - L.oz) / q) + 4.0, 0.0), hi);
+        const unsigned long long m = (spread3((unsigned long long)ux) << 2) | (spread3((unsigned long long)uy) << 1) | spread3((unsigned long long)uz);
+        keys[i] = ((unsigned long long)pair << shift) | (m & ((1ull << shift) - 1ull));
         order[i] = (uint32_t)i;
     }
 }
+
+// warp chunks: a new chunk starts every 32 sorted points and wherever the Morton block (8 x 8 x 8 quarter-cells = 2 cells
+// on a side; the pair id sits above it) changes, so a chunk's 32 queries never span more than one such block
+struct ChunkPred {
+    const uint64_t* keys;
+    const int32_t* src_off;
+    int shift;
+    __device__ __forceinline__ bool operator()(int64_t i) const {
+        const uint64_t k = keys[i];
+        const int64_t rel = i - src_off[(int)(k >> shift)];  // position inside the pair: batch-invariant chunking
+        return (rel & 31) == 0 || (k >> 9) != (keys[i - 1] >> 9);
+    }
+};
+// chunk_off[p] = first chunk of pair p (chunk_off[P] = n_chunks)
+__global__ void icp_chunk_ranges_kernel(const int32_t* __restrict__ chunk_start, const int64_t* __restrict__ n_chunks_d,
+                                        const int32_t* __restrict__ src_off, int P, int32_t* __restrict__ chunk_off) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > P) return;
+    const int32_t key = src_off[p];
+    int a = 0, b = (int)*n_chunks_d;
+    while (a < b) {
+        const int m = (a + b) >> 1;
+        if (chunk_start[m] < key) a = m + 1; else b = m;
+    }
+    chunk_off[p] = a;
+}
+struct ChunkEmit {
+    int32_t* chunk_start;
+    __device__ __forceinline__ void operator()(int64_t i, int64_t slot) const { chunk_start[slot] = (int32_t)i; }
+};
+__global__ void icp_chunk_sentinel_kernel(int32_t* chunk_start, const int64_t* n_chunks, int32_t ns) { chunk_start[*n_chunks] = ns; }
 
 __global__ void __launch_bounds__(256) icp_gather_src_kernel(const double* __restrict__ src, const uint32_t* __restrict__ order, int32_t n,
                                                              double4* __restrict__ out) {
@@ -533,11 +637,7 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
     const int P = pb.P;
     int64_t longest = 0;
     for (int p = 0; p < P; ++p) longest = std::max<int64_t>(longest, pb.src_off_h[p + 1] - pb.src_off_h[p]);
-    int blocks = (int)std::max<int64_t>(1, (longest + kIcpBlock - 1) / kIcpBlock);
-    const int cap = std::max(1, ctx->sm_count * 16 / P);
-    w->blocks = std::min(blocks, cap);
     B3D_TRY(w->state.alloc(ctx, P));
-    B3D_TRY(w->partial.alloc(ctx, (size_t)P * w->blocks * kIcpSums));
     B3D_TRY(w->sums.alloc(ctx, (size_t)P * kIcpSums));
     DevBuf<double> init_d;
     if (init_h) {
@@ -550,17 +650,18 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
     // order the source points by the target cell they start in (coherent warps in every pass)
     {
         const int32_t ns = pb.src_off_h[P];
-        unsigned __int128 max_cells = 1;
+        // Morton bits: 3 x bits(4 * cells per axis + margin), capped at 3 x 21; coordinates beyond that clamp (still correct, less compact)
+        int64_t max_axis = 1;
         for (int p = 0; p < P; ++p) {
             const Lattice& L = g.sort.lat_h[p];
-            unsigned __int128 t = (unsigned __int128)(L.nx + 2) * (unsigned __int128)(L.ny + 2) * (unsigned __int128)(L.nz + 2);
-            if (t > max_cells) max_cells = t;
+            max_axis = std::max<int64_t>(max_axis, std::max(std::max(L.nx, L.ny), L.nz));
         }
-        int shift = 1;
-        while (shift < 100 && ((unsigned __int128)1 << shift) < max_cells) ++shift;
+        int axis_bits = 1;
+        while (axis_bits < 21 && (1ll << axis_bits) < 4 * max_axis + 8) ++axis_bits;
         int pbits = 0;
         while ((1ll << pbits) < P) ++pbits;
-        if (shift + pbits > 63) return set_error(B3D_E_RANGE, "ICP target lattice too large for 63-bit keys");
+        while (3 * axis_bits + pbits > 63) --axis_bits;
+        const int shift = 3 * axis_bits;
         B3D_TRY(w->src_sorted.alloc(ctx, (size_t)std::max(ns, 1)));
         if (ns > 0) {
             DevBuf<uint64_t> k_in, k_out;
@@ -580,7 +681,29 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
             if (ctx->profiling) ctx->prof_end();
             ctx->lib_launches += 1;
             B3D_LAUNCH(ctx, icp_gather_src_kernel, ctx->grid_for(ns, 256, 1, 8), 256, 0, pb.src, o_out.p, ns, w->src_sorted.p);
+            DevBuf<int64_t> n_chunks_d;
+            B3D_TRY(n_chunks_d.alloc(ctx, 1));
+            B3D_TRY(w->chunk_start.alloc(ctx, (size_t)ns + 1));
+            B3D_TRY(compact(ctx, ChunkPred{k_out.p, pb.src_off, shift}, ChunkEmit{w->chunk_start.p}, ns, n_chunks_d.p));
+            B3D_LAUNCH(ctx, icp_chunk_sentinel_kernel, 1, 1, 0, w->chunk_start.p, n_chunks_d.p, ns);
+            B3D_TRY(w->chunk_off.alloc(ctx, (size_t)P + 1));
+            B3D_LAUNCH(ctx, icp_chunk_ranges_kernel, (P + 1 + 127) / 128, 128, 0, w->chunk_start.p, n_chunks_d.p, pb.src_off, P, w->chunk_off.p);
+            std::vector<int32_t> coff(P + 1);
+            B3D_TRY(ctx->download(coff.data(), w->chunk_off.p, (size_t)(P + 1) * sizeof(int32_t)));
+            w->n_chunks = coff[P];
+            int32_t most = 0;
+            for (int p = 0; p < P; ++p) most = std::max(most, coff[p + 1] - coff[p]);
+            // partial-sum groups per pair depend only on that pair's own chunk count (results do not depend on the batch)
+            w->blocks = std::max(1, std::min((most + kIcpBlock / 32 - 1) / (kIcpBlock / 32), kIcpMaxGroups));
+        } else {
+            B3D_TRY(w->chunk_start.alloc(ctx, 1));
+            B3D_CUDA(cudaMemsetAsync(w->chunk_start.p, 0, sizeof(int32_t), ctx->stream));
+            B3D_TRY(w->chunk_off.alloc(ctx, (size_t)P + 1));
+            B3D_CUDA(cudaMemsetAsync(w->chunk_off.p, 0, (size_t)(P + 1) * sizeof(int32_t), ctx->stream));
+            w->n_chunks = 0;
+            w->blocks = 1;
         }
+        B3D_TRY(w->partial.alloc(ctx, (size_t)P * w->blocks * kIcpSums));
     }
     if (pb.kind == B3D_ICP_POINT_TO_PLANE) {
         B3D_TRY(w->tgt_nrm_sorted.alloc(ctx, (size_t)nt * 3));
@@ -596,6 +719,9 @@ static IcpKernelArgs make_args(const IcpProblem& pb, IcpWork* w, int32_t* corr, 
     IcpKernelArgs A;
     A.kind = pb.kind;
     A.src_sorted = w->src_sorted.p;
+    A.chunk_start = w->chunk_start.p;
+    A.chunk_off = w->chunk_off.p;
+    A.n_chunks = w->n_chunks;
     A.src_cov = pb.src_cov;
     A.src_off = pb.src_off;
     A.ns_global = pb.ns_global;
@@ -613,6 +739,10 @@ static IcpKernelArgs make_args(const IcpProblem& pb, IcpWork* w, int32_t* corr, 
     A.sums = w->sums.p;
     A.corr = corr;
     A.fused = fused ? 1 : 0;
+    {
+        static const int stats_on = getenv("B3D_ICP_STATS") ? 1 : 0;
+        A.stats = stats_on;
+    }
     return A;
 }
 
@@ -723,6 +853,17 @@ static int setup_single(b3d_ctx* ctx, b3d_icp_state* st, int kind, const double*
 }
 
 extern "C" {
+
+// [0] first-round chunks, [1] second-round chunks, [2] staging overflows (per-lane fallback), [3] staged candidates,
+// [4] sum of box volumes (cm^3), [5] sum of longest box edges (0.1 mm). Debug aid, not part of the public header.
+int b3d_debug_icp_stats(unsigned long long* out8, int reset) {
+    if (out8 && cudaMemcpyFromSymbol(out8, g_icp_stats, 8 * sizeof(unsigned long long)) != cudaSuccess) return B3D_E_CUDA;
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (cudaMemcpyToSymbol(g_icp_stats, z, sizeof(z)) != cudaSuccess) return B3D_E_CUDA;
+    }
+    return B3D_OK;
+}
 
 int b3d_transform_f64(b3d_ctx* ctx, const double* T_h, double* xyz, int64_t n, double* normals, double* cov) {
     B3D_REQUIRE(ctx != nullptr && T_h != nullptr, "b3d_transform_f64: NULL argument");

@@ -19,7 +19,6 @@ cpu_baseline / --impl reference: the CPU restatement of the reference's Open3D/l
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -111,32 +110,51 @@ def run_reference(args):
 
 # ---- clocks ------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks and throttle reasons DURING the timed region through NVML in-process (an `nvidia-smi` subprocess
+    per sample takes the driver lock for tens of ms and shows up as jitter in short timed regions)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_ev = index, [], threading.Event()
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
 
     def run(self):
+        nv = self.nv
+        if nv is None:
+            return
         while not self._stop_ev.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, rs))
             except Exception:
                 pass
-            self._stop_ev.wait(0.2)
+            self._stop_ev.wait(0.05)
 
     def stop(self):
         self._stop_ev.set()
         self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        if self.nv is None or not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        nv = self.nv
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted({n for _, rs in self.rows for n, b in bits.items() if rs & b})
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.max_sm), "reasons": reasons, "samples": len(sm)}
 
 
 # ---- algorithmic bytes per launch (SURVEY.md 8d; DESIGN.md "roofline") ---------------------------------------------------
