@@ -12,7 +12,9 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "b200recon.h"
@@ -71,6 +73,15 @@ struct b3d_ctx {
     std::vector<cudaEvent_t> prof_pool;
     void prof_begin(const char* name);
     void prof_end();
+
+    // Scratch memory: a per-context caching allocator over cudaMalloc. The pipelines allocate the same sequence of sizes
+    // every step; cudaMallocAsync's pool occasionally re-maps physical memory for large blocks (measured: 20-480 ms stalls,
+    // profiles/r01e_alloc_stalls.txt), a size-keyed free list never does. All work of a context runs on ONE stream, so
+    // handing a block to the next user is ordered after the previous user's kernels.
+    std::multimap<size_t, void*> cache_free;
+    std::unordered_map<void*, size_t> cache_live;
+    size_t cache_total = 0;
+    void cache_release_all();
 
     int bind() const;
     int alloc_bytes(void** p, size_t bytes);

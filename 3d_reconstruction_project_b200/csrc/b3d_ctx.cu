@@ -2,6 +2,8 @@
 #include "b3d_common.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 namespace b3d {
@@ -20,23 +22,82 @@ int set_error(int code, const char* fmt, ...) {
 
 }  // namespace b3d
 
+namespace {
+// B3D_TRACE_SLOW=<ms>: report host-side runtime calls that take longer than <ms> (allocator growth, stalled syncs)
+double trace_slow_ms() {
+    static const double v = [] {
+        const char* e = getenv("B3D_TRACE_SLOW");
+        return e ? atof(e) : 0.0;
+    }();
+    return v;
+}
+struct SlowCall {
+    const char* what;
+    size_t bytes;
+    std::chrono::steady_clock::time_point t0;
+    SlowCall(const char* w, size_t b) : what(w), bytes(b), t0(std::chrono::steady_clock::now()) {}
+    ~SlowCall() {
+        const double lim = trace_slow_ms();
+        if (lim <= 0) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > lim) fprintf(stderr, "[b3d slow] %s(%zu) took %.1f ms\n", what, bytes, ms);
+    }
+};
+}  // namespace
+
 int b3d_ctx::bind() const {
     B3D_CUDA(cudaSetDevice(device));
     return B3D_OK;
 }
 int b3d_ctx::alloc_bytes(void** p, size_t bytes) {
-    cudaError_t e = cudaMallocAsync(p, bytes, stream);
+    SlowCall sc("alloc", bytes);
+    const size_t gran = bytes < (1u << 20) ? 512 : (2u << 20);
+    const size_t want = (bytes + gran - 1) / gran * gran;
+    auto it = cache_free.lower_bound(want);
+    if (it != cache_free.end() && it->first <= want + want / 2 + (1u << 20)) {
+        *p = it->second;
+        cache_live[*p] = it->first;
+        cache_free.erase(it);
+        return B3D_OK;
+    }
+    cudaError_t e = cudaMalloc(p, want);
+    if (e == cudaErrorMemoryAllocation) {
+        // give the cached blocks back to the driver and retry once
+        cudaGetLastError();
+        cudaStreamSynchronize(stream);
+        for (auto& kv : cache_free) {
+            cudaFree(kv.second);
+            cache_total -= kv.first;
+        }
+        cache_free.clear();
+        e = cudaMalloc(p, want);
+    }
     if (e != cudaSuccess) {
         *p = nullptr;
-        return b3d::set_error(e == cudaErrorMemoryAllocation ? B3D_E_NOMEM : B3D_E_CUDA, "cudaMallocAsync(%zu bytes): %s", bytes,
-                              cudaGetErrorString(e));
+        cudaGetLastError();
+        return b3d::set_error(e == cudaErrorMemoryAllocation ? B3D_E_NOMEM : B3D_E_CUDA, "cudaMalloc(%zu bytes): %s", want, cudaGetErrorString(e));
     }
+    cache_live[*p] = want;
+    cache_total += want;
     return B3D_OK;
 }
 void b3d_ctx::free_async(void* p) {
-    if (p) cudaFreeAsync(p, stream);
+    if (!p) return;
+    auto it = cache_live.find(p);
+    if (it == cache_live.end()) return;
+    cache_free.emplace(it->second, p);
+    cache_live.erase(it);
+}
+void b3d_ctx::cache_release_all() {
+    cudaStreamSynchronize(stream);
+    for (auto& kv : cache_free) cudaFree(kv.second);
+    for (auto& kv : cache_live) cudaFree(kv.first);
+    cache_free.clear();
+    cache_live.clear();
+    cache_total = 0;
 }
 int b3d_ctx::sync() {
+    SlowCall sc("cudaStreamSynchronize", 0);
     B3D_CUDA(cudaStreamSynchronize(stream));
     return B3D_OK;
 }
@@ -57,6 +118,7 @@ int b3d_ctx::ensure_pinned(size_t bytes) {
 int b3d_ctx::download(void* dst_h, const void* src_d, size_t bytes) {
     if (bytes == 0) return B3D_OK;
     B3D_TRY(ensure_pinned(bytes));
+    SlowCall sc("download", bytes);
     B3D_CUDA(cudaMemcpyAsync(pinned, src_d, bytes, cudaMemcpyDeviceToHost, stream));
     B3D_CUDA(cudaStreamSynchronize(stream));
     memcpy(dst_h, pinned, bytes);
@@ -64,6 +126,7 @@ int b3d_ctx::download(void* dst_h, const void* src_d, size_t bytes) {
 }
 int b3d_ctx::upload(void* dst_d, const void* src_h, size_t bytes) {
     if (bytes == 0) return B3D_OK;
+    SlowCall sc("upload", bytes);
     B3D_CUDA(cudaMemcpyAsync(dst_d, src_h, bytes, cudaMemcpyHostToDevice, stream));
     return B3D_OK;
 }
@@ -175,12 +238,6 @@ int b3d_ctx_create(int device, void* stream, b3d_ctx** out) {
     c->own_stream = false;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
-    // keep freed scratch in the pool: the per-frame pipelines re-allocate the same sizes over and over
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
     c->pinned_bytes = 4096;
     if (cudaMallocHost(&c->pinned, c->pinned_bytes) != cudaSuccess) {
         if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -195,6 +252,7 @@ int b3d_ctx_destroy(b3d_ctx* ctx) {
     if (!ctx) return B3D_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    ctx->cache_release_all();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (auto& r : ctx->prof) {
         cudaEventDestroy(r.e0);

@@ -158,7 +158,7 @@ class ClockSampler(threading.Thread):
 
 
 # ---- algorithmic bytes per launch (DESIGN.md "roofline") ---------------------------------------------------
-def kernel_bytes(name, N_raw, M_total, Mt, Ms, n_corr):
+def kernel_bytes(name, N_raw, M_total, Mt, Ms, n_corr, icp_bytes_per_launch=None):
     """Compulsory HBM traffic of one launch of `name` for a batch with N_raw raw points, M_total voxels (Ms sources, Mt targets)."""
     table = {
         "deproject_z16_vec4_kernel": 14 * N_raw / 2,  # two launches per batch (sources, targets)
@@ -171,7 +171,8 @@ def kernel_bytes(name, N_raw, M_total, Mt, Ms, n_corr):
         "widen_kernel": 12 * M_total + 24 * M_total,
         "gather_sorted_kernel": 24 * Mt + 32 * Mt,
         "normals_kernel": 24 * Mt,  # 12 M in + 12 M out (float32 units); neighbour gathers are cache traffic
-        "icp_pass_kernel": 12 * Ms + 24 * n_corr,  # source point + gathered target point and normal
+        # 12 Ns + 24 nC per EXECUTED pass of a pair (finished pairs return at once); averaged over all launches
+        "icp_pass_kernel": icp_bytes_per_launch if icp_bytes_per_launch is not None else 12 * Ms + 24 * n_corr,
     }
     return table.get(name)
 
@@ -269,15 +270,17 @@ def main():
         n_corr = sum(r["n_corr"] for r in res)
         N_raw = 2 * n_px * P
         kern_ms = sum(v[1] for v in report.values())
+        icp_launches = max(1, report.get("icp_pass_kernel", (PIPE["icp_max_iter"] + 1, 0.0))[0] // args.steps)
+        icp_bpl = sum((r["iterations"] + 1) * (12 * r["m_source"] + 24 * r["n_corr"]) for r in res) / icp_launches
         kernels = []
         for name, (cnt, ms) in report.items():
-            b = kernel_bytes(name, N_raw, Ms + Mt, Mt, Ms, n_corr)
+            b = kernel_bytes(name, N_raw, Ms + Mt, Mt, Ms, n_corr, icp_bpl)
             kernels.append({"name": name, "launches_per_step": cnt / args.steps, "ms_per_step": ms / args.steps, "share": ms / kern_ms if kern_ms else 0.0,
                             "avg_us": 1e3 * ms / cnt, "gbps": (b / (ms / cnt * 1e-3) / 1e9) if b else None})
         top = kernels[0] if kernels else None
         roofline = None
         if top:
-            b = kernel_bytes(top["name"], N_raw, Ms + Mt, Mt, Ms, n_corr)
+            b = kernel_bytes(top["name"], N_raw, Ms + Mt, Mt, Ms, n_corr, icp_bpl)
             ach = top["gbps"] if top["gbps"] is not None else 0.0
             roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                         "peak_source": peak_src, "algorithmic_bytes_per_launch": b, "avg_launch_us": top["avg_us"], "share_of_step": top["share"]}
