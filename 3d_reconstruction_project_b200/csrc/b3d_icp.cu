@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(kIcpBlock, 4) icp_pass_kernel(IcpKernelArgs A)
     __shared__ double sm[kIcpBlock / 32][32];
     __shared__ double srow[kIcpBlock / 32][32][kIcpRow];
     __shared__ float4 s_cand[kIcpBlock / 32][kStageCap];
+    __shared__ int s_cand_pos[kIcpBlock / 32][kStageCap];
     __shared__ StageScratch s_stage[kIcpBlock / 32];
     __shared__ int s_last;
     if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
@@ -311,6 +312,9 @@ __global__ void __launch_bounds__(kIcpBlock, 4) icp_pass_kernel(IcpKernelArgs A)
     double reach1 = dmax;
     if (st->iter > 0) reach1 = fmin(dmax, fmax(3.0 * st->rmse, 0.2 * dmax));
     float4* cand = s_cand[warp];
+    int* cand_pos = s_cand_pos[warp];
+    // affine transforms (last row 0 0 0 1) need no perspective division: x / 1.0 == x exactly
+    const bool affine = sT[12] == 0.0 && sT[13] == 0.0 && sT[14] == 0.0 && sT[15] == 1.0;
     // this pair's range of warp chunks (chunks never straddle pairs) and its number of partial-sum groups: a function of
     // the pair's own chunk count only, so a pair's result does not depend on what else is in the batch
     const int32_t c0 = A.chunk_off[pair], c1 = A.chunk_off[pair + 1];
@@ -332,18 +336,34 @@ __global__ void __launch_bounds__(kIcpBlock, 4) icp_pass_kernel(IcpKernelArgs A)
             oi = point_index(sp);  // original (batch-global) source index
             const double x = sp.x, y = sp.y, z = sp.z;
             // PointCloud::Transform: (T [p,1]).xyz / w
-            const double w = sT[12] * x + sT[13] * y + sT[14] * z + sT[15];
-            px = (sT[0] * x + sT[1] * y + sT[2] * z + sT[3]) / w;
-            py = (sT[4] * x + sT[5] * y + sT[6] * z + sT[7]) / w;
-            pz = (sT[8] * x + sT[9] * y + sT[10] * z + sT[11]) / w;
+            px = sT[0] * x + sT[1] * y + sT[2] * z + sT[3];
+            py = sT[4] * x + sT[5] * y + sT[6] * z + sT[7];
+            pz = sT[8] * x + sT[9] * y + sT[10] * z + sT[11];
+            if (!affine) {
+                const double w = sT[12] * x + sT[13] * y + sT[14] * z + sT[15];
+                px /= w; py /= w; pz /= w;
+            }
         }
         // ---- correspondence: staged warp search (bit-identical to nn_within_query) ------------------------------
         double d2 = 0.0;
         int idx = 0, pos = -1;
         {
-            const double big = 1.0e300;
-            const double bl[3] = {warp_min(valid ? px : big), warp_min(valid ? py : big), warp_min(valid ? pz : big)};
-            const double bh[3] = {warp_max(valid ? px : -big), warp_max(valid ? py : -big), warp_max(valid ? pz : -big)};
+            // bounding box of the chunk: reduced in float32 (half the shuffles), widened by the float rounding of the inputs
+            const float bigf = 3.0e38f;
+            float lx = valid ? (float)px : bigf, ly = valid ? (float)py : bigf, lz = valid ? (float)pz : bigf;
+            float hx = valid ? (float)px : -bigf, hy = valid ? (float)py : -bigf, hz = valid ? (float)pz : -bigf;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o));
+                ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o));
+                lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o));
+                hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+                hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o));
+                hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+            }
+            const double wid = 2.0e-7;  // relative rounding of the float conversion, with margin
+            const double bl[3] = {(double)lx - wid * fabs((double)lx), (double)ly - wid * fabs((double)ly), (double)lz - wid * fabs((double)lz)};
+            const double bh[3] = {(double)hx + wid * fabs((double)hx), (double)hy + wid * fabs((double)hy), (double)hz + wid * fabs((double)hz)};
             for (int round = 0; round < 2; ++round) {
                 const double reach = round == 0 ? reach1 : dmax;
                 if (round == 1 && !(reach1 < dmax)) break;
@@ -351,7 +371,7 @@ __global__ void __launch_bounds__(kIcpBlock, 4) icp_pass_kernel(IcpKernelArgs A)
                 const double lo[3] = {bl[0] - pad, bl[1] - pad, bl[2] - pad}, hi[3] = {bh[0] + pad, bh[1] + pad, bh[2] + pad};
                 const double center[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
                 const float half_extent = (float)(0.5 * fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2])) * 1.0001f;
-                const int count = warp_stage_box(A.grid, pair, lo, hi, center, cand, &s_stage[warp]);
+                const int count = warp_stage_box(A.grid, pair, lo, hi, center, cand, cand_pos, &s_stage[warp]);
                 if (A.stats && lane == 0) {
                     atomicAdd(&g_icp_stats[round == 0 ? 0 : 1], 1ull);
                     if (count < 0) atomicAdd(&g_icp_stats[2], 1ull);
@@ -366,7 +386,7 @@ __global__ void __launch_bounds__(kIcpBlock, 4) icp_pass_kernel(IcpKernelArgs A)
                     break;
                 }
                 pos = -1;
-                if (valid) pos = staged_nearest(A.grid, cand, count, center, half_extent, px, py, pz, &d2, &idx);
+                if (valid) pos = staged_nearest(A.grid, cand, cand_pos, count, center, half_extent, px, py, pz, &d2, &idx);
                 __syncwarp();
                 const bool certain = !valid || !(reach < dmax) || (pos >= 0 && d2 <= reach * reach);
                 if (__all_sync(0xffffffffu, certain)) break;

@@ -37,19 +37,21 @@ __device__ __forceinline__ double warp_max(double v) {
 // prefix. Returns count, or -1 when the box touches more than kStageMaxCells cells / more than kStageCap points (the
 // caller falls back to the per-lane walk). All 32 lanes must call it with identical arguments.
 __device__ __forceinline__ int warp_stage_box(const GridView<double>& g, int cloud, const double (&lo)[3], const double (&hi)[3],
-                                              const double (&center)[3], float4* __restrict__ cand, StageScratch* __restrict__ sc) {
+                                              const double (&center)[3], float4* __restrict__ cand, int* __restrict__ cand_pos, StageScratch* __restrict__ sc) {
     const Lattice L = g.lat[cloud];
     const int lane = threadIdx.x & 31;
     const double o[3] = {L.ox, L.oy, L.oz};
     const long long k0[3] = {L.kx0, L.ky0, L.kz0};
     const long long nn[3] = {L.nx, L.ny, L.nz};
+    const double inv_cell = 1.0 / L.cell;
     long long c0[3], cn[3];
     bool empty = false;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
+        // multiply by 1/cell and widen by 1e-6 cells: a superset of the cells the exact division would give
         const double lim = 1.0e9;
-        const double u0 = fmin(fmax(floor((lo[a] - o[a]) / L.cell), -lim), lim);
-        const double u1 = fmin(fmax(floor((hi[a] - o[a]) / L.cell), -lim), lim);
+        const double u0 = fmin(fmax(floor((lo[a] - o[a]) * inv_cell - 1e-6), -lim), lim);
+        const double u1 = fmin(fmax(floor((hi[a] - o[a]) * inv_cell + 1e-6), -lim), lim);
         long long a0 = (long long)u0 - k0[a], a1 = (long long)u1 - k0[a];
         if (a1 < 0 || a0 >= nn[a]) empty = true;
         a0 = a0 < 0 ? 0 : a0;
@@ -97,6 +99,7 @@ __device__ __forceinline__ int warp_stage_box(const GridView<double>& g, int clo
         const int j = jb + lane;
         bool inside = false;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        int pp = 0;
         if (j < total) {
             int a = 0, b = ncell;  // largest a with seg_off[a] <= j
             while (b - a > 1) {
@@ -106,11 +109,16 @@ __device__ __forceinline__ int warp_stage_box(const GridView<double>& g, int clo
             const int p = sc->seg_s[a] + (j - (int)sc->seg_off[a]);
             const double4 pt = ld_point(g.pts + p);
             inside = pt.x >= lo[0] && pt.x <= hi[0] && pt.y >= lo[1] && pt.y <= hi[1] && pt.z >= lo[2] && pt.z <= hi[2];
-            v = make_float4((float)(pt.x - center[0]), (float)(pt.y - center[1]), (float)(pt.z - center[2]), __int_as_float(p));
+            const float rx = (float)(pt.x - center[0]), ry = (float)(pt.y - center[1]), rz = (float)(pt.z - center[2]);
+            v = make_float4(rx, ry, rz, fmaf(rz, rz, fmaf(ry, ry, rx * rx)));
+            pp = p;
         }
         const unsigned int m = __ballot_sync(0xffffffffu, inside);
         const int slot = kept + __popc(m & ((1u << lane) - 1u));
-        if (inside && slot < kStageCap) cand[slot] = v;
+        if (inside && slot < kStageCap) {
+            cand[slot] = v;
+            cand_pos[slot] = pp;
+        }
         kept += __popc(m);
     }
     __syncwarp();
@@ -120,40 +128,38 @@ __device__ __forceinline__ int warp_stage_box(const GridView<double>& g, int clo
     return total;
 }
 
-// rounding band of a float32 squared distance computed from offsets of magnitude <= half_extent
-__device__ __forceinline__ float stage_slack(float d2, float E) { return 4.0f * sqrtf(d2) * E + 4.0f * E * E + 2.0e-6f * d2; }
-
 // Nearest staged candidate of q (exact (d2, index) rule), or -1. d2_out / idx_out as nn_within_query.
-__device__ __forceinline__ int staged_nearest(const GridView<double>& g, const float4* __restrict__ cand, int count, const double (&center)[3],
-                                              float half_extent, double qx, double qy, double qz, double* d2_out, int* idx_out) {
-    const float fx = (float)(qx - center[0]), fy = (float)(qy - center[1]), fz = (float)(qz - center[2]);
+// Scan in float32 on t = |c|^2 - 2 q.c  (= d2 - |q|^2; offsets from the box centre, |.| <= half_extent): three FMAs per
+// candidate. The rounding error of t is below 4e-6 * half_extent^2; every candidate within twice that of the smallest t is
+// re-evaluated in float64 with the exact rule, so the result is bit-identical to the per-lane grid walk.
+__device__ __forceinline__ int staged_nearest(const GridView<double>& g, const float4* __restrict__ cand, const int* __restrict__ cand_pos,
+                                              int count, const double (&center)[3], float half_extent, double qx, double qy, double qz,
+                                              double* d2_out, int* idx_out) {
+    const float fx = -2.0f * (float)(qx - center[0]), fy = -2.0f * (float)(qy - center[1]), fz = -2.0f * (float)(qz - center[2]);
     float best = 3.0e38f, second = 3.0e38f;
     int bi = -1;
 #pragma unroll 4
     for (int i = 0; i < count; ++i) {
         const float4 c = cand[i];
-        const float dx = fx - c.x, dy = fy - c.y, dz = fz - c.z;
-        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        const bool nb = d < best;
-        second = fminf(second, fmaxf(d, best));
-        best = fminf(best, d);
+        const float t = fmaf(fx, c.x, fmaf(fy, c.y, fmaf(fz, c.z, c.w)));
+        const bool nb = t < best;
+        second = fminf(second, fmaxf(t, best));
+        best = fminf(best, t);
         bi = nb ? i : bi;
     }
     if (bi < 0) return -1;
-    const float E = 2.4e-7f * half_extent;
-    const float band = best + stage_slack(best, E);
-    int pos = __float_as_int(cand[bi].w);
+    const float band = best + 8.0e-6f * half_extent * half_extent;
+    int pos = cand_pos[bi];
     double4 pt = ld_point(g.pts + pos);
     double bd = dist2<double>(qx - pt.x, qy - pt.y, qz - pt.z);
     int bidx = point_index(pt);
-    if (second < 2.9e38f && second - stage_slack(second, E) <= band) {
+    if (second <= band) {
         // more than one candidate inside the float rounding band of the best: decide in float64
         for (int i = 0; i < count; ++i) {
             const float4 c = cand[i];
-            const float dx = fx - c.x, dy = fy - c.y, dz = fz - c.z;
-            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            if (i != bi && d - stage_slack(d, E) <= band) {
-                const int p2 = __float_as_int(c.w);
+            const float t = fmaf(fx, c.x, fmaf(fy, c.y, fmaf(fz, c.z, c.w)));
+            if (i != bi && t <= band) {
+                const int p2 = cand_pos[i];
                 const double4 q2 = ld_point(g.pts + p2);
                 const double d2 = dist2<double>(qx - q2.x, qy - q2.y, qz - q2.z);
                 const int i2 = point_index(q2);

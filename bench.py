@@ -73,6 +73,11 @@ def cpu_pair(oracle, s, t, cam):
 def cpu_time_pairs(src, tgt, cam):
     import oracle
     oracle.lib()
+    # all the host threads the process may use (torchrun exports OMP_NUM_THREADS=1 to its children)
+    try:
+        oracle.set_num_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        oracle.set_num_threads(os.cpu_count() or 1)
     t0 = time.perf_counter()
     for i in range(len(src)):
         cpu_pair(oracle, src[i], tgt[i], cam)
@@ -192,7 +197,19 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on the C-level stdout when NCCL_DEBUG is set in the environment; the contract is
+        # ONE JSON line on stdout, so fd 1 points at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     from b200recon import ops, synth
     from b200recon.context import get_context
@@ -289,9 +306,12 @@ def main():
         pipe_bytes = (14 * N_raw + (12 * N_raw + 12 * (Ms + Mt)) + 20 * Mt + 24 * Mt + sum((it + 1) for it in iters) / max(1, len(iters)) * (12 * Ms + 24 * n_corr))
         pipe_gbps = pipe_bytes / (ms_dev / args.steps * 1e-3) / 1e9
 
-        cpu_n = max(1, min(args.cpu_sample, P))
-        cpu_s, cores = cpu_time_pairs(src[:cpu_n], tgt[:cpu_n], cam)
-        cpu_v = cpu_n / cpu_s
+        cpu_base = None
+        if world == 1:  # the CPU arm is timed on rank 0 at N = 1 only
+            cpu_n = max(1, min(args.cpu_sample, P))
+            cpu_s, cores = cpu_time_pairs(src[:cpu_n], tgt[:cpu_n], cam)
+            cpu_base = {"value": cpu_n / cpu_s, "unit": "pairs/s", "cores": cores, "kind": "port",
+                        "sample": f"{cpu_n} pairs of the same batch, oracle C++/OpenMP restatement of the Open3D CPU path, {cpu_s:.1f} s"}
         out = {
             "metric": "icp_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -305,8 +325,7 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "pipeline_roofline": {"achieved": pipe_gbps, "peak": peak, "unit": "GB/s", "frac": pipe_gbps / peak, "algorithmic_bytes_per_step": pipe_bytes},
-            "cpu_baseline": {"value": cpu_v, "unit": "pairs/s", "cores": cores, "kind": "port",
-                             "sample": f"{cpu_n} pairs of the same batch, oracle C++/OpenMP restatement of the Open3D CPU path, {cpu_s:.1f} s"},
+            "cpu_baseline": cpu_base,
             "kernels": kernels[:12],
             "profiled_ms_per_step": ms_prof / args.steps,
         }

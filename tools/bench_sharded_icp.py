@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""BASELINE config 5: ONE large cloud, point-to-plane ICP sharded by source points over the GPUs of one box, the 29
+normal-equation sums all-reduced (NCCL over NVLink) once per pass.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tools/bench_sharded_icp.py --side 3162 [--iters 10]
+
+--side S: the cloud is an S x S height-field grid (S = 10000 -> 1e8 points). Target = T * source with the
+C1 transform; every rank holds the whole target (replicated grid) and a contiguous slice of the source. Prints one JSON line
+(rank 0): ms per pass (device time, max over ranks), Mpoints/s, the share of the all-reduce, transform error vs truth.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--side", type=int, default=3162)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--dmax", type=float, default=0.005)
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from b200recon import distributed as D, ops, synth
+    src, nrm = synth.height_field_cloud(a.side, seed=4000)
+    T = synth.rigid(0.0003, -0.0002, 0.0004, (0.0008, -0.0006, 0.001))  # a motion well inside d_max = 5 mm
+    R = T[:3, :3]
+    tgt = src @ R.T + T[:3, 3]
+    tn = nrm @ R.T
+    n = len(src)
+    lo, hi = D.shard_range(n, rank, world)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sh = D.ShardedICP(1, src[lo:hi], n, tgt, a.dmax, tgt_normals=tn, rel_fitness=0.0, rel_rmse=0.0, max_iter=a.iters, device=local)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    acc_ms, red_ms, passes = 0.0, 0.0, 0
+    if world > 1:
+        dist.barrier()
+    while True:
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        sums = sh.accumulate()
+        e1.record()
+        D.all_reduce_sums(sums)
+        e2.record()
+        done = sh.update()
+        torch.cuda.synchronize()
+        acc_ms += e0.elapsed_time(e1)
+        red_ms += e1.elapsed_time(e2)
+        passes += 1
+        if done:
+            break
+    res = sh.finish()
+    t = torch.tensor([acc_ms, red_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    acc_ms, red_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        rot, tr = synth.transform_error(res["transformation"], T)
+        per_pass = (acc_ms + red_ms) / passes
+        print(json.dumps({"config": "config5: one cloud sharded by source points, point-to-plane, all-reduce of 29 doubles per pass",
+                          "n_points": n, "n_gpus": world, "passes": passes, "ms_per_pass": per_pass, "accumulate_ms_per_pass": acc_ms / passes,
+                          "allreduce_ms_per_pass": red_ms / passes, "allreduce_share": red_ms / (acc_ms + red_ms),
+                          "mpoints_per_sec": n / (per_pass * 1e-3) / 1e6, "setup_s": t_setup, "fitness": res["fitness"],
+                          "inlier_rmse": res["inlier_rmse"], "rot_err_rad": rot, "trans_err_m": tr, "iterations": res["iterations"]}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
