@@ -8,7 +8,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200recon.so")
+# B3D_LIB: alternative build of the same library (A/B experiments); default is the in-tree build
+LIB_PATH = os.environ.get("B3D_LIB") or os.path.join(_HERE, "libb200recon.so")
 
 OK = 0
 E_INVALID, E_CUDA, E_RANGE, E_NOMEM, E_STATE = -1, -2, -3, -4, -5

@@ -1,0 +1,161 @@
+// b3d_chunks.cu -- compact warp chunks of query points (used by the staged searches of the ICP pass and of the normals).
+#include "b3d_common.cuh"
+#include "b3d_scan.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+namespace b3d {
+namespace {
+
+__device__ __forceinline__ unsigned long long spread3(unsigned long long v) {  // 21 bits -> every third bit
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x1f00000000ffffull;
+    v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+
+// Morton key of the (transformed) query on a quarter-cell lattice of its cloud's search grid: consecutive keys are
+// spatially compact, so the 32 queries of a warp fit a small box (and stay compact under rigid updates).
+__global__ void __launch_bounds__(256) chunk_key_kernel(const double* __restrict__ pts, const int32_t* __restrict__ off, const double* __restrict__ transforms,
+                                                        int transform_stride, const Lattice* __restrict__ lat, int shift, uint64_t* __restrict__ keys,
+                                                        uint32_t* __restrict__ order) {
+    const int cloud = blockIdx.y;
+    const Lattice L = lat[cloud];
+    double T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    if (transforms != nullptr)
+        for (int k = 0; k < 12; ++k) T[k] = transforms[(int64_t)cloud * transform_stride + k];
+    const int32_t s0 = off[cloud], s1 = off[cloud + 1];
+    const double q = L.cell * 0.25;
+    for (int32_t i = s0 + blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += gridDim.x * blockDim.x) {
+        const double x = pts[3 * (int64_t)i], y = pts[3 * (int64_t)i + 1], z = pts[3 * (int64_t)i + 2];
+        const double px = T[0] * x + T[1] * y + T[2] * z + T[3];
+        const double py = T[4] * x + T[5] * y + T[6] * z + T[7];
+        const double pz = T[8] * x + T[9] * y + T[10] * z + T[11];
+        const double hi = 2097151.0;  // 2^21 - 1
+        // one cell of margin below the lattice origin; everything farther out clamps to the border
+        const double ux = fmin(fmax(floor((px - L.ox) / q) + 4.0, 0.0), hi), uy = fmin(fmax(floor((py - L.oy) / q) + 4.0, 0.0), hi),
+                     uz = fmin(fmax(floor((pz - L.oz) / q) + 4.0, 0.0), hi);
+        const unsigned long long m = (spread3((unsigned long long)ux) << 2) | (spread3((unsigned long long)uy) << 1) | spread3((unsigned long long)uz);
+        keys[i] = ((unsigned long long)cloud << shift) | (m & ((1ull << shift) - 1ull));
+        order[i] = (uint32_t)i;
+    }
+}
+
+// a new chunk starts every 32 sorted points (counted from the cloud start) and wherever the Morton block
+// (2^level quarter-cells on a side; the cloud id sits above it) changes
+struct ChunkPred {
+    const uint64_t* keys;
+    const int32_t* off;
+    int shift;
+    int block_bits;  // 3 * level: Morton bits below the block id
+    __device__ __forceinline__ bool operator()(int64_t i) const {
+        const uint64_t k = keys[i];
+        const int64_t rel = i - off[(int)(k >> shift)];
+        return (rel & 31) == 0 || (k >> block_bits) != (keys[i - 1] >> block_bits);
+    }
+};
+struct ChunkEmit {
+    int32_t* chunk_start;
+    __device__ __forceinline__ void operator()(int64_t i, int64_t slot) const { chunk_start[slot] = (int32_t)i; }
+};
+__global__ void chunk_sentinel_kernel(int32_t* chunk_start, const int64_t* n_chunks, int32_t n) { chunk_start[*n_chunks] = n; }
+
+// chunk_off[b] = first chunk of cloud b (chunk_off[B] = n_chunks)
+__global__ void chunk_ranges_kernel(const int32_t* __restrict__ chunk_start, const int64_t* __restrict__ n_chunks_d, const int32_t* __restrict__ off, int B,
+                                    int32_t* __restrict__ chunk_off) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > B) return;
+    const int32_t key = off[b];
+    int lo = 0, hi = (int)*n_chunks_d;
+    while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if (chunk_start[m] < key) lo = m + 1; else hi = m;
+    }
+    chunk_off[b] = lo;
+}
+
+__global__ void __launch_bounds__(256) chunk_gather_kernel(const double* __restrict__ pts, const uint32_t* __restrict__ order, int32_t n,
+                                                           double4* __restrict__ out) {
+    for (int32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t i = order[j];
+        out[j] = make_double4(pts[3 * (int64_t)i], pts[3 * (int64_t)i + 1], pts[3 * (int64_t)i + 2], __longlong_as_double((long long)i));
+    }
+}
+
+}  // namespace
+
+int build_query_chunks(b3d_ctx* ctx, const double* pts, const int32_t* off_d, const std::vector<int32_t>& off_h, const SpatialSort& lattices,
+                       const double* transforms, int transform_stride, QueryChunks* out) {
+    // Morton block level: blocks of 2^level quarter-cells should hold a few chunks' worth of points (surface model:
+    // points per block ~ occupancy * (cells per side)^2), so that most chunks are full; level 3 = 2 cells per side
+    int level = 3;
+    {
+        const double occ = (double)lattices.n / (double)std::max<int64_t>(1, lattices.n_runs);
+        const double cells_per_side = std::sqrt(96.0 / std::max(occ, 0.25));
+        level = (int)std::lround(2.0 + std::log2(std::max(cells_per_side, 1.0)));
+        level = std::min(std::max(level, 2), 7);
+        if (const char* e = getenv("B3D_CHUNK_LEVEL")) level = atoi(e);
+    }
+
+    const int B = (int)off_h.size() - 1;
+    const int32_t n = off_h[B];
+    out->chunk_off_h.assign(B + 1, 0);
+    out->n_chunks = 0;
+    out->most = 0;
+    B3D_TRY(out->pts.alloc(ctx, (size_t)std::max(n, 1)));
+    B3D_TRY(out->chunk_start.alloc(ctx, (size_t)n + 1));
+    B3D_TRY(out->chunk_off.alloc(ctx, (size_t)B + 1));
+    if (n == 0) {
+        B3D_CUDA(cudaMemsetAsync(out->chunk_start.p, 0, sizeof(int32_t), ctx->stream));
+        B3D_CUDA(cudaMemsetAsync(out->chunk_off.p, 0, (size_t)(B + 1) * sizeof(int32_t), ctx->stream));
+        return B3D_OK;
+    }
+    // Morton bits: 3 x bits(4 * cells per axis + margin), capped at 3 x 21; coordinates beyond that wrap (still correct, less compact)
+    int64_t max_axis = 1, longest = 0;
+    for (int b = 0; b < B; ++b) {
+        const Lattice& L = lattices.lat_h[b];
+        max_axis = std::max<int64_t>(max_axis, std::max(std::max(L.nx, L.ny), L.nz));
+        longest = std::max<int64_t>(longest, off_h[b + 1] - off_h[b]);
+    }
+    int axis_bits = 1;
+    while (axis_bits < 21 && (1ll << axis_bits) < 4 * max_axis + 8) ++axis_bits;
+    int bbits = 0;
+    while ((1ll << bbits) < B) ++bbits;
+    while (3 * axis_bits + bbits > 63) --axis_bits;
+    const int shift = 3 * axis_bits;
+    DevBuf<uint64_t> k_in, k_out;
+    DevBuf<uint32_t> o_in, o_out;
+    B3D_TRY(k_in.alloc(ctx, n));
+    B3D_TRY(k_out.alloc(ctx, n));
+    B3D_TRY(o_in.alloc(ctx, n));
+    B3D_TRY(o_out.alloc(ctx, n));
+    const int kb = (int)std::min<int64_t>((longest + 255) / 256, std::max(1, ctx->sm_count * 16 / B));
+    B3D_LAUNCH(ctx, chunk_key_kernel, dim3(std::max(1, kb), B), 256, 0, pts, off_d, transforms, transform_stride, lattices.lat.p, shift, k_in.p, o_in.p);
+    size_t tmp_bytes = 0;
+    B3D_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.p, k_out.p, o_in.p, o_out.p, n, 0, shift + bbits, ctx->stream));
+    DevBuf<uint8_t> tmp;
+    B3D_TRY(tmp.alloc(ctx, tmp_bytes));
+    if (ctx->profiling) ctx->prof_begin("cub_radix_sort_pairs");
+    B3D_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k_in.p, k_out.p, o_in.p, o_out.p, n, 0, shift + bbits, ctx->stream));
+    if (ctx->profiling) ctx->prof_end();
+    ctx->lib_launches += 1;
+    B3D_LAUNCH(ctx, chunk_gather_kernel, ctx->grid_for(n, 256, 1, 8), 256, 0, pts, o_out.p, n, out->pts.p);
+    DevBuf<int64_t> n_chunks_d;
+    B3D_TRY(n_chunks_d.alloc(ctx, 1));
+    B3D_TRY(compact(ctx, ChunkPred{k_out.p, off_d, shift, std::min(3 * level, shift)}, ChunkEmit{out->chunk_start.p}, n, n_chunks_d.p));
+    B3D_LAUNCH(ctx, chunk_sentinel_kernel, 1, 1, 0, out->chunk_start.p, n_chunks_d.p, n);
+    B3D_LAUNCH(ctx, chunk_ranges_kernel, (B + 1 + 127) / 128, 128, 0, out->chunk_start.p, n_chunks_d.p, off_d, B, out->chunk_off.p);
+    B3D_TRY(ctx->download(out->chunk_off_h.data(), out->chunk_off.p, (size_t)(B + 1) * sizeof(int32_t)));
+    out->n_chunks = out->chunk_off_h[B];
+    for (int b = 0; b < B; ++b) out->most = std::max(out->most, out->chunk_off_h[b + 1] - out->chunk_off_h[b]);
+    return B3D_OK;
+}
+
+}  // namespace b3d

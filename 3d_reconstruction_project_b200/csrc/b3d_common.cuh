@@ -408,6 +408,21 @@ struct Grid {
 template <typename T>
 int grid_build(b3d_ctx* ctx, const T* xyz, const Segments& seg, double cell, const std::vector<double>* bounds_h, Grid<T>* out);
 
+// Queries re-ordered along a Morton curve (quarter-cell lattice of a search grid) and cut into warp chunks: <= 32
+// consecutive points that never span more than one Morton block (sized to hold a few chunks) and never straddle clouds; cut points are relative
+// to the cloud start, so the chunking of a cloud does not depend on the rest of the batch.
+struct QueryChunks {
+    DevBuf<double4> pts;          // [n] queries in Morton order, .w = original (batch-global) index
+    DevBuf<int32_t> chunk_start;  // [n_chunks + 1]
+    DevBuf<int32_t> chunk_off;    // [B + 1] first chunk of every cloud
+    std::vector<int32_t> chunk_off_h;
+    int32_t n_chunks = 0;
+    int32_t most = 0;  // largest chunk count of a single cloud
+};
+// transforms: device array of B row-major 4x4 matrices applied before the key is taken (stride in doubles), or NULL
+int build_query_chunks(b3d_ctx* ctx, const double* pts, const int32_t* off_d, const std::vector<int32_t>& off_h, const SpatialSort& lattices,
+                       const double* transforms, int transform_stride, QueryChunks* out);
+
 // Chooses the cell size for (k, radius) searches (one trial build measures the occupancy) and builds the grid.
 // rmax_out: rings a query has to walk (radius searches), or the ring budget of a k-nearest walk.
 template <typename T>

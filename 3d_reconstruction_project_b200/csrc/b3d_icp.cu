@@ -285,8 +285,11 @@ struct IcpKernelArgs {
 // 32 queries of a warp share their cells: the hash probes and candidate loads hit L1 and the lanes take similar paths.
 // Every lane produces its 29 contributions; a transpose-reduce leaves value j's warp total in lane j, which is the only
 // accumulator a thread keeps (instead of 29 live doubles across the search loop).
+#ifndef B3D_ICP_MIN_BLOCKS
+#define B3D_ICP_MIN_BLOCKS 4
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(kIcpBlock, 4) icp_pass_kernel(IcpKernelArgs A) {
+__global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel(IcpKernelArgs A) {
     const int pair = blockIdx.y;
     IcpPairState* st = A.state + pair;
     if (st->done) return;
@@ -504,80 +507,6 @@ __global__ void __launch_bounds__(kIcpBlock, 4) icp_pass_kernel(IcpKernelArgs A)
     }
 }
 
-__device__ __forceinline__ unsigned long long spread3(unsigned long long v) {  // 21 bits -> every third bit
-    v &= 0x1fffffull;
-    v = (v | (v << 32)) & 0x1f00000000ffffull;
-    v = (v | (v << 16)) & 0x1f0000ff0000ffull;
-    v = (v | (v << 8)) & 0x100f00f00f00f00full;
-    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
-    v = (v | (v << 2)) & 0x1249249249249249ull;
-    return v;
-}
-
-// Morton key of the (transformed) source point on a quarter-cell lattice of the pair's target grid: consecutive keys are
-// spatially compact, so the 32 queries of a warp fit a small box (and stay compact under the rigid updates of later passes).
-__global__ void __launch_bounds__(256) icp_src_key_kernel(const double* __restrict__ src, const int32_t* __restrict__ src_off,
-                                                          const IcpPairState* __restrict__ state, const Lattice* __restrict__ lat, int shift,
-                                                          uint64_t* __restrict__ keys, uint32_t* __restrict__ order) {
-    const int pair = blockIdx.y;
-    const Lattice L = lat[pair];
-    const double* T = state[pair].T;
-    const int32_t s0 = src_off[pair], s1 = src_off[pair + 1];
-    const double q = L.cell * 0.25;
-    for (int32_t i = s0 + blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += gridDim.x * blockDim.x) {
-        const double x = src[3 * (int64_t)i], y = src[3 * (int64_t)i + 1], z = src[3 * (int64_t)i + 2];
-        const double px = T[0] * x + T[1] * y + T[2] * z + T[3];
-        const double py = T[4] * x + T[5] * y + T[6] * z + T[7];
-        const double pz = T[8] * x + T[9] * y + T[10] * z + T[11];
-        const double hi = 2097151.0;  // 2^21 - 1
-        // one cell of margin below the lattice origin; everything farther out clamps to the border
-        const double ux = fmin(fmax(floor((px - L.ox) / q) + 4.0, 0.0), hi), uy = fmin(fmax(floor((py - L.oy) / q) + 4.0, 0.0), hi),
-                     uz = fmin(fmax(floor((pz - L.oz) / q) + 4.0, 0.0), hi);
-        const unsigned long long m = (spread3((unsigned long long)ux) << 2) | (spread3((unsigned long long)uy) << 1) | spread3((unsigned long long)uz);
-        keys[i] = ((unsigned long long)pair << shift) | (m & ((1ull << shift) - 1ull));
-        order[i] = (uint32_t)i;
-    }
-}
-
-// warp chunks: a new chunk starts every 32 sorted points and wherever the Morton block (8 x 8 x 8 quarter-cells = 2 cells
-// on a side; the pair id sits above it) changes, so a chunk's 32 queries never span more than one such block
-struct ChunkPred {
-    const uint64_t* keys;
-    const int32_t* src_off;
-    int shift;
-    __device__ __forceinline__ bool operator()(int64_t i) const {
-        const uint64_t k = keys[i];
-        const int64_t rel = i - src_off[(int)(k >> shift)];  // position inside the pair: batch-invariant chunking
-        return (rel & 31) == 0 || (k >> 9) != (keys[i - 1] >> 9);
-    }
-};
-// chunk_off[p] = first chunk of pair p (chunk_off[P] = n_chunks)
-__global__ void icp_chunk_ranges_kernel(const int32_t* __restrict__ chunk_start, const int64_t* __restrict__ n_chunks_d,
-                                        const int32_t* __restrict__ src_off, int P, int32_t* __restrict__ chunk_off) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p > P) return;
-    const int32_t key = src_off[p];
-    int a = 0, b = (int)*n_chunks_d;
-    while (a < b) {
-        const int m = (a + b) >> 1;
-        if (chunk_start[m] < key) a = m + 1; else b = m;
-    }
-    chunk_off[p] = a;
-}
-struct ChunkEmit {
-    int32_t* chunk_start;
-    __device__ __forceinline__ void operator()(int64_t i, int64_t slot) const { chunk_start[slot] = (int32_t)i; }
-};
-__global__ void icp_chunk_sentinel_kernel(int32_t* chunk_start, const int64_t* n_chunks, int32_t ns) { chunk_start[*n_chunks] = ns; }
-
-__global__ void __launch_bounds__(256) icp_gather_src_kernel(const double* __restrict__ src, const uint32_t* __restrict__ order, int32_t n,
-                                                             double4* __restrict__ out) {
-    for (int32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        const uint32_t i = order[j];
-        out[j] = make_double4(src[3 * (int64_t)i], src[3 * (int64_t)i + 1], src[3 * (int64_t)i + 2], __longlong_as_double((long long)i));
-    }
-}
-
 __global__ void icp_finalize_kernel(int kind, const double* __restrict__ sums, const int32_t* __restrict__ src_off, const int64_t* __restrict__ ns_global,
                                     double rel_fitness, double rel_rmse, int max_iter, IcpPairState* state, int P) {
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
@@ -655,8 +584,6 @@ __global__ void __launch_bounds__(256) transform_kernel(const double* __restrict
 
 int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWork* w) {
     const int P = pb.P;
-    int64_t longest = 0;
-    for (int p = 0; p < P; ++p) longest = std::max<int64_t>(longest, pb.src_off_h[p + 1] - pb.src_off_h[p]);
     B3D_TRY(w->state.alloc(ctx, P));
     B3D_TRY(w->sums.alloc(ctx, (size_t)P * kIcpSums));
     DevBuf<double> init_d;
@@ -667,64 +594,12 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
     B3D_LAUNCH(ctx, icp_init_state_kernel, (P + 127) / 128, 128, 0, w->state.p, init_h ? init_d.p : (const double*)nullptr, P);
     const Grid<double>& g = *pb.tgt_grid;
     const int32_t nt = (int32_t)g.sort.n;
-    // order the source points by the target cell they start in (coherent warps in every pass)
-    {
-        const int32_t ns = pb.src_off_h[P];
-        // Morton bits: 3 x bits(4 * cells per axis + margin), capped at 3 x 21; coordinates beyond that clamp (still correct, less compact)
-        int64_t max_axis = 1;
-        for (int p = 0; p < P; ++p) {
-            const Lattice& L = g.sort.lat_h[p];
-            max_axis = std::max<int64_t>(max_axis, std::max(std::max(L.nx, L.ny), L.nz));
-        }
-        int axis_bits = 1;
-        while (axis_bits < 21 && (1ll << axis_bits) < 4 * max_axis + 8) ++axis_bits;
-        int pbits = 0;
-        while ((1ll << pbits) < P) ++pbits;
-        while (3 * axis_bits + pbits > 63) --axis_bits;
-        const int shift = 3 * axis_bits;
-        B3D_TRY(w->src_sorted.alloc(ctx, (size_t)std::max(ns, 1)));
-        if (ns > 0) {
-            DevBuf<uint64_t> k_in, k_out;
-            DevBuf<uint32_t> o_in, o_out;
-            B3D_TRY(k_in.alloc(ctx, ns));
-            B3D_TRY(k_out.alloc(ctx, ns));
-            B3D_TRY(o_in.alloc(ctx, ns));
-            B3D_TRY(o_out.alloc(ctx, ns));
-            const int kb = (int)std::min<int64_t>((longest + 255) / 256, std::max(1, ctx->sm_count * 16 / P));
-            B3D_LAUNCH(ctx, icp_src_key_kernel, dim3(std::max(1, kb), P), 256, 0, pb.src, pb.src_off, w->state.p, g.sort.lat.p, shift, k_in.p, o_in.p);
-            size_t tmp_bytes = 0;
-            B3D_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.p, k_out.p, o_in.p, o_out.p, ns, 0, shift + pbits, ctx->stream));
-            DevBuf<uint8_t> tmp;
-            B3D_TRY(tmp.alloc(ctx, tmp_bytes));
-            if (ctx->profiling) ctx->prof_begin("cub_radix_sort_pairs");
-            B3D_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k_in.p, k_out.p, o_in.p, o_out.p, ns, 0, shift + pbits, ctx->stream));
-            if (ctx->profiling) ctx->prof_end();
-            ctx->lib_launches += 1;
-            B3D_LAUNCH(ctx, icp_gather_src_kernel, ctx->grid_for(ns, 256, 1, 8), 256, 0, pb.src, o_out.p, ns, w->src_sorted.p);
-            DevBuf<int64_t> n_chunks_d;
-            B3D_TRY(n_chunks_d.alloc(ctx, 1));
-            B3D_TRY(w->chunk_start.alloc(ctx, (size_t)ns + 1));
-            B3D_TRY(compact(ctx, ChunkPred{k_out.p, pb.src_off, shift}, ChunkEmit{w->chunk_start.p}, ns, n_chunks_d.p));
-            B3D_LAUNCH(ctx, icp_chunk_sentinel_kernel, 1, 1, 0, w->chunk_start.p, n_chunks_d.p, ns);
-            B3D_TRY(w->chunk_off.alloc(ctx, (size_t)P + 1));
-            B3D_LAUNCH(ctx, icp_chunk_ranges_kernel, (P + 1 + 127) / 128, 128, 0, w->chunk_start.p, n_chunks_d.p, pb.src_off, P, w->chunk_off.p);
-            std::vector<int32_t> coff(P + 1);
-            B3D_TRY(ctx->download(coff.data(), w->chunk_off.p, (size_t)(P + 1) * sizeof(int32_t)));
-            w->n_chunks = coff[P];
-            int32_t most = 0;
-            for (int p = 0; p < P; ++p) most = std::max(most, coff[p + 1] - coff[p]);
-            // partial-sum groups per pair depend only on that pair's own chunk count (results do not depend on the batch)
-            w->blocks = std::max(1, std::min((most + kIcpBlock / 32 - 1) / (kIcpBlock / 32), kIcpMaxGroups));
-        } else {
-            B3D_TRY(w->chunk_start.alloc(ctx, 1));
-            B3D_CUDA(cudaMemsetAsync(w->chunk_start.p, 0, sizeof(int32_t), ctx->stream));
-            B3D_TRY(w->chunk_off.alloc(ctx, (size_t)P + 1));
-            B3D_CUDA(cudaMemsetAsync(w->chunk_off.p, 0, (size_t)(P + 1) * sizeof(int32_t), ctx->stream));
-            w->n_chunks = 0;
-            w->blocks = 1;
-        }
-        B3D_TRY(w->partial.alloc(ctx, (size_t)P * w->blocks * kIcpSums));
-    }
+    // order the source points along a Morton curve of the target lattice and cut them into compact warp chunks
+    B3D_TRY(build_query_chunks(ctx, pb.src, pb.src_off, pb.src_off_h, g.sort, reinterpret_cast<const double*>(w->state.p),
+                               (int)(sizeof(IcpPairState) / sizeof(double)), &w->chunks));
+    // partial-sum groups per pair depend only on that pair's own chunk count (results do not depend on the batch)
+    w->blocks = std::max(1, std::min((w->chunks.most + kIcpBlock / 32 - 1) / (kIcpBlock / 32), kIcpMaxGroups));
+    B3D_TRY(w->partial.alloc(ctx, (size_t)P * w->blocks * kIcpSums));
     if (pb.kind == B3D_ICP_POINT_TO_PLANE) {
         B3D_TRY(w->tgt_nrm_sorted.alloc(ctx, (size_t)nt * 3));
         B3D_LAUNCH(ctx, gather_by_sorted_kernel, ctx->grid_for((int64_t)nt * 3, 256, 1, 8), 256, 0, g.pts.p, nt, pb.tgt_normals, 3, w->tgt_nrm_sorted.p);
@@ -738,10 +613,10 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
 static IcpKernelArgs make_args(const IcpProblem& pb, IcpWork* w, int32_t* corr, bool fused) {
     IcpKernelArgs A;
     A.kind = pb.kind;
-    A.src_sorted = w->src_sorted.p;
-    A.chunk_start = w->chunk_start.p;
-    A.chunk_off = w->chunk_off.p;
-    A.n_chunks = w->n_chunks;
+    A.src_sorted = w->chunks.pts.p;
+    A.chunk_start = w->chunks.chunk_start.p;
+    A.chunk_off = w->chunks.chunk_off.p;
+    A.n_chunks = w->chunks.n_chunks;
     A.src_cov = pb.src_cov;
     A.src_off = pb.src_off;
     A.ns_global = pb.ns_global;

@@ -41,10 +41,7 @@ struct IcpWork {
     DevBuf<double> partial;      // [P][blocks][kIcpSums]
     DevBuf<double> sums;         // [P][kIcpSums]
     DevBuf<double> tgt_nrm_sorted, tgt_cov_sorted;
-    DevBuf<double4> src_sorted;  // source points in Morton order of the target lattice, .w = original index
-    DevBuf<int32_t> chunk_start; // [n_chunks + 1] warp chunks of the sorted source (<= 32 points, spatially compact)
-    DevBuf<int32_t> chunk_off;   // [P + 1] first chunk of every pair
-    int32_t n_chunks = 0;
+    QueryChunks chunks;  // sources in Morton order of the target lattice, cut into compact warp chunks
     DevBuf<int64_t> ns_global;
     int blocks = 1;
 };

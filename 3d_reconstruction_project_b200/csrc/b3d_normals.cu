@@ -3,8 +3,10 @@
 #include "b3d_common.cuh"
 #include "b3d_scan.cuh"
 #include "b3d_search.cuh"
+#include "b3d_stage.cuh"
 
 #include <cmath>
+#include <type_traits>
 
 namespace b3d {
 
@@ -75,10 +77,12 @@ namespace {
 // TENSOR (T = float) : two-pass centred covariance in double, /(n-1), eigen in float
 template <typename T, int KMAX, bool TENSOR>
 __global__ void __launch_bounds__(128) normals_kernel(GridView<T> g, const uint64_t* __restrict__ keys, const int32_t* __restrict__ off, int k,
-                                                      bool use_radius, T r2, int rmax, const T* __restrict__ prior, T* __restrict__ normals) {
+                                                      bool use_radius, T r2, int rmax, const T* __restrict__ prior, T* __restrict__ normals,
+                                                      const uint8_t* __restrict__ need) {
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= g.n) return;
     const typename PointT<T>::vec4 q = ld_point(g.pts + pos);
+    if (need != nullptr && need[point_index(q)] == 0) return;  // already done by the staged kernel
     const int cloud = (int)(keys[pos] >> g.shift);
     TopK<T, KMAX> tk;
     knn_hybrid_query<T, KMAX>(g, off, cloud, q.x, q.y, q.z, k, use_radius, r2, rmax, tk);
@@ -138,6 +142,150 @@ __global__ void __launch_bounds__(128) normals_kernel(GridView<T> g, const uint6
     normals[3 * oi] = nrm.x;
     normals[3 * oi + 1] = nrm.y;
     normals[3 * oi + 2] = nrm.z;
+}
+
+// ---- staged legacy normals (radius searches, k <= kNrmList) --------------------------------------------------------------
+// One warp per compact chunk of <= 32 Morton-ordered points (build_query_chunks). The warp stages every point inside the
+// chunk's bounding box + radius in shared memory (b3d_stage.cuh); each lane scans that list in float32, confirms the
+// borderline candidates in float64 (exact d2 < r2 rule), and keeps the indices of its neighbours in a small shared list.
+// Neighbour SETS are exact; the nine raw moments are then summed in staged order (the reference sums in distance order:
+// same set, same arithmetic, a different order of float64 additions). Lanes that would need a k-nearest cut (more than k
+// neighbours inside the radius) or whose chunk overflows the staging buffers are flagged in `need` and are redone by the
+// per-lane kernel afterwards.
+constexpr int kNrmBlock = 128;
+constexpr int kNrmList = 32;   // neighbours per lane kept in shared memory (k <= 32 on this path)
+constexpr int kNrmCap = 192;   // staged candidates per warp
+
+struct NrmWarpSmem {
+    float4 cand[kNrmCap];
+    double xyz[3 * kNrmCap];
+    int pos[kNrmCap];
+    unsigned int list[32][kNrmList + 1];  // per lane: (float bits of d2 with the low 9 bits replaced by the candidate id), ascending
+    StageScratch stage;
+};
+
+__global__ void __launch_bounds__(kNrmBlock) normals_staged_kernel(GridView<double> g, const double4* __restrict__ qpts,
+                                                                  const int32_t* __restrict__ chunk_start, const int32_t* __restrict__ chunk_off,
+                                                                  int B, int n_chunks, int k, double radius, double r2,
+                                                                  const double* __restrict__ prior, double* __restrict__ normals,
+                                                                  uint8_t* __restrict__ need) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    NrmWarpSmem& S = reinterpret_cast<NrmWarpSmem*>(smem_raw)[warp];
+    unsigned int* list = S.list[lane];
+    for (int c = blockIdx.x * (kNrmBlock / 32) + warp; c < n_chunks; c += gridDim.x * (kNrmBlock / 32)) {
+        // cloud of this chunk: last b with chunk_off[b] <= c
+        int lo_b = 0, hi_b = B;
+        while (hi_b - lo_b > 1) {
+            const int m = (lo_b + hi_b) >> 1;
+            if (chunk_off[m] <= c) lo_b = m; else hi_b = m;
+        }
+        const int cloud = lo_b;
+        const int32_t i = chunk_start[c] + lane;
+        const bool valid = i < chunk_start[c + 1];
+        double qx = 0, qy = 0, qz = 0;
+        int oi = 0;
+        if (valid) {
+            const double4 q = ld_point(qpts + i);
+            qx = q.x; qy = q.y; qz = q.z;
+            oi = point_index(q);
+        }
+        const float bigf = 3.0e38f;
+        float lx = valid ? (float)qx : bigf, ly = valid ? (float)qy : bigf, lz = valid ? (float)qz : bigf;
+        float hx = valid ? (float)qx : -bigf, hy = valid ? (float)qy : -bigf, hz = valid ? (float)qz : -bigf;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o));
+            ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o));
+            lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o));
+            hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o));
+            hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o));
+            hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+        }
+        const double wid = 2.0e-7;
+        const double pad = radius * (1.0 + 1e-9) + 1e-12;
+        const double lo[3] = {(double)lx - wid * fabs((double)lx) - pad, (double)ly - wid * fabs((double)ly) - pad, (double)lz - wid * fabs((double)lz) - pad};
+        const double hi[3] = {(double)hx + wid * fabs((double)hx) + pad, (double)hy + wid * fabs((double)hy) + pad, (double)hz + wid * fabs((double)hz) + pad};
+        const double center[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
+        const float H = (float)(0.5 * fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2])) * 1.0001f;
+        const int count = warp_stage_box(g, cloud, lo, hi, center, S.cand, S.pos, &S.stage, kNrmCap, S.xyz);
+        if (count < 0) {
+            if (valid) need[oi] = 1;
+            continue;
+        }
+        // ---- scan: neighbours with d2 < r2, kept sorted by (float) distance -------------------------------------------
+        const float rx = (float)(qx - center[0]), ry = (float)(qy - center[1]), rz = (float)(qz - center[2]);
+        const float fx = -2.0f * rx, fy = -2.0f * ry, fz = -2.0f * rz;
+        const float qq = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
+        const float band = 8.0e-6f * H * H + 4.0e-7f * (float)r2;
+        const float r2f = (float)r2;
+        int n = 0;
+        bool spill = false;
+        if (valid) {
+            for (int j = 0; j < count; ++j) {
+                const float4 cj = S.cand[j];
+                const float d2f = fmaf(fx, cj.x, fmaf(fy, cj.y, fmaf(fz, cj.z, cj.w))) + qq;
+                bool acc = d2f < r2f - band;
+                if (!acc && d2f <= r2f + band)
+                    acc = dist2<double>(qx - S.xyz[3 * j], qy - S.xyz[3 * j + 1], qz - S.xyz[3 * j + 2]) < r2;
+                if (acc) {
+                    if (n < kNrmList) list[n] = (__float_as_uint(fmaxf(d2f, 0.0f)) & ~511u) | (unsigned int)j;
+                    else spill = true;
+                    ++n;
+                }
+            }
+        }
+        __syncwarp();
+        if (!valid) continue;
+        if (spill || n > k) {
+            need[oi] = 1;  // needs the k nearest of more than k in-radius points: per-lane kernel
+            continue;
+        }
+        // order by distance (the reference accumulates its moments in (d2, index) order): insertion sort of the short list,
+        // all lanes of the warp sorting their own lists at the same time
+        for (int a = 1; a < n; ++a) {
+            const unsigned int key = list[a];
+            int m = a;
+            while (m > 0 && list[m - 1] > key) {
+                list[m] = list[m - 1];
+                --m;
+            }
+            list[m] = key;
+        }
+        // ---- raw-moment covariance over the neighbour set, closed-form eigenvector ------------------------------------
+        Sym3<double> C{1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
+        if (n >= 3) {
+            double cu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int j = 0; j < n; ++j) {
+                const int cidx = (int)(list[j] & 511u);
+                const double px = S.xyz[3 * cidx], py = S.xyz[3 * cidx + 1], pz = S.xyz[3 * cidx + 2];
+                cu[0] += px; cu[1] += py; cu[2] += pz;
+                cu[3] += px * px; cu[4] += px * py; cu[5] += px * pz;
+                cu[6] += py * py; cu[7] += py * pz; cu[8] += pz * pz;
+            }
+            const double cn = (double)n;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) cu[j] /= cn;
+            C.a00 = cu[3] - cu[0] * cu[0];
+            C.a11 = cu[6] - cu[1] * cu[1];
+            C.a22 = cu[8] - cu[2] * cu[2];
+            C.a01 = cu[4] - cu[0] * cu[1];
+            C.a02 = cu[5] - cu[0] * cu[2];
+            C.a12 = cu[7] - cu[1] * cu[2];
+        }
+        Vec3<double> nrm = sym3_smallest_eigvec<double>(C);
+        const double len = sqrt(nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z);
+        if (prior != nullptr) {
+            const double ox = prior[3 * (int64_t)oi], oy = prior[3 * (int64_t)oi + 1], oz = prior[3 * (int64_t)oi + 2];
+            if (len == 0.0) nrm = {ox, oy, oz};
+            else if (nrm.x * ox + nrm.y * oy + nrm.z * oz < 0.0) nrm = {-nrm.x, -nrm.y, -nrm.z};
+        } else if (len == 0.0) {
+            nrm = {0.0, 0.0, 1.0};
+        }
+        normals[3 * (int64_t)oi] = nrm.x;
+        normals[3 * (int64_t)oi + 1] = nrm.y;
+        normals[3 * (int64_t)oi + 2] = nrm.z;
+    }
 }
 
 // ---- k nearest export (b3d_knn_hybrid): arbitrary queries against a grid -------------------------------------------
@@ -313,12 +461,29 @@ int estimate_normals_batch(b3d_ctx* ctx, const T* xyz, const Segments& seg, int 
     const T r2 = r * r;
     const int n = (int)grid->sort.n;
     const int blocks = (n + 127) / 128;
+    const uint8_t* need = nullptr;
+    DevBuf<uint8_t> need_buf;
+    if constexpr (std::is_same<T, double>::value && !TENSOR) {
+        if (use_radius && max_nn <= kNrmList) {
+            // staged fast path; the per-lane kernel below only redoes the flagged points
+            QueryChunks qc;
+            B3D_TRY(build_query_chunks(ctx, xyz, seg.off, seg.off_h, grid->sort, nullptr, 0, &qc));
+            B3D_TRY(need_buf.alloc(ctx, (size_t)n));
+            B3D_CUDA(cudaMemsetAsync(need_buf.p, 0, (size_t)n, ctx->stream));
+            const int sblocks = std::max(1, std::min((qc.n_chunks + kNrmBlock / 32 - 1) / (kNrmBlock / 32), ctx->sm_count * 32));
+            const size_t smem = sizeof(NrmWarpSmem) * (kNrmBlock / 32);
+            B3D_CUDA(cudaFuncSetAttribute(normals_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            B3D_LAUNCH(ctx, normals_staged_kernel, sblocks, kNrmBlock, smem, grid->view(), qc.pts.p, qc.chunk_start.p, qc.chunk_off.p, seg.B, qc.n_chunks, max_nn,
+                       radius, r2, prior, normals, need_buf.p);
+            need = need_buf.p;
+        }
+    }
     if (max_nn <= 32) {
         B3D_LAUNCH(ctx, (normals_kernel<T, 32, TENSOR>), blocks, 128, 0, grid->view(), grid->sort.keys.p, seg.off, max_nn, use_radius, r2, rmax, prior,
-                   normals);
+                   normals, need);
     } else {
         B3D_LAUNCH(ctx, (normals_kernel<T, 64, TENSOR>), blocks, 128, 0, grid->view(), grid->sort.keys.p, seg.off, max_nn, use_radius, r2, rmax, prior,
-                   normals);
+                   normals, need);
     }
     return B3D_OK;
 }

@@ -12,7 +12,10 @@
 
 namespace b3d {
 
-constexpr int kStageCap = 384;       // staged candidates per warp (float4 each)
+#ifndef B3D_STAGE_CAP
+#define B3D_STAGE_CAP 384
+#endif
+constexpr int kStageCap = B3D_STAGE_CAP;  // staged candidates per warp (float4 each)
 constexpr int kStageMaxCells = 256;  // cells one staging call may touch
 constexpr int kStagePreCap = 8192;   // points in the touched cells before the box filter (prefix fits 16 bits)
 
@@ -37,7 +40,8 @@ __device__ __forceinline__ double warp_max(double v) {
 // prefix. Returns count, or -1 when the box touches more than kStageMaxCells cells / more than kStageCap points (the
 // caller falls back to the per-lane walk). All 32 lanes must call it with identical arguments.
 __device__ __forceinline__ int warp_stage_box(const GridView<double>& g, int cloud, const double (&lo)[3], const double (&hi)[3],
-                                              const double (&center)[3], float4* __restrict__ cand, int* __restrict__ cand_pos, StageScratch* __restrict__ sc) {
+                                              const double (&center)[3], float4* __restrict__ cand, int* __restrict__ cand_pos, StageScratch* __restrict__ sc,
+                                              int cap = kStageCap, double* __restrict__ cand_xyz = nullptr) {
     const Lattice L = g.lat[cloud];
     const int lane = threadIdx.x & 31;
     const double o[3] = {L.ox, L.oy, L.oz};
@@ -100,6 +104,7 @@ __device__ __forceinline__ int warp_stage_box(const GridView<double>& g, int clo
         bool inside = false;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         int pp = 0;
+        double ex = 0, ey = 0, ez = 0;
         if (j < total) {
             int a = 0, b = ncell;  // largest a with seg_off[a] <= j
             while (b - a > 1) {
@@ -112,17 +117,23 @@ __device__ __forceinline__ int warp_stage_box(const GridView<double>& g, int clo
             const float rx = (float)(pt.x - center[0]), ry = (float)(pt.y - center[1]), rz = (float)(pt.z - center[2]);
             v = make_float4(rx, ry, rz, fmaf(rz, rz, fmaf(ry, ry, rx * rx)));
             pp = p;
+            ex = pt.x; ey = pt.y; ez = pt.z;
         }
         const unsigned int m = __ballot_sync(0xffffffffu, inside);
         const int slot = kept + __popc(m & ((1u << lane) - 1u));
-        if (inside && slot < kStageCap) {
+        if (inside && slot < cap) {
             cand[slot] = v;
             cand_pos[slot] = pp;
+            if (cand_xyz != nullptr) {  // exact coordinates for float64 work on the staged set (normals)
+                cand_xyz[3 * slot] = ex;
+                cand_xyz[3 * slot + 1] = ey;
+                cand_xyz[3 * slot + 2] = ez;
+            }
         }
         kept += __popc(m);
     }
     __syncwarp();
-    if (kept > kStageCap) return -1;
+    if (kept > cap) return -1;
     total = kept;
     __syncwarp();
     return total;
