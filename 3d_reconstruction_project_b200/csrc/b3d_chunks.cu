@@ -98,7 +98,7 @@ int build_query_chunks(b3d_ctx* ctx, const double* pts, const int32_t* off_d, co
     int level = 3;
     {
         const double occ = (double)lattices.n / (double)std::max<int64_t>(1, lattices.n_runs);
-        const double cells_per_side = std::sqrt(96.0 / std::max(occ, 0.25));
+        const double cells_per_side = std::sqrt(64.0 / std::max(occ, 0.25));
         level = (int)std::lround(2.0 + std::log2(std::max(cells_per_side, 1.0)));
         level = std::min(std::max(level, 2), 7);
         if (const char* e = getenv("B3D_CHUNK_LEVEL")) level = atoi(e);

@@ -6,6 +6,7 @@
 #include "b3d_stage.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <type_traits>
 
 namespace b3d {
@@ -68,6 +69,10 @@ int build_search_grid(b3d_ctx* ctx, const T* xyz, const Segments& seg, int k, do
 }
 template int build_search_grid<float>(b3d_ctx*, const float*, const Segments&, int, double, Grid<float>*, int*);
 template int build_search_grid<double>(b3d_ctx*, const double*, const Segments&, int, double, Grid<double>*, int*);
+
+// debug counters of the staged normals (B3D_ICP_STATS=1): [0] chunks, [1] overflowed chunks, [2] lanes needing the k-nearest cut,
+// [3] staged candidates, [4] valid lanes
+__device__ unsigned long long g_nrm_stats[8];
 
 namespace {
 
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(kNrmBlock) normals_staged_kernel(GridView<doub
                                                                   const int32_t* __restrict__ chunk_start, const int32_t* __restrict__ chunk_off,
                                                                   int B, int n_chunks, int k, double radius, double r2,
                                                                   const double* __restrict__ prior, double* __restrict__ normals,
-                                                                  uint8_t* __restrict__ need) {
+                                                                  uint8_t* __restrict__ need, int stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     NrmWarpSmem& S = reinterpret_cast<NrmWarpSmem*>(smem_raw)[warp];
@@ -209,6 +214,14 @@ __global__ void __launch_bounds__(kNrmBlock) normals_staged_kernel(GridView<doub
         const double center[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
         const float H = (float)(0.5 * fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2])) * 1.0001f;
         const int count = warp_stage_box(g, cloud, lo, hi, center, S.cand, S.pos, &S.stage, kNrmCap, S.xyz);
+        if (stats) {
+            const unsigned int vm = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0) {
+                atomicAdd(&g_nrm_stats[0], 1ull);
+                if (count < 0) atomicAdd(&g_nrm_stats[1], 1ull); else atomicAdd(&g_nrm_stats[3], (unsigned long long)count);
+                atomicAdd(&g_nrm_stats[4], (unsigned long long)__popc(vm));
+            }
+        }
         if (count < 0) {
             if (valid) need[oi] = 1;
             continue;
@@ -238,6 +251,7 @@ __global__ void __launch_bounds__(kNrmBlock) normals_staged_kernel(GridView<doub
         __syncwarp();
         if (!valid) continue;
         if (spill || n > k) {
+            if (stats) atomicAdd(&g_nrm_stats[2], 1ull);
             need[oi] = 1;  // needs the k nearest of more than k in-radius points: per-lane kernel
             continue;
         }
@@ -474,7 +488,7 @@ int estimate_normals_batch(b3d_ctx* ctx, const T* xyz, const Segments& seg, int 
             const size_t smem = sizeof(NrmWarpSmem) * (kNrmBlock / 32);
             B3D_CUDA(cudaFuncSetAttribute(normals_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             B3D_LAUNCH(ctx, normals_staged_kernel, sblocks, kNrmBlock, smem, grid->view(), qc.pts.p, qc.chunk_start.p, qc.chunk_off.p, seg.B, qc.n_chunks, max_nn,
-                       radius, r2, prior, normals, need_buf.p);
+                       radius, r2, prior, normals, need_buf.p, getenv("B3D_ICP_STATS") ? 1 : 0);
             need = need_buf.p;
         }
     }
@@ -506,6 +520,15 @@ struct b3d_grid {
 };
 
 extern "C" {
+
+int b3d_debug_normals_stats(unsigned long long* out8, int reset) {
+    if (out8 && cudaMemcpyFromSymbol(out8, g_nrm_stats, 8 * sizeof(unsigned long long)) != cudaSuccess) return B3D_E_CUDA;
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (cudaMemcpyToSymbol(g_nrm_stats, z, sizeof(z)) != cudaSuccess) return B3D_E_CUDA;
+    }
+    return B3D_OK;
+}
 
 int b3d_estimate_normals_legacy(b3d_ctx* ctx, const double* xyz, int64_t n, int max_nn, double radius, const double* prior, double* normals) {
     B3D_REQUIRE(ctx != nullptr, "ctx is NULL");

@@ -15,6 +15,8 @@ L = N.lib()
 L.b3d_debug_icp_stats.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
 ops.register_depth_pairs(src, tgt, params)
 L.b3d_debug_icp_stats(None, 1)
+L.b3d_debug_normals_stats.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
+L.b3d_debug_normals_stats(None, 1)
 res = ops.register_depth_pairs(src, tgt, params)
 torch.cuda.synchronize()
 out = (C.c_ulonglong * 8)()
@@ -25,3 +27,8 @@ its = [r["iterations"] for r in res]
 print(f"pairs {P}, source points {ns}, iterations {its}")
 print(f"round-1 chunks {c1}, round-2 chunks {c2} ({100.0 * c2 / max(c1, 1):.1f} %), overflows {ovf} ({100.0 * ovf / max(c1 + c2, 1):.2f} %)")
 print(f"staged candidates per staging call {cand / max(c1 + c2 - ovf, 1):.1f}, mean box volume {vol / max(c1 + c2, 1):.1f} cm^3, mean longest edge {edge / max(c1 + c2, 1) / 100:.2f} cm")
+out = (C.c_ulonglong * 8)()
+L.b3d_debug_normals_stats(out, 1)
+ch, ovf, cut, cand, lanes = [int(v) for v in out[:5]]
+print(f"normals: chunks {ch}, overflowed {ovf} ({100.0 * ovf / max(ch, 1):.2f} %), lanes needing the k-nearest cut {cut}, "
+      f"candidates per chunk {cand / max(ch - ovf, 1):.1f}, valid lanes per chunk {lanes / max(ch, 1):.1f}")
