@@ -36,6 +36,12 @@ class PairParams(C.Structure):
                 ("icp_max_iter", C.c_int)]
 
 
+class DisparityParams(C.Structure):
+    _fields_ = [("w", C.c_int), ("h", C.c_int), ("Q", C.c_double * 16), ("min_disp16", C.c_int), ("voxel_size", C.c_float),
+                ("normals_max_nn", C.c_int), ("normals_radius", C.c_double), ("icp_kind", C.c_int), ("icp_max_dist", C.c_double),
+                ("icp_rel_fitness", C.c_double), ("icp_rel_rmse", C.c_double), ("icp_max_iter", C.c_int)]
+
+
 class PairResult(C.Structure):
     _fields_ = [("icp", IcpResult), ("n_raw", C.c_int64), ("m_source", C.c_int64), ("m_target", C.c_int64)]
 
@@ -57,6 +63,7 @@ SIGNATURES = {
     "b3d_deproject_z16_color": (_i, [_vp, _vp, _vp, _i, _i, _f, _f, _f, _f, _f, _vp, _vp]),
     "b3d_deproject_rgbd": (_i, [_vp, _vp, _vp, _i, _i, _d, _d, _d, _d, _f, _f, _i, _vp, _vp, _pi64]),
     "b3d_reproject_disparity": (_i, [_vp, _vp, _i, _i, C.POINTER(_d), _vp]),
+    "b3d_reproject_disparity_valid": (_i, [_vp, _vp, _i, _i, C.POINTER(_d), _i, _vp, _pi64]),
     "b3d_voxel_downsample_legacy": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _vp, _vp, _vp, _vp, _vp, _pi64]),
     "b3d_voxel_downsample_tensor": (_i, [_vp, _vp, _vp, _i64, _f, _vp, _vp, _vp, _vp, _pi64]),
     "b3d_grid_build": (_i, [_vp, _vp, _i64, _i, _d, _i, _d, C.POINTER(_vp)]),
@@ -78,6 +85,7 @@ SIGNATURES = {
     "b3d_icp_finish": (_i, [_vp, _vp, C.POINTER(IcpResult), _vp]),
     "b3d_register_depth_pair": (_i, [_vp, C.POINTER(PairParams), _vp, _vp, _i, C.POINTER(PairResult)]),
     "b3d_register_depth_pairs": (_i, [_vp, C.POINTER(PairParams), _vp, _vp, _i, _i, C.POINTER(PairResult)]),
+    "b3d_register_disparity_pairs": (_i, [_vp, C.POINTER(DisparityParams), _vp, _vp, _i, _i, C.POINTER(PairResult)]),
 }
 
 _lib = None

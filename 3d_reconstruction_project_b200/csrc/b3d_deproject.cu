@@ -131,7 +131,68 @@ __global__ void __launch_bounds__(256) reproject_disparity_kernel(const int16_t*
     }
 }
 
+// valid-only variant: pixels with disparity >= min16 (fixed point x16), raster order, frames stacked back to back
+struct DispPred {
+    const int16_t* disp;
+    int min16;
+    __device__ __forceinline__ bool operator()(int64_t i) const { return (int)disp[i] >= min16; }
+};
+struct DispEmit {
+    const int16_t* disp;
+    int w;
+    int64_t frame_px;
+    QMat Q;
+    float* xyz;
+    int32_t* src_px;  // optional: batch-global pixel index of every emitted point
+    __device__ __forceinline__ void operator()(int64_t i, int64_t slot) const {
+        const int64_t px = i % frame_px;
+        const int64_t row = px / w;
+        const double x = (double)(int)(px - row * w), y = (double)row;
+        const double d = (double)((float)disp[i] / 16.0f);
+        double v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[r] = Q.q[4 * r] * x + Q.q[4 * r + 1] * y + Q.q[4 * r + 2] * d + Q.q[4 * r + 3] * 1.0;
+        const double iw = 1.0 / v[3];
+        xyz[3 * slot] = (float)((double)(float)v[0] * iw);
+        xyz[3 * slot + 1] = (float)((double)(float)v[1] * iw);
+        xyz[3 * slot + 2] = (float)((double)(float)v[2] * iw);
+        if (src_px != nullptr) src_px[slot] = (int32_t)i;
+    }
+};
+
+// off[f] = number of emitted points whose pixel index is below f * frame_px (f = 0..frames)
+__global__ void frame_offsets_kernel(const int32_t* __restrict__ src_px, const int64_t* __restrict__ total_d, int64_t frame_px, int frames,
+                                     int32_t* __restrict__ off) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f > frames) return;
+    const int64_t key = (int64_t)f * frame_px;
+    int64_t lo = 0, hi = *total_d;
+    while (lo < hi) {
+        const int64_t m = (lo + hi) >> 1;
+        if ((int64_t)src_px[m] < key) lo = m + 1; else hi = m;
+    }
+    off[f] = (int32_t)lo;
+}
+
 }  // namespace
+
+// Valid pixels of `frames` stacked disparity rasters -> xyz (capacity frames*h*w rows); off_h receives the per-frame offsets.
+int reproject_disparity_valid_batch(b3d_ctx* ctx, const int16_t* disp, int w, int h, int frames, const double* Q_h, int min_disp16, float* xyz,
+                                    std::vector<int32_t>* off_h) {
+    const int64_t frame_px = (int64_t)w * h, n = frame_px * frames;
+    off_h->assign((size_t)frames + 1, 0);
+    if (n == 0) return B3D_OK;
+    QMat Q;
+    for (int i = 0; i < 16; ++i) Q.q[i] = Q_h[i];
+    DevBuf<int64_t> total;
+    DevBuf<int32_t> src_px, off;
+    B3D_TRY(total.alloc(ctx, 1));
+    B3D_TRY(src_px.alloc(ctx, (size_t)n));
+    B3D_TRY(off.alloc(ctx, (size_t)frames + 1));
+    B3D_TRY(compact(ctx, DispPred{disp, min_disp16}, DispEmit{disp, w, frame_px, Q, xyz, src_px.p}, n, total.p));
+    B3D_LAUNCH(ctx, frame_offsets_kernel, (frames + 1 + 127) / 128, 128, 0, src_px.p, total.p, frame_px, frames, off.p);
+    return ctx->download(off_h->data(), off.p, ((size_t)frames + 1) * sizeof(int32_t));
+}
 
 // frames: number of h x w rasters stacked back to back (batch); xyz [frames*h*w, 3]
 int deproject_z16_batch(b3d_ctx* ctx, const uint16_t* depth, const uint8_t* bgr, int w, int h, int frames, float fx, float fy, float ppx,
@@ -188,6 +249,20 @@ int b3d_deproject_rgbd(b3d_ctx* ctx, const uint16_t* depth, const uint8_t* color
     RgbdEmit emit{depth, color, w, fx, fy, cx, cy, depth_scale, flip_yz, xyz, rgb};
     B3D_TRY(compact(ctx, pred, emit, n, total.p));
     return ctx->download(n_valid_h, total.p, sizeof(int64_t));
+}
+
+int b3d_reproject_disparity_valid(b3d_ctx* ctx, const int16_t* disp, int w, int h, const double* Q_h, int min_disp16, float* xyz,
+                                  int64_t* n_valid_h) {
+    B3D_REQUIRE(ctx != nullptr && n_valid_h != nullptr, "b3d_reproject_disparity_valid: NULL argument");
+    B3D_REQUIRE(w >= 0 && h >= 0, "b3d_reproject_disparity_valid: negative image size");
+    *n_valid_h = 0;
+    if ((int64_t)w * h == 0) return B3D_OK;
+    B3D_REQUIRE(disp && xyz && Q_h, "b3d_reproject_disparity_valid: NULL buffer");
+    B3D_TRY(ctx->bind());
+    std::vector<int32_t> off;
+    B3D_TRY(reproject_disparity_valid_batch(ctx, disp, w, h, 1, Q_h, min_disp16, xyz, &off));
+    *n_valid_h = off[1];
+    return B3D_OK;
 }
 
 int b3d_reproject_disparity(b3d_ctx* ctx, const int16_t* disp, int w, int h, const double* Q_h, float* xyz) {

@@ -169,18 +169,60 @@ __device__ void umeyama_from_moments(const double* mu_s, const double* mu_d, con
         T[4 * i + 3] = mu_d[i] - (R[3 * i] * mu_s[0] + R[3 * i + 1] * mu_s[1] + R[3 * i + 2] * mu_s[2]);
     }
 }
-// (M^-1)^(1/2) of a symmetric positive-definite 3x3 (GICP weight)
+// (M^-1)^(1/2) of a symmetric positive-definite 3x3 (GICP weight, one per correspondence per pass). Closed-form
+// eigen-decomposition (the trigonometric solver of b3d_common.cuh, all three eigenpairs): W = sum_i lambda_i^(-1/2) v_i v_i^T
+// with an orthonormal basis by construction. The CPU oracle iterates Jacobi sweeps to an exactly diagonal matrix; both are
+// accurate to a few ulp, the closed form costs a tenth of the instructions (profiles/r01g_ncu_gicp_jacobi_digest.txt).
 __device__ void inv_sqrt_sym3(const double* M, double* W) {
-    double w[3], V[9];
-    jacobi_eig3(M, w, V);
-    double s[3];
-    for (int i = 0; i < 3; ++i) s[i] = 1.0 / sqrt(w[i]);
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            double a = 0;
-            for (int k = 0; k < 3; ++k) a += V[3 * i + k] * s[k] * V[3 * j + k];
-            W[3 * i + j] = a;
+    Sym3<double> A{M[0], M[1], M[2], M[4], M[5], M[8]};
+    double mx = A.a00;
+    mx = A.a01 > mx ? A.a01 : mx;
+    mx = A.a02 > mx ? A.a02 : mx;
+    mx = A.a11 > mx ? A.a11 : mx;
+    mx = A.a12 > mx ? A.a12 : mx;
+    mx = A.a22 > mx ? A.a22 : mx;
+    double lam[3] = {M[0], M[4], M[8]};
+    Vec3<double> v[3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    if (mx > 0) {
+        A.a00 /= mx; A.a01 /= mx; A.a02 /= mx; A.a11 /= mx; A.a12 /= mx; A.a22 /= mx;
+        const double norm = A.a01 * A.a01 + A.a02 * A.a02 + A.a12 * A.a12;
+        if (norm > 0) {
+            const double q = (A.a00 + A.a11 + A.a22) / 3;
+            const double b00 = A.a00 - q, b11 = A.a11 - q, b22 = A.a22 - q;
+            const double p = sqrt((b00 * b00 + b11 * b11 + b22 * b22 + norm * 2) / 6);
+            const double c00 = b11 * b22 - A.a12 * A.a12;
+            const double c01 = A.a01 * b22 - A.a12 * A.a02;
+            const double c02 = A.a01 * A.a12 - b11 * A.a02;
+            const double det = (b00 * c00 - A.a01 * c01 + A.a02 * c02) / (p * p * p);
+            double half = det * 0.5;
+            half = half < -1.0 ? -1.0 : (half > 1.0 ? 1.0 : half);
+            const double angle = acos(half) / 3.0;
+            const double beta2 = cos(angle) * 2;
+            const double beta0 = cos(angle + 2.09439510239319549) * 2;
+            const double beta1 = -(beta0 + beta2);
+            const double e0 = q + p * beta0, e1 = q + p * beta1, e2 = q + p * beta2;
+            if (half >= 0) {
+                v[2] = sym3_eigvec0(A, e2);
+                v[1] = sym3_eigvec1(A, v[2], e1);
+                v[0] = cross3(v[1], v[2]);
+            } else {
+                v[0] = sym3_eigvec0(A, e0);
+                v[1] = sym3_eigvec1(A, v[0], e1);
+                v[2] = cross3(v[0], v[1]);
+            }
+            lam[0] = e0 * mx; lam[1] = e1 * mx; lam[2] = e2 * mx;
         }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) W[i] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double f = 1.0 / sqrt(lam[k]);
+        const double vx = v[k].x, vy = v[k].y, vz = v[k].z;
+        W[0] += f * vx * vx; W[1] += f * vx * vy; W[2] += f * vx * vz;
+        W[4] += f * vy * vy; W[5] += f * vy * vz; W[8] += f * vz * vz;
+    }
+    W[3] = W[1]; W[6] = W[2]; W[7] = W[5];
 }
 
 // ---- per-warp reduction through shared memory ------------------------------------------------------------------------

@@ -13,6 +13,8 @@ namespace b3d {
 
 int deproject_z16_batch(b3d_ctx* ctx, const uint16_t* depth, const uint8_t* bgr, int w, int h, int frames, float fx, float fy, float ppx,
                         float ppy, float scale, float* xyz, float* rgb);
+int reproject_disparity_valid_batch(b3d_ctx* ctx, const int16_t* disp, int w, int h, int frames, const double* Q_h, int min_disp16, float* xyz,
+                                    std::vector<int32_t>* off_h);
 template <typename T, typename IndexT>
 int voxel_downsample_batch(b3d_ctx* ctx, const T* xyz, const T* a0, const T* a1, const Segments& seg, double voxel, int flavour, T* o_xyz,
                            T* o_a0, T* o_a1, IndexT* o_index, int32_t* o_count, SpatialSort* out_sort, const std::vector<double>* bounds_in);
@@ -28,51 +30,29 @@ __global__ void __launch_bounds__(256) widen_kernel(const float* __restrict__ in
 
 }  // namespace b3d
 
-using namespace b3d;
+namespace b3d {
 
-extern "C" {
+struct BackParams {
+    float voxel_size;
+    int normals_max_nn;
+    double normals_radius;
+    int icp_kind;
+    double icp_max_dist, icp_rel_fitness, icp_rel_rmse;
+    int icp_max_iter;
+};
 
-int b3d_register_depth_pairs(b3d_ctx* ctx, const b3d_pair_params* pr, const uint16_t* depth_src, const uint16_t* depth_tgt, int n_pairs,
-                             int device_inputs, b3d_pair_result* results_h) {
-    B3D_REQUIRE(ctx != nullptr && pr != nullptr && results_h != nullptr, "b3d_register_depth_pairs: NULL argument");
-    B3D_REQUIRE(n_pairs >= 1, "b3d_register_depth_pairs: n_pairs must be >= 1");
-    B3D_REQUIRE(pr->w > 0 && pr->h > 0, "b3d_register_depth_pairs: empty image");
-    B3D_REQUIRE(depth_src && depth_tgt, "b3d_register_depth_pairs: NULL depth buffer");
-    B3D_REQUIRE(pr->voxel_size > 0.0f, "voxel_size must be positive.");
-    B3D_REQUIRE(pr->icp_max_dist > 0.0, "Invalid max_correspondence_distance.");
-    B3D_REQUIRE(pr->icp_kind >= 0 && pr->icp_kind <= 2, "unknown ICP kind %d", pr->icp_kind);
-    B3D_REQUIRE(pr->normals_max_nn >= 1 && pr->normals_max_nn <= 64, "normals_max_nn must be in [1, 64]");
-    B3D_REQUIRE(pr->icp_max_iter >= 0, "negative icp_max_iter");
-    B3D_REQUIRE(pr->fx != 0.0f && pr->fy != 0.0f, "zero focal length");
-    B3D_TRY(ctx->bind());
-    const int P = n_pairs, F = 2 * P;
-    const int64_t N = (int64_t)pr->w * pr->h;
-    B3D_REQUIRE(N * F < (int64_t)INT32_MAX, "batch of %d frames x %lld pixels exceeds 2^31-1 points", F, (long long)N);
-
-    // 1. depth rasters -> device (e2e leg) -> float32 points, sources first then targets
-    DevBuf<uint16_t> depth_d;
-    const uint16_t* d_src = depth_src;
-    const uint16_t* d_tgt = depth_tgt;
-    if (!device_inputs) {
-        B3D_TRY(depth_d.alloc(ctx, (size_t)(N * F)));
-        B3D_CUDA(cudaMemcpyAsync(depth_d.p, depth_src, (size_t)(N * P) * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
-        B3D_CUDA(cudaMemcpyAsync(depth_d.p + N * P, depth_tgt, (size_t)(N * P) * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
-        d_src = depth_d.p;
-        d_tgt = depth_d.p + N * P;
-    }
-    DevBuf<float> xyz;
-    B3D_TRY(xyz.alloc(ctx, (size_t)(3 * N * F)));
-    B3D_TRY(deproject_z16_batch(ctx, d_src, nullptr, pr->w, pr->h, P, pr->fx, pr->fy, pr->ppx, pr->ppy, pr->depth_scale, xyz.p, nullptr));
-    B3D_TRY(deproject_z16_batch(ctx, d_tgt, nullptr, pr->w, pr->h, P, pr->fx, pr->fy, pr->ppx, pr->ppy, pr->depth_scale, xyz.p + 3 * N * P, nullptr));
-
+// Everything after the deprojection: xyz holds 2P float32 clouds back to back (P sources, then P targets), raw_off their
+// offsets. n_raw_h[f] (optional) = raw points of frame f for the result records.
+static int register_clouds_f32(b3d_ctx* ctx, DevBuf<float>& xyz, const std::vector<int32_t>& raw_off, int P, const BackParams* pr,
+                               b3d_pair_result* results_h) {
+    const int F = 2 * P;
+    const int64_t n_total = raw_off[F];
     // 2. tensor voxel down-sampling of all 2P frames in one sort
-    std::vector<int32_t> raw_off(F + 1);
-    for (int f = 0; f <= F; ++f) raw_off[f] = (int32_t)(f * N);
     DevBuf<int32_t> raw_off_d;
     Segments raw_seg;
     B3D_TRY(upload_segments(ctx, raw_off, &raw_off_d, &raw_seg));
     DevBuf<float> vox;
-    B3D_TRY(vox.alloc(ctx, (size_t)(3 * N * F)));
+    B3D_TRY(vox.alloc(ctx, (size_t)(3 * n_total)));
     SpatialSort vs;
     B3D_TRY((voxel_downsample_batch<float, int64_t>(ctx, xyz.p, nullptr, nullptr, raw_seg, (double)pr->voxel_size, kLatTensorVoxel, vox.p, nullptr,
                                                      nullptr, nullptr, nullptr, &vs, nullptr)));
@@ -150,11 +130,89 @@ int b3d_register_depth_pairs(b3d_ctx* ctx, const b3d_pair_params* pr, const uint
     B3D_TRY(icp_results(ctx, pb, &work, res.data()));
     for (int p = 0; p < P; ++p) {
         results_h[p].icp = res[p];
-        results_h[p].n_raw = 2 * N;
+        results_h[p].n_raw = (int64_t)(raw_off[p + 1] - raw_off[p]) + (int64_t)(raw_off[P + p + 1] - raw_off[P + p]);
         results_h[p].m_source = soff[p + 1] - soff[p];
         results_h[p].m_target = toff[p + 1] - toff[p];
     }
     return B3D_OK;
+}
+
+}  // namespace b3d
+
+using namespace b3d;
+
+extern "C" {
+
+int b3d_register_depth_pairs(b3d_ctx* ctx, const b3d_pair_params* pr, const uint16_t* depth_src, const uint16_t* depth_tgt, int n_pairs,
+                             int device_inputs, b3d_pair_result* results_h) {
+    B3D_REQUIRE(ctx != nullptr && pr != nullptr && results_h != nullptr, "b3d_register_depth_pairs: NULL argument");
+    B3D_REQUIRE(n_pairs >= 1, "b3d_register_depth_pairs: n_pairs must be >= 1");
+    B3D_REQUIRE(pr->w > 0 && pr->h > 0, "b3d_register_depth_pairs: empty image");
+    B3D_REQUIRE(depth_src && depth_tgt, "b3d_register_depth_pairs: NULL depth buffer");
+    B3D_REQUIRE(pr->voxel_size > 0.0f, "voxel_size must be positive.");
+    B3D_REQUIRE(pr->icp_max_dist > 0.0, "Invalid max_correspondence_distance.");
+    B3D_REQUIRE(pr->icp_kind >= 0 && pr->icp_kind <= 2, "unknown ICP kind %d", pr->icp_kind);
+    B3D_REQUIRE(pr->normals_max_nn >= 1 && pr->normals_max_nn <= 64, "normals_max_nn must be in [1, 64]");
+    B3D_REQUIRE(pr->icp_max_iter >= 0, "negative icp_max_iter");
+    B3D_REQUIRE(pr->fx != 0.0f && pr->fy != 0.0f, "zero focal length");
+    B3D_TRY(ctx->bind());
+    const int P = n_pairs, F = 2 * P;
+    const int64_t N = (int64_t)pr->w * pr->h;
+    B3D_REQUIRE(N * F < (int64_t)INT32_MAX, "batch of %d frames x %lld pixels exceeds 2^31-1 points", F, (long long)N);
+
+    // 1. depth rasters -> device (e2e leg) -> float32 points, sources first then targets
+    DevBuf<uint16_t> depth_d;
+    const uint16_t* d_src = depth_src;
+    const uint16_t* d_tgt = depth_tgt;
+    if (!device_inputs) {
+        B3D_TRY(depth_d.alloc(ctx, (size_t)(N * F)));
+        B3D_CUDA(cudaMemcpyAsync(depth_d.p, depth_src, (size_t)(N * P) * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+        B3D_CUDA(cudaMemcpyAsync(depth_d.p + N * P, depth_tgt, (size_t)(N * P) * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+        d_src = depth_d.p;
+        d_tgt = depth_d.p + N * P;
+    }
+    DevBuf<float> xyz;
+    B3D_TRY(xyz.alloc(ctx, (size_t)(3 * N * F)));
+    B3D_TRY(deproject_z16_batch(ctx, d_src, nullptr, pr->w, pr->h, P, pr->fx, pr->fy, pr->ppx, pr->ppy, pr->depth_scale, xyz.p, nullptr));
+    B3D_TRY(deproject_z16_batch(ctx, d_tgt, nullptr, pr->w, pr->h, P, pr->fx, pr->fy, pr->ppx, pr->ppy, pr->depth_scale, xyz.p + 3 * N * P, nullptr));
+
+    std::vector<int32_t> raw_off(F + 1);
+    for (int f = 0; f <= F; ++f) raw_off[f] = (int32_t)(f * N);
+    BackParams bp{pr->voxel_size, pr->normals_max_nn, pr->normals_radius, pr->icp_kind, pr->icp_max_dist, pr->icp_rel_fitness, pr->icp_rel_rmse,
+                  pr->icp_max_iter};
+    return register_clouds_f32(ctx, xyz, raw_off, P, &bp, results_h);
+}
+
+int b3d_register_disparity_pairs(b3d_ctx* ctx, const b3d_disparity_params* pr, const int16_t* disp_src, const int16_t* disp_tgt, int n_pairs,
+                                 int device_inputs, b3d_pair_result* results_h) {
+    B3D_REQUIRE(ctx != nullptr && pr != nullptr && results_h != nullptr, "b3d_register_disparity_pairs: NULL argument");
+    B3D_REQUIRE(n_pairs >= 1, "b3d_register_disparity_pairs: n_pairs must be >= 1");
+    B3D_REQUIRE(pr->w > 0 && pr->h > 0, "b3d_register_disparity_pairs: empty image");
+    B3D_REQUIRE(disp_src && disp_tgt, "b3d_register_disparity_pairs: NULL disparity buffer");
+    B3D_REQUIRE(pr->voxel_size > 0.0f, "voxel_size must be positive.");
+    B3D_REQUIRE(pr->icp_max_dist > 0.0, "Invalid max_correspondence_distance.");
+    B3D_REQUIRE(pr->icp_kind >= 0 && pr->icp_kind <= 2, "unknown ICP kind %d", pr->icp_kind);
+    B3D_REQUIRE(pr->normals_max_nn >= 1 && pr->normals_max_nn <= 64, "normals_max_nn must be in [1, 64]");
+    B3D_REQUIRE(pr->icp_max_iter >= 0, "negative icp_max_iter");
+    B3D_TRY(ctx->bind());
+    const int P = n_pairs, F = 2 * P;
+    const int64_t N = (int64_t)pr->w * pr->h;
+    B3D_REQUIRE(N * F < (int64_t)INT32_MAX, "batch of %d frames x %lld pixels exceeds 2^31-1 points", F, (long long)N);
+    DevBuf<int16_t> disp_d;
+    B3D_TRY(disp_d.alloc(ctx, (size_t)(N * F)));  // sources then targets, contiguous for the single compaction pass
+    const cudaMemcpyKind kind = device_inputs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    B3D_CUDA(cudaMemcpyAsync(disp_d.p, disp_src, (size_t)(N * P) * sizeof(int16_t), kind, ctx->stream));
+    B3D_CUDA(cudaMemcpyAsync(disp_d.p + N * P, disp_tgt, (size_t)(N * P) * sizeof(int16_t), kind, ctx->stream));
+    DevBuf<float> xyz;
+    B3D_TRY(xyz.alloc(ctx, (size_t)(3 * N * F)));
+    std::vector<int32_t> raw_off;
+    B3D_TRY(reproject_disparity_valid_batch(ctx, disp_d.p, pr->w, pr->h, F, pr->Q, pr->min_disp16, xyz.p, &raw_off));
+    disp_d.release();
+    for (int f = 0; f < F; ++f)
+        B3D_REQUIRE(raw_off[f + 1] > raw_off[f], "b3d_register_disparity_pairs: frame %d has no valid disparity", f);
+    BackParams bp{pr->voxel_size, pr->normals_max_nn, pr->normals_radius, pr->icp_kind, pr->icp_max_dist, pr->icp_rel_fitness, pr->icp_rel_rmse,
+                  pr->icp_max_iter};
+    return register_clouds_f32(ctx, xyz, raw_off, P, &bp, results_h);
 }
 
 int b3d_register_depth_pair(b3d_ctx* ctx, const b3d_pair_params* params, const uint16_t* depth_src, const uint16_t* depth_tgt, int device_inputs,

@@ -67,6 +67,18 @@ def reproject_disparity(disp16, Q, device=0, as_tensor=False):
     return _out(xyz, as_tensor)
 
 
+def reproject_disparity_valid(disp16, Q, min_disp16=16, device=0, as_tensor=False):
+    """Valid pixels only (disparity >= min_disp16; SGBM marks invalid pixels with (minDisparity - 1) * 16), raster order."""
+    ctx = get_context(device)
+    d = ctx.to_device(disp16, torch.int16)
+    h, w = d.shape
+    Qh = (C.c_double * 16)(*np.asarray(Q, dtype=np.float64).reshape(16))
+    xyz = ctx.empty((h * w, 3), torch.float32)
+    n = C.c_int64(0)
+    N.check(N.lib().b3d_reproject_disparity_valid(ctx.handle, ptr(d), w, h, Qh, int(min_disp16), ptr(xyz), C.byref(n)))
+    return _out(xyz[:n.value], as_tensor)
+
+
 # ---- K2 ------------------------------------------------------------------------------------------------------------
 def voxel_down_sample_legacy(points, voxel_size, colors=None, normals=None, device=0, as_tensor=False):
     """o3d.geometry.PointCloud.voxel_down_sample -- pointcloud_alignment.py:22-23. Returns dict(points, colors, normals,
@@ -247,10 +259,27 @@ def make_pair_params(w, h, fx, fy, ppx, ppy, depth_scale=0.001, voxel_size=0.005
                         icp_rel_rmse, icp_max_iter)
 
 
+def make_disparity_params(w, h, Q, min_disp16=16, voxel_size=0.005, normals_max_nn=30, normals_radius=0.01, icp_kind=N.ICP_GENERALIZED,
+                          icp_max_dist=0.02, icp_rel_fitness=1e-6, icp_rel_rmse=1e-6, icp_max_iter=30):
+    Qa = (C.c_double * 16)(*np.asarray(Q, dtype=np.float64).reshape(16))
+    return N.DisparityParams(w, h, Qa, min_disp16, voxel_size, normals_max_nn, normals_radius, icp_kind, icp_max_dist, icp_rel_fitness, icp_rel_rmse,
+                             icp_max_iter)
+
+
+def register_disparity_pairs(disp_src, disp_tgt, params, device=0):
+    """BASELINE config 3 path for a batch of stereo frame pairs: disparity (int16 x16) + Q -> clouds -> tensor voxel -> normals
+    -> ICP / GICP. disp_src / disp_tgt: [P,h,w] int16, host (numpy / pinned tensor) or CUDA tensors."""
+    return _register(N.lib().b3d_register_disparity_pairs, disp_src, disp_tgt, params, np.int16, device)
+
+
 def register_depth_pairs(depth_src, depth_tgt, params, device=0):
     """The full front end + registration for a batch of frame pairs. depth_src / depth_tgt: [P,h,w] uint16 as numpy /
     pinned CPU tensors (copied host->device inside the call) or CUDA tensors (already resident).
     Returns a list of dicts (transformation, fitness, inlier_rmse, iterations, converged, n_corr, n_raw, m_source, m_target)."""
+    return _register(N.lib().b3d_register_depth_pairs, depth_src, depth_tgt, params, np.uint16, device)
+
+
+def _register(fn, src, tgt, params, np_dtype, device):
     ctx = get_context(device)
 
     def prep(a):
@@ -259,20 +288,20 @@ def register_depth_pairs(depth_src, depth_tgt, params, device=0):
             if t.dim() == 2:
                 t = t.unsqueeze(0)
             return t, t.is_cuda, t.data_ptr()
-        arr = np.ascontiguousarray(a, dtype=np.uint16)
+        arr = np.ascontiguousarray(a, dtype=np_dtype)
         if arr.ndim == 2:
             arr = arr[None]
         return arr, False, arr.ctypes.data
 
-    s, s_dev, s_ptr = prep(depth_src)
-    t, t_dev, t_ptr = prep(depth_tgt)
+    s, s_dev, s_ptr = prep(src)
+    t, t_dev, t_ptr = prep(tgt)
     if s_dev != t_dev:
-        raise ValueError("depth_src and depth_tgt must both be host or both be device buffers")
+        raise ValueError("source and target rasters must both be host or both be device buffers")
     P = s.shape[0]
     if tuple(s.shape) != tuple(t.shape) or tuple(s.shape[1:]) != (params.h, params.w):
-        raise ValueError(f"depth stacks must both be [P, {params.h}, {params.w}]")
+        raise ValueError(f"raster stacks must both be [P, {params.h}, {params.w}]")
     res = (N.PairResult * P)()
-    N.check(N.lib().b3d_register_depth_pairs(ctx.handle, C.byref(params), C.c_void_p(s_ptr), C.c_void_p(t_ptr), P, int(s_dev), res))
+    N.check(fn(ctx.handle, C.byref(params), C.c_void_p(s_ptr), C.c_void_p(t_ptr), P, int(s_dev), res))
     out = []
     for r in res:
         d = _result_dict(r.icp, None)

@@ -24,8 +24,9 @@ def _wall(x, y, z0):
     return z0 + 0.15 * np.sin(3.0 * x) * np.cos(2.0 * y) + 0.05 * np.sin(11.0 * x + 1.0)
 
 
-def render_depth(w, h, fx, fy, ppx, ppy, pose=None, z0=2.0, depth_scale=0.001, zmin=0.5, zmax=4.0, holes=0.05, rng=None):
-    """Depth raster (uint16, units of depth_scale metres) of the scene seen from camera pose ``pose`` (camera -> world, 4x4)."""
+def render_depth(w, h, fx, fy, ppx, ppy, pose=None, z0=2.0, depth_scale=0.001, zmin=0.5, zmax=4.0, holes=0.05, rng=None, as_metres=False):
+    """Depth raster (uint16, units of depth_scale metres) of the scene seen from camera pose ``pose`` (camera -> world, 4x4).
+    as_metres=True returns the float64 depth in metres instead (0 = no return)."""
     pose = np.eye(4) if pose is None else pose
     j, i = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
     d_cam = np.stack([(j - ppx) / fx, (i - ppy) / fy, np.ones_like(j)], axis=-1)
@@ -56,6 +57,8 @@ def render_depth(w, h, fx, fy, ppx, ppy, pose=None, z0=2.0, depth_scale=0.001, z
         tf = (0.8 - o[1]) / d[..., 1]
     best = np.minimum(best, np.where(np.isfinite(tf) & (tf > 0), tf, np.inf))
     z = np.where((best >= zmin) & (best <= zmax), best, 0.0)
+    if as_metres:
+        return z
     depth = np.rint(z / depth_scale).astype(np.uint16)
     if holes > 0:
         rng = rng or np.random.default_rng(0)
@@ -109,3 +112,35 @@ def rotation_angle(R):
 def transform_error(Ta, Tb):
     """(rotation angle of Ra^T Rb in rad, |ta - tb| in m)"""
     return rotation_angle(Ta[:3, :3].T @ Tb[:3, :3]), float(np.linalg.norm(Ta[:3, 3] - Tb[:3, 3]))
+
+
+# ---- stereo (BASELINE config 3) -------------------------------------------------------------------------------------------
+def stereo_q(scale=3.4, f=525.60716928, cx=107.42533255, cy=250.54165268, inv_baseline_per_mm=3.17597752e-02):
+    """Q of Calib_depth/jetson_stereo_8MP_stereo.npz (960x540 calibration) scaled to `scale` x the resolution, output in
+    METRES (the file's Q yields millimetres: last row x 1000). SURVEY.md 8d, config 3."""
+    Q = np.zeros((4, 4))
+    Q[0, 0] = Q[1, 1] = 1.0
+    Q[0, 3], Q[1, 3], Q[2, 3] = -cx * scale, -cy * scale, f * scale
+    Q[3, 2] = inv_baseline_per_mm * 1000.0
+    return Q
+
+
+def disparity_pair(seed_a, seed_b, w=3264, h=2448, scale=3.4, invalid=0.03, max_rot_deg=2.0, max_trans=0.02):
+    """(disp_src, disp_tgt [h,w] int16 fixed point x16, Q, T_true) for the synthetic scene seen by the scaled stereo rig.
+    Invalid pixels (no return, out of the 1..128 px range, or a Bernoulli dropout of `invalid`) carry -16."""
+    Q = stereo_q(scale)
+    f, cx, cy = Q[2, 3], -Q[0, 3], -Q[1, 3]
+    fb = f / Q[3, 2]  # disparity = f * B / Z  (px * m)
+    ra, rb = np.random.default_rng(seed_a), np.random.default_rng(seed_b)
+    ang = np.deg2rad(max_rot_deg) * (2 * rb.random(3) - 1)
+    tr = max_trans * (2 * rb.random(3) - 1)
+    pose_src = rigid(ang[0], ang[1], ang[2], tr)
+    out = []
+    for pose, rng in ((pose_src, rb), (np.eye(4), ra)):
+        z = render_depth(w, h, f, f, cx, cy, pose=pose, holes=0.0, as_metres=True)
+        with np.errstate(divide="ignore"):
+            d = np.where(z > 0, fb / z, 0.0)
+        d16 = np.rint(d * 16.0)
+        bad = (d16 < 16) | (d16 > 128 * 16) | (rng.random(z.shape) < invalid)
+        out.append(np.where(bad, -16, d16).astype(np.int16))
+    return out[0], out[1], Q, pose_src

@@ -78,6 +78,10 @@ int b3d_deproject_rgbd(b3d_ctx* ctx, const uint16_t* depth, const uint8_t* color
  * Calib_depth/depth4.py:98; disparity is SGBM int16 fixed point x16 (Calib_depth/depth1.py:331).
  * Q_h: 16 doubles row-major on the HOST. xyz: float32 [h*w,3]. */
 int b3d_reproject_disparity(b3d_ctx* ctx, const int16_t* disp, int w, int h, const double* Q_h, float* xyz);
+/* Same arithmetic, valid pixels only (disparity >= min_disp16, fixed point x16; SGBM marks invalid pixels with
+ * (minDisparity - 1) * 16), raster order. xyz: float32 [h*w,3] capacity; n_valid_h receives the point count. */
+int b3d_reproject_disparity_valid(b3d_ctx* ctx, const int16_t* disp, int w, int h, const double* Q_h, int min_disp16, float* xyz,
+                                  int64_t* n_valid_h);
 
 /* ---- K2 voxel down-sampling ----------------------------------------------------------------------------- */
 /* Legacy PointCloud.voxel_down_sample -- pointcloud_alignment.py:22-23, test/check84.py:180, test/mini1.py:174.
@@ -195,6 +199,24 @@ int b3d_register_depth_pair(b3d_ctx* ctx, const b3d_pair_params* params, const u
  * spatial keys), the ICP passes are n_pairs wide. results_h: [n_pairs]. Each pair's result equals the single-pair call. */
 int b3d_register_depth_pairs(b3d_ctx* ctx, const b3d_pair_params* params, const uint16_t* depth_src, const uint16_t* depth_tgt,
                              int n_pairs, int device_inputs, b3d_pair_result* results_h);
+
+/* Stereo flavour of the same path (BASELINE config 3): SGBM disparity rasters (int16 x16, Calib_depth/depth1.py:331) +
+ * the rectification Q matrix (Calib_depth/depth4.py:98) -> valid-pixel clouds -> tensor voxel -> normals -> ICP / GICP.
+ * disp_src / disp_tgt: [n_pairs, h, w] int16 stacks (host, or device when device_inputs != 0). */
+typedef struct b3d_disparity_params {
+    int w, h;
+    double Q[16];      /* row-major 4x4; scale its last row to choose the output unit (e.g. x1000: mm -> m) */
+    int min_disp16;    /* smallest valid disparity, fixed point x16 */
+    float voxel_size;
+    int normals_max_nn;
+    double normals_radius;
+    int icp_kind;
+    double icp_max_dist, icp_rel_fitness, icp_rel_rmse;
+    int icp_max_iter;
+} b3d_disparity_params;
+
+int b3d_register_disparity_pairs(b3d_ctx* ctx, const b3d_disparity_params* params, const int16_t* disp_src, const int16_t* disp_tgt,
+                                 int n_pairs, int device_inputs, b3d_pair_result* results_h);
 
 #ifdef __cplusplus
 }

@@ -177,3 +177,48 @@ def test_stepwise_icp_two_shards_equal_single(b3):
     assert res[0]["iterations"] == single["iterations"] and abs(res[0]["fitness"] - single["fitness"]) < 1e-12
     corr = np.concatenate([res[0]["corr"], res[1]["corr"]])
     assert np.array_equal(corr, single["corr"])
+
+
+def test_reproject_disparity_valid_bit_exact(b3):
+    from b200recon import ops, synth
+    s, _, Q, _ = synth.disparity_pair(2000, 2001, w=408, h=306, scale=0.425)
+    ref = oracle.reproject_disparity(s, Q).reshape(-1, 3)[(s >= 16).reshape(-1)]
+    out = ops.reproject_disparity_valid(s, Q, 16)
+    assert out.shape == ref.shape and np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    assert ops.reproject_disparity_valid(np.full((8, 8), -16, np.int16), Q, 16).shape == (0, 3)
+
+
+def oracle_disparity_pair(ds, dt, Q, voxel, k, radius, kind, dmax, max_iter):
+    """CPU restatement of the stereo flavour: reproject valid pixels -> tensor voxel -> legacy normals -> ICP / GICP."""
+    xs = oracle.reproject_disparity(ds, Q).reshape(-1, 3)[(ds >= 16).reshape(-1)]
+    xt = oracle.reproject_disparity(dt, Q).reshape(-1, 3)[(dt >= 16).reshape(-1)]
+    vs = oracle.voxel_tensor(xs, voxel)["points"].astype(np.float64)
+    vt = oracle.voxel_tensor(xt, voxel)["points"].astype(np.float64)
+    nt = oracle.normals_legacy(vt, k, radius)
+    kw = dict(tgt_normals=nt)
+    if kind == 2:
+        ns = oracle.normals_legacy(vs, k, radius)
+        kw = dict(src_cov=oracle.covariances_from_normals(ns).reshape(-1, 9), tgt_cov=oracle.covariances_from_normals(nt).reshape(-1, 9))
+    r = oracle.icp(kind, vs, vt, dmax, max_iter=max_iter, **kw)
+    r.update(m_source=len(vs), m_target=len(vt), n_raw=len(xs) + len(xt))
+    return r
+
+
+@pytest.mark.parametrize("kind", [2, 1])
+def test_disparity_pair_pipeline_vs_oracle(b3, kind):
+    """BASELINE config 3 at reduced size (same rig scaled to 408x306): stereo disparity -> cloud -> voxel -> normals -> GICP."""
+    from b200recon import ops, synth
+    pairs = [synth.disparity_pair(2000 + 2 * i, 2001 + 2 * i, w=408, h=306, scale=0.425) for i in range(2)]
+    Q = pairs[0][2]
+    ds = np.stack([p[0] for p in pairs])
+    dt = np.stack([p[1] for p in pairs])
+    voxel, radius, dmax = 0.01, 0.03, 0.04
+    params = ops.make_disparity_params(408, 306, Q, 16, voxel_size=voxel, normals_max_nn=30, normals_radius=radius, icp_kind=kind, icp_max_dist=dmax, icp_max_iter=30)
+    res = ops.register_disparity_pairs(ds, dt, params)
+    for i in range(2):
+        ref = oracle_disparity_pair(ds[i], dt[i], Q, voxel, 30, radius, kind, dmax, 30)
+        r = res[i]
+        assert (r["m_source"], r["m_target"], r["n_raw"]) == (ref["m_source"], ref["m_target"], ref["n_raw"])
+        assert rot_err(r["transformation"][:3, :3], ref["transformation"][:3, :3]) < 1e-5
+        assert np.linalg.norm(r["transformation"][:3, 3] - ref["transformation"][:3, 3]) < 1e-5
+        assert abs(r["fitness"] - ref["fitness"]) < 1e-4 and abs(r["inlier_rmse"] - ref["inlier_rmse"]) < 1e-4
