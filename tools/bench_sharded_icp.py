@@ -36,16 +36,35 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from b200recon import distributed as D, ops, synth
-    src, nrm = synth.height_field_cloud(a.side, seed=4000)
+    # the cloud is generated on the device (same seed on every rank -> identical replicas of the target); only this rank's
+    # slice of the source is kept
     T = synth.rigid(0.0003, -0.0002, 0.0004, (0.0008, -0.0006, 0.001))  # a motion well inside d_max = 5 mm
-    R = T[:3, :3]
-    tgt = src @ R.T + T[:3, 3]
-    tn = nrm @ R.T
-    n = len(src)
+    dev = torch.device("cuda", local)
+    g = torch.Generator(device=dev)
+    g.manual_seed(4000)
+    S = a.side
+    u = (torch.arange(S, device=dev, dtype=torch.float64) - S / 2) * 0.001
+    x = u.repeat(S) + 0.0002 * torch.randn(S * S, device=dev, dtype=torch.float64, generator=g)
+    y = u.repeat_interleave(S) + 0.0002 * torch.randn(S * S, device=dev, dtype=torch.float64, generator=g)
+    z = 2.0 + 0.15 * torch.sin(3 * x) * torch.cos(2 * y) + 0.05 * torch.sin(11 * x + 1)
+    nx = -(0.45 * torch.cos(3 * x) * torch.cos(2 * y) + 0.55 * torch.cos(11 * x + 1))
+    ny = 0.30 * torch.sin(3 * x) * torch.sin(2 * y)
+    inv = torch.rsqrt(nx * nx + ny * ny + 1.0)
+    src_all = torch.stack([x, y, z], dim=1)
+    nrm_all = torch.stack([nx * inv, ny * inv, inv], dim=1)
+    del x, y, z, nx, ny, inv
+    Tt = torch.from_numpy(T).to(dev)
+    tgt = src_all @ Tt[:3, :3].T + Tt[:3, 3]
+    tn = nrm_all @ Tt[:3, :3].T
+    del nrm_all
+    n = S * S
     lo, hi = D.shard_range(n, rank, world)
+    src = src_all[lo:hi].clone()
+    del src_all
+    torch.cuda.empty_cache()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    sh = D.ShardedICP(1, src[lo:hi], n, tgt, a.dmax, tgt_normals=tn, rel_fitness=0.0, rel_rmse=0.0, max_iter=a.iters, device=local)
+    sh = D.ShardedICP(1, src, n, tgt, a.dmax, tgt_normals=tn, rel_fitness=0.0, rel_rmse=0.0, max_iter=a.iters, device=local)
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t0
     ev = lambda: torch.cuda.Event(enable_timing=True)
