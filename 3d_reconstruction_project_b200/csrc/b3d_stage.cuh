@@ -97,27 +97,45 @@ __device__ __forceinline__ int warp_stage_box(const GridView<double>& g, int clo
     }
     if (lane == 0) sc->seg_off[ncell] = (unsigned short)total;
     __syncwarp();
-    // flat copy, keeping only the points inside the box (ballot compaction keeps the order deterministic)
+    // Copy, keeping only the points inside the box. Lane l owns the contiguous slice [l*m, (l+1)*m) of the flat list of
+    // cell points: ONE binary search per lane finds the first cell, after that the lane just walks on to the next
+    // non-empty cell. All lanes step through their slices in lock step, so a ballot compacts every step's survivors
+    // (deterministic order).
+    const int per_lane = (total + 31) >> 5;
+    int j = lane * per_lane;
+    const int j_end = min(total, j + per_lane);
+    int cell = 0, cell_end = 0, src = 0;
+    if (j < j_end) {
+        int a = 0, b = ncell;  // largest a with seg_off[a] <= j
+        while (b - a > 1) {
+            const int m = (a + b) >> 1;
+            if ((int)sc->seg_off[m] <= j) a = m; else b = m;
+        }
+        cell = a;
+        cell_end = (int)sc->seg_off[cell + 1];
+        src = sc->seg_s[cell] + (j - (int)sc->seg_off[cell]);
+    }
     int kept = 0;
-    for (int jb = 0; jb < total; jb += 32) {
-        const int j = jb + lane;
+    for (int step = 0; step < per_lane; ++step) {
         bool inside = false;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         int pp = 0;
         double ex = 0, ey = 0, ez = 0;
-        if (j < total) {
-            int a = 0, b = ncell;  // largest a with seg_off[a] <= j
-            while (b - a > 1) {
-                const int m = (a + b) >> 1;
-                if ((int)sc->seg_off[m] <= j) a = m; else b = m;
+        if (j < j_end) {
+            while (j >= cell_end) {  // next non-empty cell
+                ++cell;
+                cell_end = (int)sc->seg_off[cell + 1];
+                src = sc->seg_s[cell];
             }
-            const int p = sc->seg_s[a] + (j - (int)sc->seg_off[a]);
+            const int p = src;
             const double4 pt = ld_point(g.pts + p);
             inside = pt.x >= lo[0] && pt.x <= hi[0] && pt.y >= lo[1] && pt.y <= hi[1] && pt.z >= lo[2] && pt.z <= hi[2];
             const float rx = (float)(pt.x - center[0]), ry = (float)(pt.y - center[1]), rz = (float)(pt.z - center[2]);
             v = make_float4(rx, ry, rz, fmaf(rz, rz, fmaf(ry, ry, rx * rx)));
             pp = p;
             ex = pt.x; ey = pt.y; ez = pt.z;
+            ++j;
+            ++src;
         }
         const unsigned int m = __ballot_sync(0xffffffffu, inside);
         const int slot = kept + __popc(m & ((1u << lane) - 1u));
