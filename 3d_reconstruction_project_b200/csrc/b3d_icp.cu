@@ -23,6 +23,7 @@ __device__ unsigned long long g_icp_stats[8];
 namespace {
 
 constexpr int kIcpBlock = 128;
+constexpr int kIcpInformation = 3;  // internal kind: G^T G of get_information_matrix_from_point_clouds (rows from the target point)
 constexpr int kIcpMaxGroups = 1024;  // partial-sum groups (blocks) per pair
 
 // ---- small dense helpers (device) ----------------------------------------------------------------------------------
@@ -445,7 +446,9 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
                 const double4 q = ld_point(A.grid.pts + pos);
                 e[7] = 1.0;
                 e[8] = d2;
-                if (KIND == B3D_ICP_POINT_TO_POINT) {
+                if (KIND == kIcpInformation) {
+                    gp[0] = q.x; gp[1] = q.y; gp[2] = q.z;
+                } else if (KIND == B3D_ICP_POINT_TO_POINT) {
                     e[0] = px; e[1] = py; e[2] = pz;
                     e[3] = q.x; e[4] = q.y; e[5] = q.z;
                 } else if (KIND == B3D_ICP_POINT_TO_PLANE) {
@@ -474,8 +477,19 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
                 }
             }
         }
-        const int n_rows = KIND == B3D_ICP_GENERALIZED ? 3 : 1;
+        const int n_rows = (KIND == B3D_ICP_GENERALIZED || KIND == kIcpInformation) ? 3 : 1;
         for (int row = 0; row < n_rows; ++row) {
+            if (KIND == kIcpInformation) {
+                if (matched) {
+                    // G = [ -[t]x | I ] for the target point t (kept in gp)
+                    e[0] = row == 0 ? 0.0 : (row == 1 ? -gp[2] : gp[1]);
+                    e[1] = row == 0 ? gp[2] : (row == 1 ? 0.0 : -gp[0]);
+                    e[2] = row == 0 ? -gp[1] : (row == 1 ? gp[0] : 0.0);
+                    e[3] = row == 0 ? 1.0 : 0.0; e[4] = row == 1 ? 1.0 : 0.0; e[5] = row == 2 ? 1.0 : 0.0;
+                    e[6] = 0.0;
+                    if (row > 0) { e[7] = 0.0; e[8] = 0.0; }
+                }
+            }
             if (KIND == B3D_ICP_GENERALIZED) {
                 if (matched) {
                     const double w0 = W[3 * row], w1 = W[3 * row + 1], w2 = W[3 * row + 2];
@@ -491,7 +505,7 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
 #pragma unroll
             for (int j = 0; j < kIcpRow; ++j) rows[lane][j] = e[j];
             __syncwarp();
-            if (KIND == B3D_ICP_GENERALIZED && row > 0 && lane >= 27) {
+            if ((KIND == B3D_ICP_GENERALIZED || KIND == kIcpInformation) && row > 0 && lane >= 27) {
                 // count and sum d2 are taken once per correspondence (row 0)
             } else {
 #pragma unroll 8
@@ -688,6 +702,8 @@ int icp_pass(b3d_ctx* ctx, const IcpProblem& pb, IcpWork* w, int32_t* corr, bool
     const dim3 grid(w->blocks, pb.P);
     if (pb.kind == B3D_ICP_POINT_TO_POINT) {
         B3D_LAUNCH(ctx, icp_pass_kernel<B3D_ICP_POINT_TO_POINT>, grid, kIcpBlock, 0, A);
+    } else if (pb.kind == kIcpInformation) {
+        B3D_LAUNCH(ctx, icp_pass_kernel<kIcpInformation>, grid, kIcpBlock, 0, A);
     } else if (pb.kind == B3D_ICP_POINT_TO_PLANE) {
         B3D_LAUNCH(ctx, icp_pass_kernel<B3D_ICP_POINT_TO_PLANE>, grid, kIcpBlock, 0, A);
     } else {
@@ -835,6 +851,29 @@ int b3d_icp_correspondences(b3d_ctx* ctx, const double* src, int64_t ns, const d
         stats_h[0] = sums[27];
         stats_h[1] = sums[28];
     }
+    return B3D_OK;
+}
+
+int b3d_information_matrix(b3d_ctx* ctx, const double* src, int64_t ns, const double* tgt, int64_t nt, const double* T_h, double max_dist,
+                           double* info_h) {
+    B3D_REQUIRE(ctx != nullptr && info_h != nullptr, "b3d_information_matrix: NULL argument");
+    B3D_TRY(validate_icp(B3D_ICP_POINT_TO_POINT, src, ns, nullptr, tgt, nt, nullptr, nullptr, max_dist, 0));
+    for (int i = 0; i < 36; ++i) info_h[i] = 0.0;
+    if (ns == 0 || nt == 0) return B3D_OK;
+    B3D_TRY(ctx->bind());
+    b3d_icp_state st;
+    B3D_TRY(setup_single(ctx, &st, B3D_ICP_POINT_TO_POINT, src, ns, nullptr, tgt, nt, nullptr, nullptr, max_dist, T_h, 1e-6, 1e-6, 0));
+    st.pb.kind = kIcpInformation;
+    B3D_TRY(icp_pass(ctx, st.pb, &st.work, nullptr, false));
+    double sums[kIcpSums];
+    B3D_TRY(ctx->download(sums, st.work.sums.p, sizeof(sums)));
+    int t = 0;
+    for (int u = 0; u < 6; ++u)
+        for (int v = u; v < 6; ++v) {
+            info_h[6 * u + v] = sums[t];
+            info_h[6 * v + u] = sums[t];
+            ++t;
+        }
     return B3D_OK;
 }
 

@@ -233,6 +233,15 @@ def correspondences(src, tgt, T=None, max_dist=0.02, device=0, as_tensor=False):
     return _out(corr[:s.shape[0]], as_tensor), int(st[0]), float(st[1])
 
 
+def information_matrix(src, tgt, max_dist, T=None, device=0):
+    """get_information_matrix_from_point_clouds(source, target, max_dist, T) -- test/mini1.py:302. -> [6,6] float64"""
+    ctx = get_context(device)
+    s, t = ctx.to_device(src, torch.float64), ctx.to_device(tgt, torch.float64)
+    out = (C.c_double * 36)()
+    N.check(N.lib().b3d_information_matrix(ctx.handle, ptr(s), s.shape[0], ptr(t), t.shape[0], _T16(T), float(max_dist), out))
+    return np.array(out[:], dtype=np.float64).reshape(6, 6)
+
+
 def _result_dict(r, corr):
     return dict(transformation=np.array(r.transformation[:], dtype=np.float64).reshape(4, 4), fitness=r.fitness, inlier_rmse=r.inlier_rmse,
                 iterations=int(r.iterations), converged=bool(r.converged), n_corr=int(r.n_correspondences), corr=corr)

@@ -95,3 +95,11 @@ def evaluate_registration(source, target, max_correspondence_distance, transform
     corr, n, s = ops.correspondences(np.asarray(source.points), np.asarray(target.points), T, max_correspondence_distance, device=source.device)
     return RegistrationResult(dict(transformation=T, fitness=(n / ns if n else 0.0), inlier_rmse=(np.sqrt(s / n) if n else 0.0), iterations=0,
                                    converged=False, corr=corr))
+
+
+def get_information_matrix_from_point_clouds(source, target, max_correspondence_distance, transformation):
+    """test/mini1.py:302, test/check2.py:160 -- the 6x6 information matrix the reference's pose graph edges carry."""
+    source, target = as_cloud(source), as_cloud(target)
+    if not source.has_points() or not target.has_points():
+        return np.zeros((6, 6))
+    return ops.information_matrix(np.asarray(source.points), np.asarray(target.points), max_correspondence_distance, transformation, device=source.device)

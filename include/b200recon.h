@@ -149,6 +149,11 @@ int b3d_transform_f64(b3d_ctx* ctx, const double* T_h, double* xyz, int64_t n, d
 int b3d_icp_correspondences(b3d_ctx* ctx, const double* src, int64_t ns, const double* tgt, int64_t nt, const double* T_h,
                             double max_dist, int32_t* corr, double* stats_h);
 
+/* get_information_matrix_from_point_clouds(source, target, max_dist, T) -- test/mini1.py:302, test/check2.py:160 (feeds the
+ * reference's pose graph): correspondences of T*source in target, G^T G with G = [-[t]x | I] per TARGET point. info_h: 36 doubles. */
+int b3d_information_matrix(b3d_ctx* ctx, const double* src, int64_t ns, const double* tgt, int64_t nt, const double* T_h, double max_dist,
+                           double* info_h);
+
 /* registration_icp(source, target, max_dist, init, estimation, criteria) / registration_generalized_icp
  *  P2P -- pointcloud_alignment.py:35-39; P2L -- test/mini1.py:293-296, test/check2.py:151-154; GICP -- test/GICP1.py:99-102.
  * tgt_normals required for P2L; src_cov/tgt_cov ([n,9] double) required for GICP. init_h may be NULL (identity).

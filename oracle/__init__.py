@@ -37,6 +37,7 @@ def lib():
         _lib.orc_radius_outlier.restype = C.c_int64
         _lib.orc_correspondences.restype = C.c_int64
         _lib.orc_icp.restype = C.c_int
+        _lib.orc_information_matrix.restype = C.c_int64
     return _lib
 
 
@@ -189,6 +190,15 @@ def correspondences(src, tgt, T, dmax):
     s = C.c_double(0)
     n = lib().orc_correspondences(_p(src), C.c_int64(len(src)), _p(tgt), C.c_int64(len(tgt)), _p(T), C.c_double(dmax), _p(corr), C.byref(s))
     return corr, int(n), s.value
+
+
+def information_matrix(src, tgt, dmax, T=None):
+    src = _c(src, np.float64)
+    tgt = _c(tgt, np.float64)
+    T = _c(np.eye(4) if T is None else T, np.float64)
+    out = np.empty((6, 6), np.float64)
+    lib().orc_information_matrix(_p(src), C.c_int64(len(src)), _p(tgt), C.c_int64(len(tgt)), _p(T), C.c_double(dmax), _p(out))
+    return out
 
 
 P2P, P2L, GICP = 0, 1, 2

@@ -984,6 +984,29 @@ int64_t orc_correspondences(const double* src, int64_t ns, const double* tgt, in
     return r.n;
 }
 
+// ---- get_information_matrix_from_point_clouds (test/mini1.py:302, check2.py:160; "next" row of SURVEY.md 8f) [PARITY UNPINNED] ----
+// Correspondences of T*source in target within dmax; GTG = sum over correspondences of G^T G with
+// G = [ -[t]x | I ] for the TARGET point t (rows [0 z -y 1 0 0], [-z 0 x 0 1 0], [y -x 0 0 0 1]). out: 36 doubles row-major.
+int64_t orc_information_matrix(const double* src, int64_t ns, const double* tgt, int64_t nt, const double* T, double dmax, double* out36) {
+    std::vector<double> s(src, src + 3 * ns);
+    if (T && !mat4_is_identity(T)) transform_cloud(T, s.data(), ns, nullptr, nullptr);
+    KdTree<double> tree;
+    tree.build(tgt, nt);
+    std::vector<int32_t> corr(std::max<int64_t>(ns, 1));
+    CorrResult r = find_correspondences(tree, s.data(), ns, dmax, corr.data());
+    double G[36] = {0};
+    for (int64_t i = 0; i < ns; ++i) {
+        if (corr[i] < 0) continue;
+        const double* t = tgt + 3 * (int64_t)corr[i];
+        const double rows[3][6] = {{0, t[2], -t[1], 1, 0, 0}, {-t[2], 0, t[0], 0, 1, 0}, {t[1], -t[0], 0, 0, 0, 1}};
+        for (int k = 0; k < 3; ++k)
+            for (int u = 0; u < 6; ++u)
+                for (int v = 0; v < 6; ++v) G[6 * u + v] += rows[k][u] * rows[k][v];
+    }
+    std::memcpy(out36, G, sizeof(G));
+    return r.n;
+}
+
 // ---- a10/a11: registration_icp / registration_generalized_icp. SURVEY.md A.6 [PARITY UNPINNED] ----
 // kind: 0 point-to-point (pointcloud_alignment.py:35-39), 1 point-to-plane (test/mini1.py:293-296),
 //       2 generalized (test/GICP1.py:99-102; src_cov/tgt_cov [n,9] required).

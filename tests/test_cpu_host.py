@@ -221,3 +221,18 @@ def test_two_rank_gloo_sharding(built, tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r} failed:\n{o}"
         assert f"rank {r} ok" in o
+
+
+def test_shims_resolve_reference_main(built):
+    """With shims/ first on sys.path the reference's unchanged main.py imports b200recon's classes."""
+    ref = "/root/reference"
+    if not os.path.isfile(os.path.join(ref, "main.py")):
+        pytest.skip("reference tree only exists in the build container")
+    shims = os.path.join(ROOT, "3d_reconstruction_project_b200", "shims")
+    code = ("import sys; sys.path[:0] = [%r, %r, %r]; import main, b200recon; "
+            "assert main.RealSensePipeline is b200recon.RealSensePipeline; assert main.PointCloudCapture is b200recon.PointCloudCapture; "
+            "assert main.PointCloudAlignment is b200recon.PointCloudAlignment; assert main.o3d.geometry.PointCloud is b200recon.PointCloud; "
+            "import realsense_pipeline, pyrealsense2.pyrealsense2 as rs, pycuda.driver, pycuda.autoinit, cupy; assert cupy.eye(4).get().shape == (4, 4); print('ok')"
+            % (shims, ROOT, ref))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(ROOT))
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr

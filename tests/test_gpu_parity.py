@@ -365,3 +365,19 @@ def test_icp_errors_and_empty(ops):
     assert r["fitness"] == 0 and r["inlier_rmse"] == 0 and np.array_equal(r["transformation"], np.eye(4))
     r = ops.icp(0, tgt[:100] + 50.0, tgt, 0.02)  # nothing within range: identity, fitness 0
     assert r["fitness"] == 0 and r["n_corr"] == 0 and np.array_equal(r["transformation"], np.eye(4))
+
+
+def test_information_matrix(ops):
+    """get_information_matrix_from_point_clouds (test/mini1.py:302) after a multi-scale point-to-plane refinement (check2.py:143-155)."""
+    tgt, nrm = golden_cloud("output_00050")
+    T = small_rigid(0.02, 0.01, -0.02, (0.01, 0.005, -0.008))
+    src = oracle.transform(np.linalg.inv(T), tgt)[0][::2]
+    cur_g, cur_o = np.eye(4), np.eye(4)
+    for dist, iters in ((0.3, 30), (0.1, 20), (0.03, 10)):  # voxel 0.02 x (15, 5, 1.5)
+        cur_g = ops.icp(1, src, tgt, dist, init=cur_g, tgt_normals=nrm, max_iter=iters)["transformation"]
+        cur_o = oracle.icp(1, src, tgt, dist, T0=cur_o, tgt_normals=nrm, max_iter=iters)["transformation"]
+    assert rot_err(cur_g[:3, :3], cur_o[:3, :3]) < 1e-5 and np.linalg.norm(cur_g[:3, 3] - cur_o[:3, 3]) < 1e-5
+    ref = oracle.information_matrix(src, tgt, 0.03, cur_o)
+    out = ops.information_matrix(src, tgt, 0.03, cur_o)
+    assert np.allclose(out, ref, rtol=1e-12, atol=1e-9) and np.array_equal(out, out.T)
+    assert abs(out[3, 3] - out[4, 4]) < 1e-9 and out[3, 3] > 0.9 * len(src)

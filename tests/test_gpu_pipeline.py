@@ -222,3 +222,29 @@ def test_disparity_pair_pipeline_vs_oracle(b3, kind):
         assert rot_err(r["transformation"][:3, :3], ref["transformation"][:3, :3]) < 1e-5
         assert np.linalg.norm(r["transformation"][:3, 3] - ref["transformation"][:3, 3]) < 1e-5
         assert abs(r["fitness"] - ref["fitness"]) < 1e-4 and abs(r["inlier_rmse"] - ref["inlier_rmse"]) < 1e-4
+
+
+def test_replay_scan_example(b3, tmp_path):
+    """The reference's whole flow (main.py:14-86) on replayed synthetic frames through the reference-facing classes."""
+    import importlib.util
+    from b200recon import synth
+    spec = importlib.util.spec_from_file_location("replay_scan", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "replay_scan.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cam = SMALL_CAM
+    rng = np.random.default_rng(0)
+    frames = []
+    for i in range(3):
+        pose = synth.rigid(0.004 * i, -0.003 * i, 0.002 * i, (0.004 * i, 0.0, -0.002 * i))
+        frames.append((synth.render_depth(cam["w"], cam["h"], cam["fx"], cam["fy"], cam["ppx"], cam["ppy"], pose=pose, rng=rng),
+                       rng.integers(0, 256, (cam["h"], cam["w"], 3), dtype=np.uint8)))
+    combined, processed, with_normals = mod.run(frames, cam, str(tmp_path), voxel_size=0.02)
+    assert len(combined.points) > 30000 and combined.has_colors()
+    assert os.path.isfile(tmp_path / "captured_data_on_the_fly.ply")
+    # the reference's fixed filter (16 neighbours within 1 cm, pointcloud_processing.py:39) is tuned to 2.5 mm clouds: on this
+    # coarse replay it may remove everything, exactly like Open3D would
+    assert len(processed.points) <= len(combined.points)
+    ne = b3.NormalEstimation().estimate_normals(combined)
+    assert ne.has_normals() and np.allclose(np.linalg.norm(np.asarray(ne.normals), axis=1), 1.0, atol=1e-5)
+    if len(processed.points):
+        assert with_normals.has_normals()
