@@ -321,6 +321,11 @@ struct IcpKernelArgs {
     double* sums;
     int32_t* corr;
     int fused;
+    // per-chunk cache of the staged candidate set (sorted positions) and of the box it covers: later passes whose box lies
+    // inside re-stage from it without touching the hash grid
+    double* cache_box;   // [n_chunks][6]
+    int* cache_count;    // [n_chunks], -1 = empty
+    int* cache_idx;      // [n_chunks][kStageCap]
     int stats;  // count chunks / rounds / staged candidates into g_icp_stats
 };
 
@@ -417,7 +422,31 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
                 const double lo[3] = {bl[0] - pad, bl[1] - pad, bl[2] - pad}, hi[3] = {bh[0] + pad, bh[1] + pad, bh[2] + pad};
                 const double center[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
                 const float half_extent = (float)(0.5 * fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2])) * 1.0001f;
-                const int count = warp_stage_box(A.grid, pair, lo, hi, center, cand, cand_pos, &s_stage[warp]);
+                int count = -2;
+                if (round == 0 && A.cache_count != nullptr) {
+                    const int nc = A.cache_count[c];
+                    if (nc >= 0) {
+                        const double* cb = A.cache_box + 6 * (int64_t)c;
+                        if (lo[0] >= cb[0] && lo[1] >= cb[1] && lo[2] >= cb[2] && hi[0] <= cb[3] && hi[1] <= cb[4] && hi[2] <= cb[5]) {
+                            count = warp_stage_cached(A.grid, A.cache_idx + (int64_t)c * kStageCap, nc, lo, hi, center, cand, cand_pos);
+                            if (A.stats && lane == 0) atomicAdd(&g_icp_stats[6], 1ull);
+                        }
+                    }
+                }
+                if (count == -2) {
+                    count = warp_stage_box(A.grid, pair, lo, hi, center, cand, cand_pos, &s_stage[warp]);
+                    if (round == 0 && A.cache_count != nullptr && count >= 0) {
+                        // remember this staged set for the coming passes
+                        int* ci = A.cache_idx + (int64_t)c * kStageCap;
+                        for (int j = lane; j < count; j += 32) ci[j] = cand_pos[j];
+                        if (lane == 0) {
+                            double* cbw = A.cache_box + 6 * (int64_t)c;
+                            cbw[0] = lo[0]; cbw[1] = lo[1]; cbw[2] = lo[2];
+                            cbw[3] = hi[0]; cbw[4] = hi[1]; cbw[5] = hi[2];
+                        }
+                        if (lane == 0) A.cache_count[c] = count;
+                    }
+                }
                 if (A.stats && lane == 0) {
                     atomicAdd(&g_icp_stats[round == 0 ? 0 : 1], 1ull);
                     if (count < 0) atomicAdd(&g_icp_stats[2], 1ull);
@@ -653,6 +682,20 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
     // order the source points along a Morton curve of the target lattice and cut them into compact warp chunks
     B3D_TRY(build_query_chunks(ctx, pb.src, pb.src_off, pb.src_off_h, g.sort, reinterpret_cast<const double*>(w->state.p),
                                (int)(sizeof(IcpPairState) / sizeof(double)), &w->chunks));
+    // staged-set cache (skipped for very large problems: 1.6 KB per chunk)
+    w->cache_box.release();
+    w->cache_count.release();
+    w->cache_idx.release();
+    {
+        const size_t nc = (size_t)std::max(w->chunks.n_chunks, 1);
+        static const bool cache_off = getenv("B3D_ICP_NO_CACHE") != nullptr;
+        if (!cache_off && nc * (size_t)kStageCap * sizeof(int) <= ((size_t)6 << 30)) {
+            B3D_TRY(w->cache_box.alloc(ctx, nc * 6));
+            B3D_TRY(w->cache_count.alloc(ctx, nc));
+            B3D_TRY(w->cache_idx.alloc(ctx, nc * (size_t)kStageCap));
+            B3D_CUDA(cudaMemsetAsync(w->cache_count.p, 0xff, nc * sizeof(int), ctx->stream));
+        }
+    }
     // partial-sum groups per pair depend only on that pair's own chunk count (results do not depend on the batch)
     w->blocks = std::max(1, std::min((w->chunks.most + kIcpBlock / 32 - 1) / (kIcpBlock / 32), kIcpMaxGroups));
     B3D_TRY(w->partial.alloc(ctx, (size_t)P * w->blocks * kIcpSums));
@@ -690,6 +733,9 @@ static IcpKernelArgs make_args(const IcpProblem& pb, IcpWork* w, int32_t* corr, 
     A.sums = w->sums.p;
     A.corr = corr;
     A.fused = fused ? 1 : 0;
+    A.cache_box = w->cache_box.p;
+    A.cache_count = w->cache_count.p;
+    A.cache_idx = w->cache_idx.p;
     {
         static const int stats_on = getenv("B3D_ICP_STATS") ? 1 : 0;
         A.stats = stats_on;
@@ -718,9 +764,27 @@ int icp_finalize_from_sums(b3d_ctx* ctx, const IcpProblem& pb, IcpWork* w) {
     return B3D_OK;
 }
 
+__global__ void icp_count_active_kernel(const IcpPairState* __restrict__ state, int P, int* __restrict__ active) {
+    int n = 0;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) n += state[p].done ? 0 : 1;
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (threadIdx.x == 0) *active = n;
+}
+
 int icp_run(b3d_ctx* ctx, const IcpProblem& pb, IcpWork* w, int32_t* corr) {
-    // max_iter updates need max_iter + 1 correspondence passes; finished pairs return at once
-    for (int k = 0; k <= pb.max_iter; ++k) B3D_TRY(icp_pass(ctx, pb, w, corr, true));
+    // max_iter updates need max_iter + 1 correspondence passes; finished pairs return at once. Most runs converge long before
+    // max_iter: from the fourth pass on the host looks (every other pass) whether any pair is still active.
+    DevBuf<int> active_d;
+    B3D_TRY(active_d.alloc(ctx, 1));
+    for (int k = 0; k <= pb.max_iter; ++k) {
+        B3D_TRY(icp_pass(ctx, pb, w, corr, true));
+        if (k >= 3 && (k & 1) == 1 && k < pb.max_iter) {
+            B3D_LAUNCH(ctx, icp_count_active_kernel, 1, 32, 0, w->state.p, pb.P, active_d.p);
+            int active = 1;
+            B3D_TRY(ctx->download(&active, active_d.p, sizeof(int)));
+            if (active == 0) break;
+        }
+    }
     return B3D_OK;
 }
 

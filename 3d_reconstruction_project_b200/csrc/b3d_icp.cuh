@@ -43,6 +43,8 @@ struct IcpWork {
     DevBuf<double> tgt_nrm_sorted, tgt_cov_sorted;
     QueryChunks chunks;  // sources in Morton order of the target lattice, cut into compact warp chunks
     DevBuf<int64_t> ns_global;
+    DevBuf<double> cache_box;  // staged-set cache of the pass kernel (per chunk)
+    DevBuf<int> cache_count, cache_idx;
     int blocks = 1;
 };
 

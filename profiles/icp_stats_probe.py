@@ -22,6 +22,8 @@ torch.cuda.synchronize()
 out = (C.c_ulonglong * 8)()
 L.b3d_debug_icp_stats(out, 1)
 c1, c2, ovf, cand, vol, edge = [int(v) for v in out[:6]]
+print("cache hits", int(out[6]), "of", c1, "first-round stagings")
+print("cache hits", int(out[6]))
 ns = sum(r["m_source"] for r in res)
 its = [r["iterations"] for r in res]
 print(f"pairs {P}, source points {ns}, iterations {its}")
