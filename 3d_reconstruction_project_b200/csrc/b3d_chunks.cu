@@ -2,8 +2,6 @@
 #include "b3d_common.cuh"
 #include "b3d_scan.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -138,14 +136,12 @@ int build_query_chunks(b3d_ctx* ctx, const double* pts, const int32_t* off_d, co
     B3D_TRY(o_out.alloc(ctx, n));
     const int kb = (int)std::min<int64_t>((longest + 255) / 256, std::max(1, ctx->sm_count * 16 / B));
     B3D_LAUNCH(ctx, chunk_key_kernel, dim3(std::max(1, kb), B), 256, 0, pts, off_d, transforms, transform_stride, lattices.lat.p, shift, k_in.p, o_in.p);
-    size_t tmp_bytes = 0;
-    B3D_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.p, k_out.p, o_in.p, o_out.p, n, 0, shift + bbits, ctx->stream));
-    DevBuf<uint8_t> tmp;
-    B3D_TRY(tmp.alloc(ctx, tmp_bytes));
-    if (ctx->profiling) ctx->prof_begin("cub_radix_sort_pairs");
-    B3D_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k_in.p, k_out.p, o_in.p, o_out.p, n, 0, shift + bbits, ctx->stream));
-    if (ctx->profiling) ctx->prof_end();
-    ctx->lib_launches += 1;
+    bool in_a = true;
+    B3D_TRY(radix_sort_pairs(ctx, k_in.p, o_in.p, k_out.p, o_out.p, n, shift + bbits, &in_a));
+    if (in_a) {
+        std::swap(k_in, k_out);
+        std::swap(o_in, o_out);
+    }
     B3D_LAUNCH(ctx, chunk_gather_kernel, ctx->grid_for(n, 256, 1, 8), 256, 0, pts, o_out.p, n, out->pts.p);
     DevBuf<int64_t> n_chunks_d;
     B3D_TRY(n_chunks_d.alloc(ctx, 1));

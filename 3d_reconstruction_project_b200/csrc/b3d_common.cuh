@@ -344,6 +344,9 @@ struct SpatialSort {
     int B = 1;
 };
 
+// hand-written stable LSD radix sort of (key, value) pairs by key bits [0, end_bit) (b3d_radix.cu); ping-pong buffers
+int radix_sort_pairs(b3d_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int64_t n, int end_bit, bool* result_in_a);
+
 // bounds_h: [B][6] (min xyz, max xyz) per cloud; clouds with no points get +-DBL_MAX
 template <typename T>
 int compute_bounds(b3d_ctx* ctx, const T* xyz, const Segments& seg, std::vector<double>* bounds_h);

@@ -9,8 +9,6 @@
 #include "b3d_scan.cuh"
 #include "b3d_stage.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
-
 #include <cmath>
 #include <cstdlib>
 #include <cstring>

@@ -1,12 +1,9 @@
 // b3d_sort.cu -- spatial sort shared by voxel down-sampling and the neighbour-search grid:
 // per-cloud bounds -> per-cloud lattice -> composite cell keys -> stable LSD radix sort of (key, point index) ->
-// run heads -> hashed cell table. The radix sort passes are the CUB device primitive (library code, counted in
-// ctx->lib_launches); everything else is hand-written.
+// run heads -> hashed cell table. All hand-written (the radix sort is b3d_radix.cu).
 #include "b3d_common.cuh"
 #include "b3d_scan.cuh"
 #include "b3d_search.cuh"
-
-#include <cub/device/device_radix_sort.cuh>
 
 #include <cfloat>
 #include <climits>
@@ -275,18 +272,14 @@ int spatial_sort(b3d_ctx* ctx, const T* xyz, const Segments& seg, double cell, i
         blocks = std::max(1, blocks);
         B3D_LAUNCH(ctx, cell_key_kernel<T>, dim3(blocks, B), 256, 0, xyz, seg.off, out->lat.p, shift, keys_in.p, ord_in.p);
     }
-    size_t tmp_bytes = 0;
-    B3D_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.p, keys_out.p, ord_in.p, ord_out.p, n, 0, end_bit, ctx->stream));
-    DevBuf<uint8_t> tmp(ctx);
-    B3D_TRY(tmp.alloc(ctx, tmp_bytes));
-    if (ctx->profiling) ctx->prof_begin("cub_radix_sort_pairs");
-    B3D_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_in.p, keys_out.p, ord_in.p, ord_out.p, n, 0, end_bit, ctx->stream));
-    if (ctx->profiling) ctx->prof_end();
-    ctx->lib_launches += 1;
+    bool in_a = true;
+    B3D_TRY(radix_sort_pairs(ctx, keys_in.p, ord_in.p, keys_out.p, ord_out.p, n, end_bit, &in_a));
+    if (in_a) {
+        std::swap(keys_in, keys_out);
+        std::swap(ord_in, ord_out);
+    }
     keys_in.release();
     ord_in.release();
-    tmp.release();
-
     // run heads -> run_start[], count -> host
     DevBuf<int32_t> run_start(ctx);
     DevBuf<int64_t> n_runs_d(ctx);

@@ -169,7 +169,6 @@ def kernel_bytes(name, N_raw, M_total, Mt, Ms, n_corr, icp_bytes_per_launch=None
         "deproject_z16_vec4_kernel": 14 * N_raw / 2,  # two launches per batch (sources, targets)
         "bounds_partial_kernel": 12 * N_raw,
         "cell_key_kernel": 12 * N_raw + 12 * N_raw,  # points in, (key, index) out
-        "cub_radix_sort_pairs": 2 * 12 * N_raw,  # one read + one write of the 12-byte pairs (a multi-pass sort moves more)
         "compact_kernel": 8 * N_raw + 4 * M_total,
         "voxel_reduce_short_kernel": 12 * N_raw + 12 * M_total,
         "voxel_reduce_long_kernel": 12 * N_raw * 0.05,
