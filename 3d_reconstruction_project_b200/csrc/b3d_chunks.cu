@@ -9,16 +9,6 @@
 namespace b3d {
 namespace {
 
-__device__ __forceinline__ unsigned long long spread3(unsigned long long v) {  // 21 bits -> every third bit
-    v &= 0x1fffffull;
-    v = (v | (v << 32)) & 0x1f00000000ffffull;
-    v = (v | (v << 16)) & 0x1f0000ff0000ffull;
-    v = (v | (v << 8)) & 0x100f00f00f00f00full;
-    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
-    v = (v | (v << 2)) & 0x1249249249249249ull;
-    return v;
-}
-
 // Morton key of the (transformed) query on a quarter-cell lattice of its cloud's search grid: consecutive keys are
 // spatially compact, so the 32 queries of a warp fit a small box (and stay compact under rigid updates).
 __global__ void __launch_bounds__(256) chunk_key_kernel(const double* __restrict__ pts, const int32_t* __restrict__ off, const double* __restrict__ transforms,
@@ -40,7 +30,7 @@ __global__ void __launch_bounds__(256) chunk_key_kernel(const double* __restrict
         // one cell of margin below the lattice origin; everything farther out clamps to the border
         const double ux = fmin(fmax(floor((px - L.ox) / q) + 4.0, 0.0), hi), uy = fmin(fmax(floor((py - L.oy) / q) + 4.0, 0.0), hi),
                      uz = fmin(fmax(floor((pz - L.oz) / q) + 4.0, 0.0), hi);
-        const unsigned long long m = (spread3((unsigned long long)ux) << 2) | (spread3((unsigned long long)uy) << 1) | spread3((unsigned long long)uz);
+        const unsigned long long m = (morton_spread3((unsigned long long)ux) << 2) | (morton_spread3((unsigned long long)uy) << 1) | morton_spread3((unsigned long long)uz);
         keys[i] = ((unsigned long long)cloud << shift) | (m & ((1ull << shift) - 1ull));
         order[i] = (uint32_t)i;
     }
@@ -146,6 +136,39 @@ int build_query_chunks(b3d_ctx* ctx, const double* pts, const int32_t* off_d, co
     DevBuf<int64_t> n_chunks_d;
     B3D_TRY(n_chunks_d.alloc(ctx, 1));
     B3D_TRY(compact(ctx, ChunkPred{k_out.p, off_d, shift, std::min(3 * level, shift)}, ChunkEmit{out->chunk_start.p}, n, n_chunks_d.p));
+    B3D_LAUNCH(ctx, chunk_sentinel_kernel, 1, 1, 0, out->chunk_start.p, n_chunks_d.p, n);
+    B3D_LAUNCH(ctx, chunk_ranges_kernel, (B + 1 + 127) / 128, 128, 0, out->chunk_start.p, n_chunks_d.p, off_d, B, out->chunk_off.p);
+    B3D_TRY(ctx->download(out->chunk_off_h.data(), out->chunk_off.p, (size_t)(B + 1) * sizeof(int32_t)));
+    out->n_chunks = out->chunk_off_h[B];
+    for (int b = 0; b < B; ++b) out->most = std::max(out->most, out->chunk_off_h[b + 1] - out->chunk_off_h[b]);
+    out->q = out->pts.p;
+    return B3D_OK;
+}
+
+int chunks_from_grid(b3d_ctx* ctx, const Grid<double>& grid, const int32_t* off_d, const std::vector<int32_t>& off_h, QueryChunks* out) {
+    const SpatialSort& ss = grid.sort;
+    const int B = (int)off_h.size() - 1;
+    const int32_t n = off_h[B];
+    out->chunk_off_h.assign(B + 1, 0);
+    out->n_chunks = 0;
+    out->most = 0;
+    out->pts.release();
+    out->q = grid.pts.p;
+    B3D_TRY(out->chunk_start.alloc(ctx, (size_t)n + 1));
+    B3D_TRY(out->chunk_off.alloc(ctx, (size_t)B + 1));
+    if (n == 0) {
+        B3D_CUDA(cudaMemsetAsync(out->chunk_start.p, 0, sizeof(int32_t), ctx->stream));
+        B3D_CUDA(cudaMemsetAsync(out->chunk_off.p, 0, (size_t)(B + 1) * sizeof(int32_t), ctx->stream));
+        return B3D_OK;
+    }
+    // Morton block = 2^level cells on a side, sized to hold a few chunks' worth of points (surface model)
+    const double occ = (double)ss.n / (double)std::max<int64_t>(1, ss.n_runs);
+    int level = (int)std::lround(std::log2(std::max(std::sqrt(64.0 / std::max(occ, 0.25)), 1.0)));
+    level = std::min(std::max(level, 0), 6);
+    if (const char* e = getenv("B3D_GRID_CHUNK_LEVEL")) level = atoi(e);
+    DevBuf<int64_t> n_chunks_d;
+    B3D_TRY(n_chunks_d.alloc(ctx, 1));
+    B3D_TRY(compact(ctx, ChunkPred{ss.keys.p, off_d, ss.shift, std::min(3 * level, ss.shift)}, ChunkEmit{out->chunk_start.p}, n, n_chunks_d.p));
     B3D_LAUNCH(ctx, chunk_sentinel_kernel, 1, 1, 0, out->chunk_start.p, n_chunks_d.p, n);
     B3D_LAUNCH(ctx, chunk_ranges_kernel, (B + 1 + 127) / 128, 128, 0, out->chunk_start.p, n_chunks_d.p, off_d, B, out->chunk_off.p);
     B3D_TRY(ctx->download(out->chunk_off_h.data(), out->chunk_off.p, (size_t)(B + 1) * sizeof(int32_t)));

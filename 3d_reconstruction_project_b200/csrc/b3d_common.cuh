@@ -303,8 +303,26 @@ struct Lattice {
     int64_t nx, ny, nz;     // extents in cells
     int mode;               // 0: double lattice  floor((p - o) / cell)   (legacy voxel, search grid)
                             // 1: float lattice   floor(float(p) / float(cell))  (tensor voxel, origin 0)
-    int pad;
+    int morton;             // 1: cell keys are Morton codes of (cx, cy, cz) (search grids: consecutive cells are compact in
+                            //    space, so the sorted points double as warp-chunk order); 0: linear (cx*ny + cy)*nz + cz (voxel
+                            //    grids: ascending key order = ascending (ix, iy, iz), the canonical output order)
 };
+
+__host__ __device__ __forceinline__ unsigned long long morton_spread3(unsigned long long v) {  // 21 bits -> every third bit
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x1f00000000ffffull;
+    v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+
+// key of the cell (x, y, z) (coordinates already biased into [0, n)) inside its cloud
+__host__ __device__ __forceinline__ unsigned long long lattice_key(const Lattice& L, long long x, long long y, long long z) {
+    if (L.morton) return (morton_spread3((unsigned long long)x) << 2) | (morton_spread3((unsigned long long)y) << 1) | morton_spread3((unsigned long long)z);
+    return (unsigned long long)((x * L.ny + y) * L.nz + z);
+}
 
 enum LatticeFlavour { kLatLegacyVoxel = 0, kLatTensorVoxel = 1, kLatSearch = 2 };
 
@@ -415,7 +433,8 @@ int grid_build(b3d_ctx* ctx, const T* xyz, const Segments& seg, double cell, con
 // consecutive points that never span more than one Morton block (sized to hold a few chunks) and never straddle clouds; cut points are relative
 // to the cloud start, so the chunking of a cloud does not depend on the rest of the batch.
 struct QueryChunks {
-    DevBuf<double4> pts;          // [n] queries in Morton order, .w = original (batch-global) index
+    const double4* q = nullptr;   // the queries in chunk order (pts.p, or a search grid's own sorted points)
+    DevBuf<double4> pts;          // [n] queries in Morton order, .w = original (batch-global) index (empty when q aliases a grid)
     DevBuf<int32_t> chunk_start;  // [n_chunks + 1]
     DevBuf<int32_t> chunk_off;    // [B + 1] first chunk of every cloud
     std::vector<int32_t> chunk_off_h;
@@ -425,6 +444,10 @@ struct QueryChunks {
 // transforms: device array of B row-major 4x4 matrices applied before the key is taken (stride in doubles), or NULL
 int build_query_chunks(b3d_ctx* ctx, const double* pts, const int32_t* off_d, const std::vector<int32_t>& off_h, const SpatialSort& lattices,
                        const double* transforms, int transform_stride, QueryChunks* out);
+// chunks over a Morton-ordered search grid's own points (no extra sort, no copy): queries = the grid's points
+template <typename T>
+struct Grid;
+int chunks_from_grid(b3d_ctx* ctx, const Grid<double>& grid, const int32_t* off_d, const std::vector<int32_t>& off_h, QueryChunks* out);
 
 // Chooses the cell size for (k, radius) searches (one trial build measures the occupancy) and builds the grid.
 // rmax_out: rings a query has to walk (radius searches), or the ring budget of a k-nearest walk.

@@ -710,7 +710,7 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
 static IcpKernelArgs make_args(const IcpProblem& pb, IcpWork* w, int32_t* corr, bool fused) {
     IcpKernelArgs A;
     A.kind = pb.kind;
-    A.src_sorted = w->chunks.pts.p;
+    A.src_sorted = w->chunks.q;
     A.chunk_start = w->chunks.chunk_start.p;
     A.chunk_off = w->chunks.chunk_off.p;
     A.n_chunks = w->chunks.n_chunks;

@@ -481,13 +481,13 @@ int estimate_normals_batch(b3d_ctx* ctx, const T* xyz, const Segments& seg, int 
         if (use_radius && max_nn <= kNrmList) {
             // staged fast path; the per-lane kernel below only redoes the flagged points
             QueryChunks qc;
-            B3D_TRY(build_query_chunks(ctx, xyz, seg.off, seg.off_h, grid->sort, nullptr, 0, &qc));
+            B3D_TRY(chunks_from_grid(ctx, *grid, seg.off, seg.off_h, &qc));
             B3D_TRY(need_buf.alloc(ctx, (size_t)n));
             B3D_CUDA(cudaMemsetAsync(need_buf.p, 0, (size_t)n, ctx->stream));
             const int sblocks = std::max(1, std::min((qc.n_chunks + kNrmBlock / 32 - 1) / (kNrmBlock / 32), ctx->sm_count * 32));
             const size_t smem = sizeof(NrmWarpSmem) * (kNrmBlock / 32);
             B3D_CUDA(cudaFuncSetAttribute(normals_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            B3D_LAUNCH(ctx, normals_staged_kernel, sblocks, kNrmBlock, smem, grid->view(), qc.pts.p, qc.chunk_start.p, qc.chunk_off.p, seg.B, qc.n_chunks, max_nn,
+            B3D_LAUNCH(ctx, normals_staged_kernel, sblocks, kNrmBlock, smem, grid->view(), qc.q, qc.chunk_start.p, qc.chunk_off.p, seg.B, qc.n_chunks, max_nn,
                        radius, r2, prior, normals, need_buf.p, getenv("B3D_ICP_STATS") ? 1 : 0);
             need = need_buf.p;
         }

@@ -9,6 +9,8 @@
 #include "b3d_icp.cuh"
 #include "b3d_search.cuh"
 
+#include <algorithm>
+
 namespace b3d {
 
 int deproject_z16_batch(b3d_ctx* ctx, const uint16_t* depth, const uint8_t* bgr, int w, int h, int frames, float fx, float fy, float ppx,
@@ -78,22 +80,26 @@ static int register_clouds_f32(b3d_ctx* ctx, DevBuf<float>& xyz, const std::vect
     B3D_TRY(upload_segments(ctx, soff, &soff_d, &sseg));
     B3D_TRY(upload_segments(ctx, toff, &toff_d, &tseg));
 
-    // 4. target grid (shared by the normals and by the ICP correspondence search when the ring count allows)
-    Grid<double> tgrid;
-    int n_rmax = 1;
-    B3D_TRY(build_search_grid<double>(ctx, tgt_pts, tseg, pr->normals_max_nn, pr->normals_radius, &tgrid, &n_rmax));
+    // 4. ONE target grid for the normals and for the ICP correspondence search whenever their radii are comparable: cell =
+    // the larger radius (one ring covers both; the staged searches take any cell size). One sort instead of two.
+    Grid<double> tgrid, icp_grid_own;
+    const Grid<double>* icp_grid = &tgrid;
+    int n_rmax = 1, icp_rmax = 1;
+    const double r_n = pr->normals_radius, r_i = pr->icp_max_dist;
+    const bool shared = r_n > 0 && std::max(r_n, r_i) <= 3.0 * std::min(r_n, r_i);
+    if (shared) {
+        const double cell = std::max(r_n, r_i) * 1.001;
+        B3D_TRY(grid_build<double>(ctx, tgt_pts, tseg, cell, nullptr, &tgrid));
+        n_rmax = rings_for_radius(r_n, cell);
+        icp_rmax = rings_for_radius(r_i, cell);
+    } else {
+        B3D_TRY(build_search_grid<double>(ctx, tgt_pts, tseg, pr->normals_max_nn, r_n, &tgrid, &n_rmax));
+        B3D_TRY(build_search_grid<double>(ctx, tgt_pts, tseg, 8, r_i, &icp_grid_own, &icp_rmax));
+        icp_grid = &icp_grid_own;
+    }
     DevBuf<double> tnrm;
     B3D_TRY(tnrm.alloc(ctx, (size_t)(3 * (int64_t)Mt)));
     B3D_TRY((estimate_normals_batch<double, false>(ctx, tgt_pts, tseg, pr->normals_max_nn, pr->normals_radius, nullptr, tnrm.p, &tgrid, n_rmax)));
-    Grid<double> icp_grid_own;
-    const Grid<double>* icp_grid = &tgrid;
-    int icp_rmax = rings_for_radius(pr->icp_max_dist, tgrid.cell);
-    // A source point without a partner walks every ring up to d_max; with cells of d_max that is 27 probes instead of
-    // (2 rmax + 1)^3, and one such lane holds back its whole warp, so the ICP search gets its own one-ring grid.
-    if (icp_rmax > 1) {
-        B3D_TRY(build_search_grid<double>(ctx, tgt_pts, tseg, 8, pr->icp_max_dist, &icp_grid_own, &icp_rmax));
-        icp_grid = &icp_grid_own;
-    }
 
     // 5. generalized ICP needs covariances on both sides (from normals, eps = 1e-3)
     DevBuf<double> snrm, scov, tcov;

@@ -115,7 +115,7 @@ __device__ __forceinline__ int grid_walk(const GridView<T>& g, int cloud, T qx, 
                     const double gz = dz > 0 ? (double)dz - fz : (dz < 0 ? fz - (double)dz - 1.0 : 0.0);
                     const double box2 = (gxy2 + gz * gz) * h2;
                     if (box2 > thr()) continue;
-                    const unsigned long long key = cloud_bits | (unsigned long long)((x * L.ny + y) * L.nz + z);
+                    const unsigned long long key = cloud_bits | lattice_key(L, x, y, z);
                     int s, e;
                     if (!grid_lookup(g, key, s, e)) continue;
                     for (int p = s; p < e; ++p) visit(p, ld_point(g.pts + p));
@@ -226,7 +226,7 @@ __device__ __forceinline__ int nn_within_query(const GridView<T>& g, int cloud, 
     const double face = fmin(fmin(fmin(fx, 1.0 - fx), fmin(fy, 1.0 - fy)), fmin(fz, 1.0 - fz));
     const unsigned long long cloud_bits = (unsigned long long)cloud << g.shift;
     auto scan_cell = [&](long long x, long long y, long long z) {
-        const unsigned long long key = cloud_bits | (unsigned long long)((x * L.ny + y) * L.nz + z);
+        const unsigned long long key = cloud_bits | lattice_key(L, x, y, z);
         int s, e;
         if (!grid_lookup(g, key, s, e)) return;
         for (int p = s; p < e; ++p) {

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) cell_key_kernel(const T* __restrict__ xyz
         int64_t cx, cy, cz;
         lattice_coord<T>(L, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], cx, cy, cz);
         cx -= L.kx0; cy -= L.ky0; cz -= L.kz0;
-        keys[i] = cloud_bits | (uint64_t)((cx * L.ny + cy) * L.nz + cz);
+        keys[i] = cloud_bits | lattice_key(L, cx, cy, cz);
         order[i] = (uint32_t)i;
     }
 }
@@ -243,12 +243,20 @@ int spatial_sort(b3d_ctx* ctx, const T* xyz, const Segments& seg, double cell, i
     if (!(cell > 0)) return set_error(B3D_E_INVALID, "spatial_sort: cell size must be positive");
     std::vector<Lattice> lat(B);
     unsigned __int128 max_cells = 1;
+    int64_t max_axis = 1;
     for (int b = 0; b < B; ++b) {
         B3D_TRY(make_lattice(&bounds_h[(size_t)b * 6], seg.off_h[b + 1] == seg.off_h[b], cell, flavour, &lat[b]));
+        lat[b].morton = flavour == kLatSearch ? 1 : 0;
         unsigned __int128 t = (unsigned __int128)lat[b].nx * (unsigned __int128)lat[b].ny * (unsigned __int128)lat[b].nz;
         if (t > max_cells) max_cells = t;
+        max_axis = std::max<int64_t>(max_axis, std::max(std::max(lat[b].nx, lat[b].ny), lat[b].nz));
     }
-    const int shift = std::max(1, bits_for(max_cells));
+    int shift = std::max(1, bits_for(max_cells));
+    if (flavour == kLatSearch) {
+        // Morton keys: three interleaved axes of bits(max axis) bits each
+        if (max_axis > (1ll << 21)) return set_error(B3D_E_RANGE, "search grid needs more than 2^21 cells on an axis (cell size too small)");
+        shift = 3 * std::max(1, bits_for((unsigned __int128)max_axis));
+    }
     const int cloud_bits = bits_for((unsigned __int128)B);
     if (shift + cloud_bits > 63) return set_error(B3D_E_RANGE, "voxel_size is too small. (cell lattice needs %d + %d key bits)", shift, cloud_bits);
     const int end_bit = shift + cloud_bits;

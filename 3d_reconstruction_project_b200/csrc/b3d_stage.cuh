@@ -77,7 +77,7 @@ __device__ __forceinline__ int warp_stage_box(const GridView<double>& g, int clo
             const int t = ci / (int)cn[2];
             const int yc = t % (int)cn[1], xc = t / (int)cn[1];
             const long long x = c0[0] + xc, y = c0[1] + yc, z = c0[2] + zc;
-            const unsigned long long key = cloud_bits | (unsigned long long)((x * L.ny + y) * L.nz + z);
+            const unsigned long long key = cloud_bits | lattice_key(L, x, y, z);
             int e;
             if (grid_lookup(g, key, s, e)) cnt = e - s;
         }
