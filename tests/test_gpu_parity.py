@@ -381,3 +381,36 @@ def test_information_matrix(ops):
     out = ops.information_matrix(src, tgt, 0.03, cur_o)
     assert np.allclose(out, ref, rtol=1e-12, atol=1e-9) and np.array_equal(out, out.T)
     assert abs(out[3, 3] - out[4, 4]) < 1e-9 and out[3, 3] > 0.9 * len(src)
+
+
+def test_correspondences_far_from_origin_and_dense_duplicates(ops):
+    """The staged search scans float32 offsets from a local centre: results must stay bit-exact for clouds far from the origin
+    (large absolute coordinates) and for targets with many coincident / nearly coincident points (float rounding band)."""
+    tgt, _ = golden_cloud("output_00094")
+    rng = np.random.default_rng(31)
+    T = small_rigid()
+    for offset in ((1000.0, -2000.0, 500.0), (-1.0e5, 3.0e4, 7.0e4)):
+        t2 = tgt + np.array(offset)
+        s2 = oracle.transform(np.linalg.inv(T), tgt)[0][::2] + np.array(offset)
+        rc, rn, _ = oracle.correspondences(s2, t2, None, 0.02)
+        gc, gn, _ = ops.correspondences(s2, t2, None, 0.02)
+        assert np.array_equal(gc, rc) and gn == rn
+    # duplicates and 1e-9-scale perturbations of the same targets: the winner is decided by the exact float64 rule
+    dup = np.concatenate([tgt, tgt[::3], tgt[::5] + rng.normal(0, 1e-9, (len(tgt[::5]), 3))])
+    src = tgt[::2] + rng.normal(0, 1e-4, (len(tgt[::2]), 3))
+    rc, rn, rs = oracle.correspondences(src, dup, None, 0.02)
+    gc, gn, gs = ops.correspondences(src, dup, None, 0.02)
+    assert np.array_equal(gc, rc) and gn == rn
+
+
+def test_knn_far_from_origin(ops):
+    pts = surface_cloud(30_000, seed=37) + np.array([5.0e3, -7.0e3, 1.0e3])
+    for k, r in ((30, 0.02), (12, 0.0)):
+        ri, rd, rc = oracle.knn(pts, pts[::5], k, r)
+        gi, gd, gc = ops.knn(pts, pts[::5], k, r)
+        assert np.array_equal(gc, rc) and np.array_equal(gi, ri) and np.array_equal(gd, rd)
+    ref = oracle.normals_legacy(pts, 30, 0.02)
+    out = ops.estimate_normals_legacy(pts, 30, 0.02)
+    # raw-moment covariances lose digits far from the origin (in the reference too): only the well-conditioned bulk is compared
+    d = np.abs(out - ref).max(axis=1)
+    assert np.quantile(d, 0.9) < 1e-3

@@ -248,3 +248,21 @@ def test_replay_scan_example(b3, tmp_path):
     assert ne.has_normals() and np.allclose(np.linalg.norm(np.asarray(ne.normals), axis=1), 1.0, atol=1e-5)
     if len(processed.points):
         assert with_normals.has_normals()
+
+
+def test_pair_pipeline_degenerate_frames(b3):
+    """A batch mixing a normal pair with an empty (all-zero depth) source frame and an empty target frame: rs.pointcloud keeps
+    zero-depth pixels as (0,0,0), so an empty frame is a one-voxel cloud; results must match the oracle chain pair by pair."""
+    from b200recon import ops
+    src, tgt, _ = _pairs(3, SMALL_CAM)
+    src[1][:] = 0
+    tgt[2][:] = 0
+    params = ops.make_pair_params(**SMALL_CAM, voxel_size=0.02, normals_max_nn=30, normals_radius=0.05, icp_kind=1, icp_max_dist=0.05, icp_max_iter=30)
+    res = ops.register_depth_pairs(src, tgt, params)
+    for i in range(3):
+        ref = oracle_pair(src[i], tgt[i], SMALL_CAM, 0.02, 30, 0.05, 1, 0.05, 30)
+        r = res[i]
+        assert r["m_source"] == ref["m_source"] and r["m_target"] == ref["m_target"]
+        assert abs(r["fitness"] - ref["fitness"]) < 1e-4 and abs(r["inlier_rmse"] - ref["inlier_rmse"]) < 1e-4
+        assert np.abs(r["transformation"] - ref["transformation"]).max() < 1e-5
+    assert res[1]["m_source"] == 1 and res[2]["m_target"] == 1
