@@ -9,11 +9,38 @@
 namespace b3d {
 namespace {
 
+// Hilbert index of (x, y, z) with `bits` bits per axis (Skilling's transpose form, then bit interleave): consecutive
+// indices are face-adjacent cells, so runs of consecutive points are spatially tighter than along a Morton curve.
+__device__ __forceinline__ unsigned long long hilbert3(uint32_t x, uint32_t y, uint32_t z, int bits) {
+    uint32_t X[3] = {x, y, z};
+    const uint32_t M = 1u << (bits - 1);
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (X[i] & Q) {
+                X[0] ^= P;
+            } else {
+                const uint32_t t = (X[0] ^ X[i]) & P;
+                X[0] ^= t;
+                X[i] ^= t;
+            }
+        }
+    }
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    uint32_t t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t; X[1] ^= t; X[2] ^= t;
+    return (morton_spread3(X[0]) << 2) | (morton_spread3(X[1]) << 1) | morton_spread3(X[2]);
+}
+
 // Morton key of the (transformed) query on a quarter-cell lattice of its cloud's search grid: consecutive keys are
 // spatially compact, so the 32 queries of a warp fit a small box (and stay compact under rigid updates).
 __global__ void __launch_bounds__(256) chunk_key_kernel(const double* __restrict__ pts, const int32_t* __restrict__ off, const double* __restrict__ transforms,
-                                                        int transform_stride, const Lattice* __restrict__ lat, int shift, uint64_t* __restrict__ keys,
-                                                        uint32_t* __restrict__ order) {
+                                                        int transform_stride, const Lattice* __restrict__ lat, int shift, int hilbert_bits,
+                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ order) {
     const int cloud = blockIdx.y;
     const Lattice L = lat[cloud];
     double T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
@@ -30,7 +57,10 @@ __global__ void __launch_bounds__(256) chunk_key_kernel(const double* __restrict
         // one cell of margin below the lattice origin; everything farther out clamps to the border
         const double ux = fmin(fmax(floor((px - L.ox) / q) + 4.0, 0.0), hi), uy = fmin(fmax(floor((py - L.oy) / q) + 4.0, 0.0), hi),
                      uz = fmin(fmax(floor((pz - L.oz) / q) + 4.0, 0.0), hi);
-        const unsigned long long m = (morton_spread3((unsigned long long)ux) << 2) | (morton_spread3((unsigned long long)uy) << 1) | morton_spread3((unsigned long long)uz);
+        const unsigned long long cap = (1ull << (shift / 3)) - 1ull;  // coordinates beyond the keyed range clamp to the border
+        const unsigned long long ix = min((unsigned long long)ux, cap), iy = min((unsigned long long)uy, cap), iz = min((unsigned long long)uz, cap);
+        const unsigned long long m = hilbert_bits > 0 ? hilbert3((uint32_t)ix, (uint32_t)iy, (uint32_t)iz, hilbert_bits)
+                                                      : (morton_spread3(ix) << 2) | (morton_spread3(iy) << 1) | morton_spread3(iz);
         keys[i] = ((unsigned long long)cloud << shift) | (m & ((1ull << shift) - 1ull));
         order[i] = (uint32_t)i;
     }
@@ -47,6 +77,31 @@ struct ChunkPred {
         const uint64_t k = keys[i];
         const int64_t rel = i - off[(int)(k >> shift)];
         return (rel & 31) == 0 || (k >> block_bits) != (keys[i - 1] >> block_bits);
+    }
+};
+// gap-based chunking: runs of consecutive sorted points without a jump longer than tau; chunks = every 32 points of a run
+struct GapPred {
+    const double4* pts;
+    const uint64_t* keys;
+    int shift;
+    double tau2;
+    __device__ __forceinline__ bool operator()(int64_t i) const {
+        if (i == 0 || (keys[i] >> shift) != (keys[i - 1] >> shift)) return true;  // first point of a cloud
+        const double4 a = pts[i], b = pts[i - 1];
+        const double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+        return dx * dx + dy * dy + dz * dz > tau2;
+    }
+};
+struct RunChunkPred {
+    const int32_t* heads;  // sorted run heads
+    const int64_t* n_heads;
+    __device__ __forceinline__ bool operator()(int64_t i) const {
+        int lo = 0, hi = (int)*n_heads;  // last head <= i
+        while (hi - lo > 1) {
+            const int m = (lo + hi) >> 1;
+            if ((int64_t)heads[m] <= i) lo = m; else hi = m;
+        }
+        return ((i - (int64_t)heads[lo]) & 31) == 0;
     }
 };
 struct ChunkEmit {
@@ -78,6 +133,24 @@ __global__ void __launch_bounds__(256) chunk_gather_kernel(const double* __restr
 }
 
 }  // namespace
+
+// chunk_start / n_chunks from sorted keys (+ sorted points for the gap rule)
+static int cut_chunks(b3d_ctx* ctx, const uint64_t* keys, const double4* pts, const int32_t* off_d, int shift, int block_bits, double cell, int32_t n,
+                      int32_t* chunk_start, int64_t* n_chunks_d) {
+    static const bool by_blocks = getenv("B3D_CHUNK_BLOCKS") != nullptr;
+    if (by_blocks) return compact(ctx, ChunkPred{keys, off_d, shift, block_bits}, ChunkEmit{chunk_start}, n, n_chunks_d);
+    // runs of spatially consecutive points (no jump longer than 1.5 cells), then a chunk every 32 points of a run: chunks
+    // are full except at the end of a run, and compact because the curve does not jump inside a run
+    DevBuf<int32_t> heads;
+    DevBuf<int64_t> n_heads;
+    B3D_TRY(heads.alloc(ctx, (size_t)n));
+    B3D_TRY(n_heads.alloc(ctx, 1));
+    double tau_cells = 2.0;
+    if (const char* e = getenv("B3D_CHUNK_GAP")) tau_cells = atof(e);
+    const double tau = tau_cells * cell;
+    B3D_TRY(compact(ctx, GapPred{pts, keys, shift, tau * tau}, ChunkEmit{heads.p}, n, n_heads.p));
+    return compact(ctx, RunChunkPred{heads.p, n_heads.p}, ChunkEmit{chunk_start}, n, n_chunks_d);
+}
 
 int build_query_chunks(b3d_ctx* ctx, const double* pts, const int32_t* off_d, const std::vector<int32_t>& off_h, const SpatialSort& lattices,
                        const double* transforms, int transform_stride, QueryChunks* out) {
@@ -125,7 +198,8 @@ int build_query_chunks(b3d_ctx* ctx, const double* pts, const int32_t* off_d, co
     B3D_TRY(o_in.alloc(ctx, n));
     B3D_TRY(o_out.alloc(ctx, n));
     const int kb = (int)std::min<int64_t>((longest + 255) / 256, std::max(1, ctx->sm_count * 16 / B));
-    B3D_LAUNCH(ctx, chunk_key_kernel, dim3(std::max(1, kb), B), 256, 0, pts, off_d, transforms, transform_stride, lattices.lat.p, shift, k_in.p, o_in.p);
+    B3D_LAUNCH(ctx, chunk_key_kernel, dim3(std::max(1, kb), B), 256, 0, pts, off_d, transforms, transform_stride, lattices.lat.p, shift,
+               getenv("B3D_CHUNK_MORTON") ? 0 : axis_bits, k_in.p, o_in.p);
     bool in_a = true;
     B3D_TRY(radix_sort_pairs(ctx, k_in.p, o_in.p, k_out.p, o_out.p, n, shift + bbits, &in_a));
     if (in_a) {
@@ -135,7 +209,7 @@ int build_query_chunks(b3d_ctx* ctx, const double* pts, const int32_t* off_d, co
     B3D_LAUNCH(ctx, chunk_gather_kernel, ctx->grid_for(n, 256, 1, 8), 256, 0, pts, o_out.p, n, out->pts.p);
     DevBuf<int64_t> n_chunks_d;
     B3D_TRY(n_chunks_d.alloc(ctx, 1));
-    B3D_TRY(compact(ctx, ChunkPred{k_out.p, off_d, shift, std::min(3 * level, shift)}, ChunkEmit{out->chunk_start.p}, n, n_chunks_d.p));
+    B3D_TRY(cut_chunks(ctx, k_out.p, out->pts.p, off_d, shift, std::min(3 * level, shift), lattices.lat_h[0].cell, n, out->chunk_start.p, n_chunks_d.p));
     B3D_LAUNCH(ctx, chunk_sentinel_kernel, 1, 1, 0, out->chunk_start.p, n_chunks_d.p, n);
     B3D_LAUNCH(ctx, chunk_ranges_kernel, (B + 1 + 127) / 128, 128, 0, out->chunk_start.p, n_chunks_d.p, off_d, B, out->chunk_off.p);
     B3D_TRY(ctx->download(out->chunk_off_h.data(), out->chunk_off.p, (size_t)(B + 1) * sizeof(int32_t)));
@@ -168,7 +242,7 @@ int chunks_from_grid(b3d_ctx* ctx, const Grid<double>& grid, const int32_t* off_
     if (const char* e = getenv("B3D_GRID_CHUNK_LEVEL")) level = atoi(e);
     DevBuf<int64_t> n_chunks_d;
     B3D_TRY(n_chunks_d.alloc(ctx, 1));
-    B3D_TRY(compact(ctx, ChunkPred{ss.keys.p, off_d, ss.shift, std::min(3 * level, ss.shift)}, ChunkEmit{out->chunk_start.p}, n, n_chunks_d.p));
+    B3D_TRY(cut_chunks(ctx, ss.keys.p, grid.pts.p, off_d, ss.shift, std::min(3 * level, ss.shift), grid.cell, n, out->chunk_start.p, n_chunks_d.p));
     B3D_LAUNCH(ctx, chunk_sentinel_kernel, 1, 1, 0, out->chunk_start.p, n_chunks_d.p, n);
     B3D_LAUNCH(ctx, chunk_ranges_kernel, (B + 1 + 127) / 128, 128, 0, out->chunk_start.p, n_chunks_d.p, off_d, B, out->chunk_off.p);
     B3D_TRY(ctx->download(out->chunk_off_h.data(), out->chunk_off.p, (size_t)(B + 1) * sizeof(int32_t)));

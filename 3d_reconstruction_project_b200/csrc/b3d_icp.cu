@@ -324,6 +324,7 @@ struct IcpKernelArgs {
     double* cache_box;   // [n_chunks][6]
     int* cache_count;    // [n_chunks], -1 = empty
     int* cache_idx;      // [n_chunks][kStageCap]
+    double reach_factor;  // first-round reach in units of the previous pass's inlier rmse
     int stats;  // count chunks / rounds / staged candidates into g_icp_stats
 };
 
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
     // converged pass are that close); lanes that are not certain after it trigger a second round at d_max
     const double dmax = sqrt(A.r2);
     double reach1 = dmax;
-    if (st->iter > 0) reach1 = fmin(dmax, fmax(3.0 * st->rmse, 0.2 * dmax));
+    if (st->iter > 0) reach1 = fmin(dmax, fmax(A.reach_factor * st->rmse, 0.2 * dmax));
     float4* cand = s_cand[warp];
     int* cand_pos = s_cand_pos[warp];
     // affine transforms (last row 0 0 0 1) need no perspective division: x / 1.0 == x exactly
@@ -369,19 +370,33 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
     const int32_t c0 = A.chunk_off[pair], c1 = A.chunk_off[pair + 1];
     const int groups = max(1, min((c1 - c0 + kIcpBlock / 32 - 1) / (kIcpBlock / 32), kIcpMaxGroups));
     if ((int)blockIdx.x >= groups) return;
-    for (int32_t c = c0 + blockIdx.x * (kIcpBlock / 32) + warp; c < c1; c += groups * (kIcpBlock / 32)) {
+    // the next chunk's query is fetched while the current one is processed (two dependent loads off the critical path)
+    const int32_t c_step = groups * (kIcpBlock / 32);
+    int32_t c = c0 + blockIdx.x * (kIcpBlock / 32) + warp;
+    double4 nsp = make_double4(0.0, 0.0, 0.0, 0.0);
+    bool nvalid = false;
+    if (c < c1) {
         const int32_t i = A.chunk_start[c] + lane;
-        const int32_t chunk_end = A.chunk_start[c + 1];
+        nvalid = i < A.chunk_start[c + 1];
+        if (nvalid) nsp = ld_point(A.src_sorted + i);
+    }
+    for (; c < c1; c += c_step) {
+        const double4 sp = nsp;
+        const bool valid = nvalid;
+        nvalid = false;
+        if (c + c_step < c1) {
+            const int32_t i = A.chunk_start[c + c_step] + lane;
+            nvalid = i < A.chunk_start[c + c_step + 1];
+            if (nvalid) nsp = ld_point(A.src_sorted + i);
+        }
         double e[kIcpRow];
 #pragma unroll
         for (int j = 0; j < kIcpRow; ++j) e[j] = 0.0;
         double W[9], gd[3], gp[3];  // generalized ICP only
         bool matched = false;
-        const bool valid = i < chunk_end;
         double px = 0, py = 0, pz = 0;
         int oi = 0;
         if (valid) {
-            const double4 sp = ld_point(A.src_sorted + i);
             oi = point_index(sp);  // original (batch-global) source index
             const double x = sp.x, y = sp.y, z = sp.z;
             // PointCloud::Transform: (T [p,1]).xyz / w
@@ -731,6 +746,10 @@ static IcpKernelArgs make_args(const IcpProblem& pb, IcpWork* w, int32_t* corr, 
     A.sums = w->sums.p;
     A.corr = corr;
     A.fused = fused ? 1 : 0;
+    {
+        static const double rf = getenv("B3D_ICP_REACH") ? atof(getenv("B3D_ICP_REACH")) : 2.5;
+        A.reach_factor = rf;
+    }
     A.cache_box = w->cache_box.p;
     A.cache_count = w->cache_count.p;
     A.cache_idx = w->cache_idx.p;
