@@ -16,7 +16,11 @@ def main(path):
     for r in rows[start:]:
         if len(r) <= vi:
             continue
-        name = r[ki].split("(")[0].replace("void ", "").replace("b3d::", "").replace("<unnamed>::", "").split("<")[0]
+        name = r[ki].replace("<unnamed>::", "").replace("b3d::", "").replace("void ", "").split("(")[0]
+        if name.startswith("compact_kernel<"):
+            name = "compact_kernel<" + name[len("compact_kernel<"):].split(",")[0].strip() + ">"
+        else:
+            name = name.split("<")[0]
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += float(r[vi].replace(",", ""))
