@@ -16,7 +16,7 @@ def main(path):
     for r in rows[start:]:
         if len(r) <= vi:
             continue
-        name = r[ki].replace("<unnamed>::", "").replace("b3d::", "").replace("void ", "").split("(")[0]
+        name = r[ki].replace("<unnamed>::", "").replace("unnamed>::", "").replace("b3d::", "").replace("void ", "").split("(")[0]
         if name.startswith("compact_kernel<"):
             name = "compact_kernel<" + name[len("compact_kernel<"):].split(",")[0].strip() + ">"
         else:
