@@ -83,11 +83,12 @@ namespace {
 template <typename T, int KMAX, bool TENSOR>
 __global__ void __launch_bounds__(128) normals_kernel(GridView<T> g, const uint64_t* __restrict__ keys, const int32_t* __restrict__ off, int k,
                                                       bool use_radius, T r2, int rmax, const T* __restrict__ prior, T* __restrict__ normals,
-                                                      const uint8_t* __restrict__ need) {
-    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= g.n) return;
+                                                      const int* __restrict__ todo, const int* __restrict__ todo_count) {
+    // todo == NULL: every point of the grid; else only the sorted positions the staged kernel flagged
+    const int n_work = todo != nullptr ? *todo_count : g.n;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_work; t += gridDim.x * blockDim.x) {
+    const int pos = todo != nullptr ? todo[t] : t;
     const typename PointT<T>::vec4 q = ld_point(g.pts + pos);
-    if (need != nullptr && need[point_index(q)] == 0) return;  // already done by the staged kernel
     const int cloud = (int)(keys[pos] >> g.shift);
     TopK<T, KMAX> tk;
     knn_hybrid_query<T, KMAX>(g, off, cloud, q.x, q.y, q.z, k, use_radius, r2, rmax, tk);
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(128) normals_kernel(GridView<T> g, const uint6
     normals[3 * oi] = nrm.x;
     normals[3 * oi + 1] = nrm.y;
     normals[3 * oi + 2] = nrm.z;
+    }
 }
 
 // ---- staged legacy normals (radius searches, k <= kNrmList) --------------------------------------------------------------
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(128) normals_kernel(GridView<T> g, const uint6
 // borderline candidates in float64 (exact d2 < r2 rule), and keeps the indices of its neighbours in a small shared list.
 // Neighbour SETS are exact; the nine raw moments are then summed in staged order (the reference sums in distance order:
 // same set, same arithmetic, a different order of float64 additions). Lanes that would need a k-nearest cut (more than k
-// neighbours inside the radius) or whose chunk overflows the staging buffers are flagged in `need` and are redone by the
+// neighbours inside the radius) or whose chunk overflows the staging buffers are queued (sorted positions) and redone by the
 // per-lane kernel afterwards.
 constexpr int kNrmBlock = 128;
 constexpr int kNrmList = 32;   // neighbours per lane kept in shared memory (k <= 32 on this path)
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(kNrmBlock) normals_staged_kernel(GridView<doub
                                                                   const int32_t* __restrict__ chunk_start, const int32_t* __restrict__ chunk_off,
                                                                   int B, int n_chunks, int k, double radius, double r2,
                                                                   const double* __restrict__ prior, double* __restrict__ normals,
-                                                                  uint8_t* __restrict__ need, int stats) {
+                                                                  int* __restrict__ todo, int* __restrict__ todo_count, int stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     NrmWarpSmem& S = reinterpret_cast<NrmWarpSmem*>(smem_raw)[warp];
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(kNrmBlock) normals_staged_kernel(GridView<doub
             }
         }
         if (count < 0) {
-            if (valid) need[oi] = 1;
+            if (valid) todo[atomicAdd(todo_count, 1)] = i;
             continue;
         }
         // ---- scan: neighbours with d2 < r2, kept sorted by (float) distance -------------------------------------------
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(kNrmBlock) normals_staged_kernel(GridView<doub
         if (!valid) continue;
         if (spill || n > k) {
             if (stats) atomicAdd(&g_nrm_stats[2], 1ull);
-            need[oi] = 1;  // needs the k nearest of more than k in-radius points: per-lane kernel
+            todo[atomicAdd(todo_count, 1)] = i;  // needs the k nearest of more than k in-radius points: per-lane kernel
             continue;
         }
         // order by distance (the reference accumulates its moments in (d2, index) order): insertion sort of the short list,
@@ -474,30 +476,34 @@ int estimate_normals_batch(b3d_ctx* ctx, const T* xyz, const Segments& seg, int 
     const T r = (T)radius;
     const T r2 = r * r;
     const int n = (int)grid->sort.n;
-    const int blocks = (n + 127) / 128;
-    const uint8_t* need = nullptr;
-    DevBuf<uint8_t> need_buf;
+    const int* todo = nullptr;
+    const int* todo_count = nullptr;
+    DevBuf<int> todo_buf, todo_count_buf;
+    int blocks = (n + 127) / 128;
     if constexpr (std::is_same<T, double>::value && !TENSOR) {
         if (use_radius && max_nn <= kNrmList) {
-            // staged fast path; the per-lane kernel below only redoes the flagged points
+            // staged fast path; the per-lane kernel below only redoes the queued points
             QueryChunks qc;
             B3D_TRY(chunks_from_grid(ctx, *grid, seg.off, seg.off_h, &qc));
-            B3D_TRY(need_buf.alloc(ctx, (size_t)n));
-            B3D_CUDA(cudaMemsetAsync(need_buf.p, 0, (size_t)n, ctx->stream));
+            B3D_TRY(todo_buf.alloc(ctx, (size_t)n));
+            B3D_TRY(todo_count_buf.alloc(ctx, 1));
+            B3D_CUDA(cudaMemsetAsync(todo_count_buf.p, 0, sizeof(int), ctx->stream));
             const int sblocks = std::max(1, std::min((qc.n_chunks + kNrmBlock / 32 - 1) / (kNrmBlock / 32), ctx->sm_count * 32));
             const size_t smem = sizeof(NrmWarpSmem) * (kNrmBlock / 32);
             B3D_CUDA(cudaFuncSetAttribute(normals_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             B3D_LAUNCH(ctx, normals_staged_kernel, sblocks, kNrmBlock, smem, grid->view(), qc.q, qc.chunk_start.p, qc.chunk_off.p, seg.B, qc.n_chunks, max_nn,
-                       radius, r2, prior, normals, need_buf.p, getenv("B3D_ICP_STATS") ? 1 : 0);
-            need = need_buf.p;
+                       radius, r2, prior, normals, todo_buf.p, todo_count_buf.p, getenv("B3D_ICP_STATS") ? 1 : 0);
+            todo = todo_buf.p;
+            todo_count = todo_count_buf.p;
+            blocks = std::min(blocks, ctx->sm_count * 4);  // the queue is short; the kernel strides over it
         }
     }
     if (max_nn <= 32) {
         B3D_LAUNCH(ctx, (normals_kernel<T, 32, TENSOR>), blocks, 128, 0, grid->view(), grid->sort.keys.p, seg.off, max_nn, use_radius, r2, rmax, prior,
-                   normals, need);
+                   normals, todo, todo_count);
     } else {
         B3D_LAUNCH(ctx, (normals_kernel<T, 64, TENSOR>), blocks, 128, 0, grid->view(), grid->sort.keys.p, seg.off, max_nn, use_radius, r2, rmax, prior,
-                   normals, need);
+                   normals, todo, todo_count);
     }
     return B3D_OK;
 }
