@@ -80,6 +80,7 @@ SIGNATURES = {
     "b3d_icp_correspondences": (_i, [_vp, _vp, _i64, _vp, _i64, C.POINTER(_d), _d, _vp, C.POINTER(_d)]),
     "b3d_information_matrix": (_i, [_vp, _vp, _i64, _vp, _i64, C.POINTER(_d), _d, C.POINTER(_d)]),
     "b3d_icp": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _d, C.POINTER(_d), _d, _d, _i, C.POINTER(IcpResult), _vp]),
+    "b3d_icp_batch": (_i, [_vp, _i, _i, _vp, _pi64, _vp, _vp, _pi64, _vp, _vp, _d, C.POINTER(_d), _d, _d, _i, C.POINTER(IcpResult), _vp]),
     "b3d_icp_begin": (_i, [_vp, _i, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _d, C.POINTER(_d), _d, _d, _i, C.POINTER(_vp)]),
     "b3d_icp_accumulate": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "b3d_icp_update": (_i, [_vp, _vp, C.POINTER(_i)]),

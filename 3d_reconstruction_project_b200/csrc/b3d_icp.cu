@@ -976,6 +976,55 @@ int b3d_icp(b3d_ctx* ctx, int kind, const double* src, int64_t ns, const double*
     return icp_results(ctx, st.pb, &st.work, result_h);
 }
 
+int b3d_icp_batch(b3d_ctx* ctx, int kind, int n_pairs, const double* src, const int64_t* src_off_h, const double* src_cov, const double* tgt,
+                  const int64_t* tgt_off_h, const double* tgt_normals, const double* tgt_cov, double max_dist, const double* init_h,
+                  double rel_fitness, double rel_rmse, int max_iter, b3d_icp_result* results_h, int32_t* corr) {
+    B3D_REQUIRE(ctx != nullptr && results_h != nullptr && src_off_h != nullptr && tgt_off_h != nullptr, "b3d_icp_batch: NULL argument");
+    B3D_REQUIRE(n_pairs >= 1, "b3d_icp_batch: n_pairs must be >= 1");
+    const int P = n_pairs;
+    B3D_REQUIRE(src_off_h[0] == 0 && tgt_off_h[0] == 0, "b3d_icp_batch: offsets must start at 0");
+    for (int p = 0; p < P; ++p)
+        B3D_REQUIRE(src_off_h[p + 1] >= src_off_h[p] && tgt_off_h[p + 1] >= tgt_off_h[p], "b3d_icp_batch: offsets must be non-decreasing");
+    const int64_t ns = src_off_h[P], nt = tgt_off_h[P];
+    B3D_REQUIRE(ns < (int64_t)INT32_MAX && nt < (int64_t)INT32_MAX, "b3d_icp_batch: more than 2^31-1 points");
+    B3D_TRY(validate_icp(kind, src, ns, src_cov, tgt, nt, tgt_normals, tgt_cov, max_dist, max_iter));
+    for (int p = 0; p < P; ++p) empty_result(init_h ? init_h + 16 * p : nullptr, &results_h[p]);
+    if (ns == 0) return B3D_OK;
+    B3D_TRY(ctx->bind());
+    if (corr) B3D_CUDA(cudaMemsetAsync(corr, 0xff, (size_t)ns * sizeof(int32_t), ctx->stream));
+    if (nt == 0) return ctx->sync();
+    b3d_icp_state st;
+    std::vector<int32_t> so(P + 1), to(P + 1);
+    for (int p = 0; p <= P; ++p) {
+        so[p] = (int32_t)src_off_h[p];
+        to[p] = (int32_t)tgt_off_h[p];
+    }
+    Segments sseg;
+    B3D_TRY(upload_segments(ctx, to, &st.tgt_off, &st.tgt_seg));
+    B3D_TRY(upload_segments(ctx, so, &st.src_off, &sseg));
+    int rmax = 1;
+    B3D_TRY(build_search_grid<double>(ctx, tgt, st.tgt_seg, 8, max_dist, &st.grid, &rmax));
+    IcpProblem& pb = st.pb;
+    pb.kind = kind;
+    pb.P = P;
+    pb.src = src;
+    pb.src_cov = src_cov;
+    pb.src_off = st.src_off.p;
+    pb.src_off_h = so;
+    pb.tgt_grid = &st.grid;
+    pb.tgt_off = st.tgt_off.p;
+    pb.tgt_normals = tgt_normals;
+    pb.tgt_cov = tgt_cov;
+    pb.max_dist = max_dist;
+    pb.rmax = rmax;
+    pb.rel_fitness = rel_fitness;
+    pb.rel_rmse = rel_rmse;
+    pb.max_iter = max_iter;
+    B3D_TRY(icp_prepare(ctx, pb, init_h, &st.work));
+    B3D_TRY(icp_run(ctx, pb, &st.work, corr));
+    return icp_results(ctx, pb, &st.work, results_h);
+}
+
 int b3d_icp_begin(b3d_ctx* ctx, int kind, const double* src, int64_t ns_local, int64_t ns_total, const double* src_cov, const double* tgt,
                   int64_t nt, const double* tgt_normals, const double* tgt_cov, double max_dist, const double* init_h, double rel_fitness,
                   double rel_rmse, int max_iter, b3d_icp_state** out) {

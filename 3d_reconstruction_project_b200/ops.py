@@ -261,6 +261,29 @@ def icp(kind, src, tgt, max_dist, init=None, tgt_normals=None, src_cov=None, tgt
     return _result_dict(r, None if corr is None else corr[:s.shape[0]].cpu().numpy())
 
 
+def icp_batch(kind, srcs, tgts, max_dist, inits=None, tgt_normals=None, src_covs=None, tgt_covs=None, rel_fitness=1e-6, rel_rmse=1e-6,
+              max_iter=30, device=0, want_corr=True):
+    """A batch of independent registrations in the same launches (b3d_icp_batch). srcs / tgts (and the optional per-cloud
+    normals / covariances): lists of [n_i, 3] arrays. Returns one result dict per pair, each equal to the single-pair icp()."""
+    ctx = get_context(device)
+    P = len(srcs)
+    if P == 0 or len(tgts) != P:
+        raise ValueError("icp_batch needs equally long, non-empty lists of sources and targets")
+    cat = lambda arrs, cols: None if arrs is None else ctx.to_device(np.concatenate([np.asarray(a, dtype=np.float64).reshape(-1, cols) for a in arrs]), torch.float64)
+    so = np.concatenate([[0], np.cumsum([len(a) for a in srcs])]).astype(np.int64)
+    to = np.concatenate([[0], np.cumsum([len(a) for a in tgts])]).astype(np.int64)
+    s, t = cat(srcs, 3), cat(tgts, 3)
+    tn, sc, tc = cat(tgt_normals, 3), cat(src_covs, 9), cat(tgt_covs, 9)
+    corr = ctx.empty((max(int(so[-1]), 1),), torch.int32) if want_corr else None
+    init = None if inits is None else (C.c_double * (16 * P))(*np.asarray(inits, dtype=np.float64).reshape(-1))
+    res = (N.IcpResult * P)()
+    N.check(N.lib().b3d_icp_batch(ctx.handle, int(kind), P, ptr(s), so.ctypes.data_as(C.POINTER(C.c_int64)), ptr(sc), ptr(t),
+                                  to.ctypes.data_as(C.POINTER(C.c_int64)), ptr(tn), ptr(tc), float(max_dist), init, float(rel_fitness), float(rel_rmse),
+                                  int(max_iter), res, ptr(corr)))
+    ch = None if corr is None else corr.cpu().numpy()
+    return [_result_dict(res[p], None if ch is None else ch[so[p]:so[p + 1]]) for p in range(P)]
+
+
 # ---- whole path ----------------------------------------------------------------------------------------------------
 def make_pair_params(w, h, fx, fy, ppx, ppy, depth_scale=0.001, voxel_size=0.005, normals_max_nn=30, normals_radius=0.01,
                      icp_kind=N.ICP_POINT_TO_PLANE, icp_max_dist=0.02, icp_rel_fitness=1e-6, icp_rel_rmse=1e-6, icp_max_iter=30):

@@ -162,6 +162,16 @@ int b3d_icp(b3d_ctx* ctx, int kind, const double* src, int64_t ns, const double*
             const double* tgt_normals, const double* tgt_cov, double max_dist, const double* init_h, double rel_fitness,
             double rel_rmse, int max_iter, b3d_icp_result* result_h, int32_t* corr);
 
+/* A batch of n_pairs independent registrations in the same launches (grid.y = pair): pair p registers
+ * src[src_off_h[p] .. src_off_h[p+1]) onto tgt[tgt_off_h[p] .. tgt_off_h[p+1]) (offsets in points, HOST arrays of n_pairs + 1
+ * entries starting at 0; normals / covariances are indexed like their clouds). init_h: n_pairs x 16 doubles or NULL.
+ * results_h: [n_pairs]; corr (optional): int32 [total source points], target indices local to the pair's target cloud.
+ * A pair's result is bit-identical to the single-pair b3d_icp call. An empty target cloud inside a non-empty batch is an error
+ * of the grid build only when ALL targets are empty; empty pairs return fitness 0 and their init. */
+int b3d_icp_batch(b3d_ctx* ctx, int kind, int n_pairs, const double* src, const int64_t* src_off_h, const double* src_cov, const double* tgt,
+                  const int64_t* tgt_off_h, const double* tgt_normals, const double* tgt_cov, double max_dist, const double* init_h,
+                  double rel_fitness, double rel_rmse, int max_iter, b3d_icp_result* results_h, int32_t* corr);
+
 /* Step-wise ICP for one cloud sharded by SOURCE points over several GPUs (BASELINE config 5). Each rank holds a
  * contiguous slice of the source and a replica of the target. Per iteration:
  *   b3d_icp_accumulate  -> fills sums (29 doubles on the device: 21 JtJ upper + 6 Jtr + |C| + sum d2)

@@ -414,3 +414,23 @@ def test_knn_far_from_origin(ops):
     # raw-moment covariances lose digits far from the origin (in the reference too): only the well-conditioned bulk is compared
     d = np.abs(out - ref).max(axis=1)
     assert np.quantile(d, 0.9) < 1e-3
+
+
+def test_icp_batch_equals_single_calls(ops):
+    """b3d_icp_batch: pairs of different sizes (one with an empty source) in the same launches; each pair bit-identical to b3d_icp."""
+    clouds = [golden_cloud(n) for n in ("output_00094", "output84_00008", "output_00050")]
+    T = small_rigid()
+    srcs = [oracle.transform(np.linalg.inv(T), c[0])[0][::k] for c, k in zip(clouds, (1, 2, 3))]
+    srcs.append(np.zeros((0, 3)))
+    tgts = [c[0] for c in clouds] + [clouds[0][0][:500]]
+    nrms = [c[1] for c in clouds] + [clouds[0][1][:500]]
+    res = ops.icp_batch(1, srcs, tgts, 0.02, tgt_normals=nrms, max_iter=30)
+    assert len(res) == 4 and res[3]["fitness"] == 0 and np.array_equal(res[3]["transformation"], np.eye(4))
+    for i in range(3):
+        single = ops.icp(1, srcs[i], tgts[i], 0.02, tgt_normals=nrms[i], max_iter=30)
+        assert np.array_equal(res[i]["transformation"], single["transformation"])
+        assert res[i]["fitness"] == single["fitness"] and res[i]["inlier_rmse"] == single["inlier_rmse"] and res[i]["iterations"] == single["iterations"]
+        assert np.array_equal(res[i]["corr"], single["corr"])
+        ref = oracle.icp(1, srcs[i], tgts[i], 0.02, tgt_normals=nrms[i], max_iter=30)
+        assert rot_err(res[i]["transformation"][:3, :3], ref["transformation"][:3, :3]) < 1e-5
+        assert np.array_equal(res[i]["corr"], ref["corr"])
