@@ -66,19 +66,6 @@ __global__ void __launch_bounds__(256) chunk_key_kernel(const double* __restrict
     }
 }
 
-// a new chunk starts every 32 sorted points (counted from the cloud start) and wherever the Morton block
-// (2^level quarter-cells on a side; the cloud id sits above it) changes
-struct ChunkPred {
-    const uint64_t* keys;
-    const int32_t* off;
-    int shift;
-    int block_bits;  // 3 * level: Morton bits below the block id
-    __device__ __forceinline__ bool operator()(int64_t i) const {
-        const uint64_t k = keys[i];
-        const int64_t rel = i - off[(int)(k >> shift)];
-        return (rel & 31) == 0 || (k >> block_bits) != (keys[i - 1] >> block_bits);
-    }
-};
 // gap-based chunking: runs of consecutive sorted points without a jump longer than tau; chunks = every 32 points of a run
 struct GapPred {
     const double4* pts;
@@ -135,10 +122,8 @@ __global__ void __launch_bounds__(256) chunk_gather_kernel(const double* __restr
 }  // namespace
 
 // chunk_start / n_chunks from sorted keys (+ sorted points for the gap rule)
-static int cut_chunks(b3d_ctx* ctx, const uint64_t* keys, const double4* pts, const int32_t* off_d, int shift, int block_bits, double cell, int32_t n,
+static int cut_chunks(b3d_ctx* ctx, const uint64_t* keys, const double4* pts, int shift, double cell, int32_t n,
                       int32_t* chunk_start, int64_t* n_chunks_d) {
-    static const bool by_blocks = getenv("B3D_CHUNK_BLOCKS") != nullptr;
-    if (by_blocks) return compact(ctx, ChunkPred{keys, off_d, shift, block_bits}, ChunkEmit{chunk_start}, n, n_chunks_d);
     // runs of spatially consecutive points (no jump longer than 1.5 cells), then a chunk every 32 points of a run: chunks
     // are full except at the end of a run, and compact because the curve does not jump inside a run
     DevBuf<int32_t> heads;
@@ -154,17 +139,6 @@ static int cut_chunks(b3d_ctx* ctx, const uint64_t* keys, const double4* pts, co
 
 int build_query_chunks(b3d_ctx* ctx, const double* pts, const int32_t* off_d, const std::vector<int32_t>& off_h, const SpatialSort& lattices,
                        const double* transforms, int transform_stride, QueryChunks* out) {
-    // Morton block level: blocks of 2^level quarter-cells should hold a few chunks' worth of points (surface model:
-    // points per block ~ occupancy * (cells per side)^2), so that most chunks are full; level 3 = 2 cells per side
-    int level = 3;
-    {
-        const double occ = (double)lattices.n / (double)std::max<int64_t>(1, lattices.n_runs);
-        const double cells_per_side = std::sqrt(64.0 / std::max(occ, 0.25));
-        level = (int)std::lround(2.0 + std::log2(std::max(cells_per_side, 1.0)));
-        level = std::min(std::max(level, 2), 7);
-        if (const char* e = getenv("B3D_CHUNK_LEVEL")) level = atoi(e);
-    }
-
     const int B = (int)off_h.size() - 1;
     const int32_t n = off_h[B];
     out->chunk_off_h.assign(B + 1, 0);
@@ -209,7 +183,7 @@ int build_query_chunks(b3d_ctx* ctx, const double* pts, const int32_t* off_d, co
     B3D_LAUNCH(ctx, chunk_gather_kernel, ctx->grid_for(n, 256, 1, 8), 256, 0, pts, o_out.p, n, out->pts.p);
     DevBuf<int64_t> n_chunks_d;
     B3D_TRY(n_chunks_d.alloc(ctx, 1));
-    B3D_TRY(cut_chunks(ctx, k_out.p, out->pts.p, off_d, shift, std::min(3 * level, shift), lattices.lat_h[0].cell, n, out->chunk_start.p, n_chunks_d.p));
+    B3D_TRY(cut_chunks(ctx, k_out.p, out->pts.p, shift, lattices.lat_h[0].cell, n, out->chunk_start.p, n_chunks_d.p));
     B3D_LAUNCH(ctx, chunk_sentinel_kernel, 1, 1, 0, out->chunk_start.p, n_chunks_d.p, n);
     B3D_LAUNCH(ctx, chunk_ranges_kernel, (B + 1 + 127) / 128, 128, 0, out->chunk_start.p, n_chunks_d.p, off_d, B, out->chunk_off.p);
     B3D_TRY(ctx->download(out->chunk_off_h.data(), out->chunk_off.p, (size_t)(B + 1) * sizeof(int32_t)));
@@ -235,14 +209,9 @@ int chunks_from_grid(b3d_ctx* ctx, const Grid<double>& grid, const int32_t* off_
         B3D_CUDA(cudaMemsetAsync(out->chunk_off.p, 0, (size_t)(B + 1) * sizeof(int32_t), ctx->stream));
         return B3D_OK;
     }
-    // Morton block = 2^level cells on a side, sized to hold a few chunks' worth of points (surface model)
-    const double occ = (double)ss.n / (double)std::max<int64_t>(1, ss.n_runs);
-    int level = (int)std::lround(std::log2(std::max(std::sqrt(64.0 / std::max(occ, 0.25)), 1.0)));
-    level = std::min(std::max(level, 0), 6);
-    if (const char* e = getenv("B3D_GRID_CHUNK_LEVEL")) level = atoi(e);
     DevBuf<int64_t> n_chunks_d;
     B3D_TRY(n_chunks_d.alloc(ctx, 1));
-    B3D_TRY(cut_chunks(ctx, ss.keys.p, grid.pts.p, off_d, ss.shift, std::min(3 * level, ss.shift), grid.cell, n, out->chunk_start.p, n_chunks_d.p));
+    B3D_TRY(cut_chunks(ctx, ss.keys.p, grid.pts.p, ss.shift, grid.cell, n, out->chunk_start.p, n_chunks_d.p));
     B3D_LAUNCH(ctx, chunk_sentinel_kernel, 1, 1, 0, out->chunk_start.p, n_chunks_d.p, n);
     B3D_LAUNCH(ctx, chunk_ranges_kernel, (B + 1 + 127) / 128, 128, 0, out->chunk_start.p, n_chunks_d.p, off_d, B, out->chunk_off.p);
     B3D_TRY(ctx->download(out->chunk_off_h.data(), out->chunk_off.p, (size_t)(B + 1) * sizeof(int32_t)));

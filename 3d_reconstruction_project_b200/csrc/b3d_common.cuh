@@ -60,7 +60,6 @@ struct b3d_ctx {
     bool own_stream = false;
     int sm_count = 148;
     int64_t launches = 0;      // hand-written kernels
-    int64_t lib_launches = 0;  // CUB device-wide primitives, counted per call
     void* pinned = nullptr;    // pinned host staging block (results, counters); valid until the next call that uses it
     size_t pinned_bytes = 0;
     // per-kernel timing (off by default): one event pair per launch, resolved by prof_report()
@@ -146,12 +145,6 @@ struct DevBuf {
 template <typename T>
 __host__ __device__ __forceinline__ T dist2(T dx, T dy, T dz) {
     return (dx * dx + dy * dy) + dz * dz;  // fixed association, no FMA (-fmad=false)
-}
-
-// (d2, index) lexicographic order: the library-wide tie-break
-template <typename T>
-__device__ __forceinline__ bool cand_less(T d2a, int ia, T d2b, int ib) {
-    return d2a < d2b || (d2a == d2b && ia < ib);
 }
 
 template <typename T>
@@ -379,15 +372,6 @@ int single_segment(b3d_ctx* ctx, int64_t n, DevBuf<int32_t>* storage, Segments* 
 int upload_segments(b3d_ctx* ctx, const std::vector<int32_t>& off_h, DevBuf<int32_t>* storage, Segments* seg);
 
 // ---------------------------------------------------------------------------------------------------------
-// stream compaction of a predicate (single pass, decoupled look-back): out[j] = i for the j-th i with pred(i).
-// ---------------------------------------------------------------------------------------------------------
-struct ScanState {
-    DevBuf<unsigned long long> tile_status;  // per tile: (flag << 62) | value
-    DevBuf<unsigned int> ticket;
-    DevBuf<int64_t> total;  // device count
-};
-
-// ---------------------------------------------------------------------------------------------------------
 // neighbour-search grid (device view, passed to kernels by value)
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
@@ -429,9 +413,10 @@ struct Grid {
 template <typename T>
 int grid_build(b3d_ctx* ctx, const T* xyz, const Segments& seg, double cell, const std::vector<double>* bounds_h, Grid<T>* out);
 
-// Queries re-ordered along a Morton curve (quarter-cell lattice of a search grid) and cut into warp chunks: <= 32
-// consecutive points that never span more than one Morton block (sized to hold a few chunks) and never straddle clouds; cut points are relative
-// to the cloud start, so the chunking of a cloud does not depend on the rest of the batch.
+// Queries re-ordered along a space-filling curve (Hilbert on a quarter-cell lattice of a search grid, or the grid's own
+// Morton cell order) and cut into warp chunks: the sorted points are split into runs wherever two consecutive points are
+// more than two cells apart (the curve jumped) or a new cloud starts, and every run is cut every 32 points. Chunks are
+// mostly full, spatially compact, never straddle clouds, and depend only on their own cloud (not on the rest of the batch).
 struct QueryChunks {
     const double4* q = nullptr;   // the queries in chunk order (pts.p, or a search grid's own sorted points)
     DevBuf<double4> pts;          // [n] queries in Morton order, .w = original (batch-global) index (empty when q aliases a grid)
