@@ -173,6 +173,17 @@ def covariances_from_normals(normals, eps=1e-3, device=0, as_tensor=False):
     return _out(cov, as_tensor)
 
 
+def compute_fpfh(points, normals, max_nn, radius, device=0, as_tensor=False):
+    """o3d.pipelines.registration.compute_fpfh_feature(pcd, KDTreeSearchParamHybrid(radius, max_nn)) -- test/mini1.py:244-250.
+    -> [N, 33] float64 (the transpose of Open3D's Feature.data)."""
+    ctx = get_context(device)
+    p, nr = ctx.to_device(points, torch.float64), ctx.to_device(normals, torch.float64)
+    _check_n3(p, "points")
+    out = ctx.empty((p.shape[0], 33), torch.float64)
+    N.check(N.lib().b3d_compute_fpfh(ctx.handle, ptr(p), ptr(nr), p.shape[0], int(max_nn), float(radius), ptr(out)))
+    return _out(out, as_tensor)
+
+
 def _outlier(fn, points, a, b, device, as_tensor):
     ctx = get_context(device)
     p = ctx.to_device(points, torch.float64)

@@ -103,3 +103,32 @@ def get_information_matrix_from_point_clouds(source, target, max_correspondence_
     if not source.has_points() or not target.has_points():
         return np.zeros((6, 6))
     return ops.information_matrix(np.asarray(source.points), np.asarray(target.points), max_correspondence_distance, transformation, device=source.device)
+
+
+class Feature:
+    """o3d.pipelines.registration.Feature: data is [dimension, N]."""
+
+    def __init__(self, data):
+        self.data = data
+
+    def dimension(self):
+        return self.data.shape[0]
+
+    def num(self):
+        return self.data.shape[1]
+
+
+def compute_fpfh_feature(input, search_param):
+    """test/mini1.py:244-250, test/check2.py:95-100: FPFH descriptors (33 x N)."""
+    from .geometry import KDTreeSearchParamHybrid, KDTreeSearchParamKNN
+    pcd = as_cloud(input)
+    if not pcd.has_normals():
+        raise RuntimeError("Failed because input point cloud has no normal.")
+    if isinstance(search_param, KDTreeSearchParamHybrid):
+        k, r = search_param.max_nn, search_param.radius
+    elif isinstance(search_param, KDTreeSearchParamKNN):
+        k, r = search_param.knn, 0.0
+    else:
+        raise RuntimeError("compute_fpfh_feature: only KDTreeSearchParamHybrid / KDTreeSearchParamKNN are supported")
+    f = ops.compute_fpfh(np.asarray(pcd.points), np.asarray(pcd.normals), k, r, device=pcd.device)
+    return Feature(np.ascontiguousarray(f.T))

@@ -120,6 +120,11 @@ int b3d_estimate_normals_tensor(b3d_ctx* ctx, const float* xyz, int64_t n, int m
 /* GICP covariances from normals, C = R diag(eps,1,1) R^T -- inside registration_generalized_icp, test/GICP1.py:99-102 */
 int b3d_covariances_from_normals(b3d_ctx* ctx, const double* normals, int64_t n, double eps, double* cov);
 
+/* compute_fpfh_feature(pcd, KDTreeSearchParamHybrid(radius, max_nn)) -- test/mini1.py:244-250, test/check2.py:95-100 (the
+ * descriptor behind the reference's RANSAC initialisation). normals are required; max_nn <= 128; radius <= 0: KNN.
+ * out: float64 [n, 33] row-major (Open3D's Feature.data is its transpose). */
+int b3d_compute_fpfh(b3d_ctx* ctx, const double* xyz, const double* normals, int64_t n, int max_nn, double radius, double* out);
+
 /* ---- outlier filters -------------------------------------------------------------------------------------- */
 /* remove_statistical_outlier(nb_neighbors, std_ratio) -- pointcloud_processing.py:35-36, test/mini1.py:175.
  * keep: uint8 [n]; kept_idx: int64 [n] ascending indices (optional); n_kept_h: count. */

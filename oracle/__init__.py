@@ -201,6 +201,14 @@ def information_matrix(src, tgt, dmax, T=None):
     return out
 
 
+def fpfh(points, normals, max_nn, radius):
+    points = _c(points, np.float64)
+    normals = _c(normals, np.float64)
+    out = np.empty((len(points), 33), np.float64)
+    lib().orc_fpfh(_p(points), _p(normals), C.c_int64(len(points)), int(max_nn), C.c_double(radius), _p(out))
+    return out
+
+
 P2P, P2L, GICP = 0, 1, 2
 
 

@@ -1007,6 +1007,96 @@ int64_t orc_information_matrix(const double* src, int64_t ns, const double* tgt,
     return r.n;
 }
 
+// ---- compute_fpfh_feature(pcd, KDTreeSearchParamHybrid(r, k)) -- test/mini1.py:244-250, check2.py:95-100 ("next" row of SURVEY.md 8f)
+// [PARITY UNPINNED: restated from Open3D's Feature.cpp]. SPFH: per point, pair features (alpha, phi, theta) of every neighbour
+// (self excluded) binned into 3 x 11 bins with increment 100 / (n - 1); FPFH: sum over the neighbours of spfh_j / d2_j, each
+// 11-bin group normalised to 100, plus the point's own SPFH. out: [n, 33] row-major.
+static void pair_features(const double* p1, const double* n1, const double* p2, const double* n2, double* f) {
+    f[0] = f[1] = f[2] = f[3] = 0.0;
+    double d[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+    const double dist = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    if (dist == 0.0) return;
+    double a[3] = {n1[0], n1[1], n1[2]}, b[3] = {n2[0], n2[1], n2[2]};
+    const double angle1 = (a[0] * d[0] + a[1] * d[1] + a[2] * d[2]) / dist;
+    const double angle2 = (b[0] * d[0] + b[1] * d[1] + b[2] * d[2]) / dist;
+    double f2;
+    if (std::acos(std::fabs(angle1)) > std::acos(std::fabs(angle2))) {
+        for (int k = 0; k < 3; ++k) { a[k] = n2[k]; b[k] = n1[k]; d[k] = -d[k]; }
+        f2 = -angle2;
+    } else {
+        f2 = angle1;
+    }
+    double v[3] = {d[1] * a[2] - d[2] * a[1], d[2] * a[0] - d[0] * a[2], d[0] * a[1] - d[1] * a[0]};
+    const double vn = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (vn == 0.0) return;
+    for (int k = 0; k < 3; ++k) v[k] /= vn;
+    const double w[3] = {a[1] * v[2] - a[2] * v[1], a[2] * v[0] - a[0] * v[2], a[0] * v[1] - a[1] * v[0]};
+    f[3] = dist;
+    f[2] = f2;
+    f[1] = v[0] * b[0] + v[1] * b[1] + v[2] * b[2];
+    f[0] = std::atan2(w[0] * b[0] + w[1] * b[1] + w[2] * b[2], a[0] * b[0] + a[1] * b[1] + a[2] * b[2]);
+}
+static inline int bin11(double t) {
+    int h = (int)std::floor(11.0 * t);
+    return h < 0 ? 0 : (h > 10 ? 10 : h);
+}
+void orc_fpfh(const double* pts, const double* nrm, int64_t n, int k, double radius, double* out) {
+    KdTree<double> tree;
+    tree.build(pts, n);
+    std::vector<int32_t> nb((size_t)n * k);
+    std::vector<double> nd((size_t)n * k);
+    std::vector<int32_t> cnt(n);
+    std::vector<double> spfh((size_t)n * 33, 0.0);
+    const double pi = 3.14159265358979323846;
+#pragma omp parallel
+    {
+        std::vector<KdTree<double>::Cand> heap(k);
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t i = 0; i < n; ++i) {
+            const int c = hybrid<double>(tree, pts + 3 * i, k, radius, heap.data());
+            cnt[i] = c;
+            for (int j = 0; j < c; ++j) { nb[i * k + j] = heap[j].i; nd[i * k + j] = heap[j].d2; }
+            if (c > 1) {
+                const double incr = 100.0 / (double)(c - 1);
+                double* h = &spfh[(size_t)i * 33];
+                for (int j = 1; j < c; ++j) {
+                    double f[4];
+                    const int64_t q = heap[j].i;
+                    pair_features(pts + 3 * i, nrm + 3 * i, pts + 3 * q, nrm + 3 * q, f);
+                    h[bin11((f[0] + pi) / (2.0 * pi))] += incr;
+                    h[11 + bin11((f[1] + 1.0) * 0.5)] += incr;
+                    h[22 + bin11((f[2] + 1.0) * 0.5)] += incr;
+                }
+            }
+        }
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t i = 0; i < n; ++i) {
+            double* o = out + (size_t)i * 33;
+            for (int j = 0; j < 33; ++j) o[j] = 0.0;
+            const int c = cnt[i];
+            if (c > 1) {
+                double sum[3] = {0, 0, 0};
+                for (int t = 1; t < c; ++t) {
+                    const double dist = nd[i * k + t];
+                    if (dist == 0.0) continue;
+                    const double* sj = &spfh[(size_t)nb[i * k + t] * 33];
+                    for (int j = 0; j < 33; ++j) {
+                        const double val = sj[j] / dist;
+                        sum[j / 11] += val;
+                        o[j] += val;
+                    }
+                }
+                for (int g = 0; g < 3; ++g)
+                    if (sum[g] != 0.0) sum[g] = 100.0 / sum[g];
+                for (int j = 0; j < 33; ++j) {
+                    o[j] *= sum[j / 11];
+                    o[j] += spfh[(size_t)i * 33 + j];
+                }
+            }
+        }
+    }
+}
+
 // ---- a10/a11: registration_icp / registration_generalized_icp. SURVEY.md A.6 [PARITY UNPINNED] ----
 // kind: 0 point-to-point (pointcloud_alignment.py:35-39), 1 point-to-plane (test/mini1.py:293-296),
 //       2 generalized (test/GICP1.py:99-102; src_cov/tgt_cov [n,9] required).

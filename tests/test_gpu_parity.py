@@ -434,3 +434,19 @@ def test_icp_batch_equals_single_calls(ops):
         ref = oracle.icp(1, srcs[i], tgts[i], 0.02, tgt_normals=nrms[i], max_iter=30)
         assert rot_err(res[i]["transformation"][:3, :3], ref["transformation"][:3, :3]) < 1e-5
         assert np.array_equal(res[i]["corr"], ref["corr"])
+
+
+def test_fpfh_features(ops):
+    """compute_fpfh_feature(Hybrid(0.1, 100)) as in test/mini1.py:244-250 on a fixture cloud with its own normals."""
+    pts, nrm = golden_cloud("output_00094")
+    for k, r in ((100, 0.1), (30, 0.05), (20, 0.0)):
+        ref = oracle.fpfh(pts, nrm, k, r)
+        out = ops.compute_fpfh(pts, nrm, k, r)
+        assert out.shape == ref.shape == (len(pts), 33)
+        # histogram bins are integer decisions on float64 features (libm acos / atan2 differ in the last ulp): a handful of
+        # points may move one increment between adjacent bins; everything else agrees to rounding
+        bad = np.abs(out - ref).max(axis=1) > 1e-6
+        assert bad.mean() < 2e-3, bad.mean()
+        assert np.allclose(out.sum(axis=1), ref.sum(axis=1), atol=1e-6)
+    with pytest.raises(RuntimeError, match="max_nn must be in"):
+        ops.compute_fpfh(pts[:10], nrm[:10], 200, 0.1)
