@@ -80,6 +80,8 @@ struct b3d_ctx {
     std::multimap<size_t, void*> cache_free;
     std::unordered_map<void*, size_t> cache_live;
     size_t cache_total = 0;
+    size_t cache_free_bytes = 0;
+    size_t cache_cap_bytes = (size_t)16 << 30;
     void cache_release_all();
 
     int bind() const;

@@ -57,6 +57,7 @@ int b3d_ctx::alloc_bytes(void** p, size_t bytes) {
     if (it != cache_free.end() && it->first <= want + want / 2 + (1u << 20)) {
         *p = it->second;
         cache_live[*p] = it->first;
+        cache_free_bytes -= it->first;
         cache_free.erase(it);
         return B3D_OK;
     }
@@ -70,6 +71,7 @@ int b3d_ctx::alloc_bytes(void** p, size_t bytes) {
             cache_total -= kv.first;
         }
         cache_free.clear();
+        cache_free_bytes = 0;
         e = cudaMalloc(p, want);
     }
     if (e != cudaSuccess) {
@@ -86,7 +88,19 @@ void b3d_ctx::free_async(void* p) {
     auto it = cache_live.find(p);
     if (it == cache_live.end()) return;
     cache_free.emplace(it->second, p);
+    cache_free_bytes += it->second;
     cache_live.erase(it);
+    // Workloads whose sizes keep changing (a growing map, different batch sizes) would let the free list grow without bound:
+    // above the cap the idle blocks go back to the driver (after the stream drained; the next step re-allocates what it needs).
+    if (cache_free_bytes > cache_cap_bytes) {
+        cudaStreamSynchronize(stream);
+        for (auto& kv : cache_free) {
+            cudaFree(kv.second);
+            cache_total -= kv.first;
+        }
+        cache_free.clear();
+        cache_free_bytes = 0;
+    }
 }
 void b3d_ctx::cache_release_all() {
     cudaStreamSynchronize(stream);
@@ -95,6 +109,7 @@ void b3d_ctx::cache_release_all() {
     cache_free.clear();
     cache_live.clear();
     cache_total = 0;
+    cache_free_bytes = 0;
 }
 int b3d_ctx::sync() {
     SlowCall sc("cudaStreamSynchronize", 0);
@@ -237,7 +252,10 @@ int b3d_ctx_create(int device, void* stream, b3d_ctx** out) {
     c->stream = reinterpret_cast<cudaStream_t>(stream);
     c->own_stream = false;
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        c->sm_count = prop.multiProcessorCount;
+        c->cache_cap_bytes = prop.totalGlobalMem / 4;  // idle scratch kept for re-use: at most a quarter of the device memory
+    }
     c->pinned_bytes = 4096;
     if (cudaMallocHost(&c->pinned, c->pinned_bytes) != cudaSuccess) {
         if (c->own_stream) cudaStreamDestroy(c->stream);

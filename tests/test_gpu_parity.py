@@ -450,3 +450,47 @@ def test_fpfh_features(ops):
         assert np.allclose(out.sum(axis=1), ref.sum(axis=1), atol=1e-6)
     with pytest.raises(RuntimeError, match="max_nn must be in"):
         ops.compute_fpfh(pts[:10], nrm[:10], 200, 0.1)
+
+
+def test_fuzz_small_random_clouds(ops):
+    """Many small random configurations (sizes 1..3000, clustered / duplicated / planar / far-apart points, random voxel sizes,
+    k and radii): every integer / index result bit-exact against the oracle. Exercises the tile edges of the scan, the
+    one-chunk / one-cell grids and the isolated-point fallbacks."""
+    rng = np.random.default_rng(2024)
+    for case in range(40):
+        n = int(rng.choice([1, 2, 3, 5, 31, 32, 33, 64, 100, 257, 1000, 3000]))
+        kind = case % 4
+        if kind == 0:
+            pts = rng.normal(0, 0.05, (n, 3))
+        elif kind == 1:  # planar patch with duplicates
+            pts = np.column_stack([rng.random(n) * 0.2, rng.random(n) * 0.2, np.zeros(n)])
+            pts[rng.random(n) < 0.2] = pts[0]
+        elif kind == 2:  # two clusters far apart
+            pts = np.concatenate([rng.normal(0, 0.01, (n // 2 + 1, 3)), rng.normal(5.0, 0.01, (n - n // 2 - 1 if n > 1 else 0, 3))])[:n]
+        else:  # lattice (exact ties)
+            s = int(np.ceil(n ** (1 / 3)))
+            g = np.stack(np.meshgrid(np.arange(s), np.arange(s), np.arange(s), indexing="ij"), -1).reshape(-1, 3)[:n] * 0.01
+            pts = g.astype(np.float64)
+        pts = np.ascontiguousarray(pts + rng.choice([0.0, 10.0, -3.0]))
+        vs = float(rng.choice([0.003, 0.01, 0.05, 1.0]))
+        ref = oracle.voxel_legacy(pts, vs)
+        out = ops.voxel_down_sample_legacy(pts, vs)
+        assert np.array_equal(out["index"], ref["index"]) and np.array_equal(out["points"], ref["points"]), (case, n, vs)
+        p32 = pts.astype(np.float32)
+        ref = oracle.voxel_tensor(p32, vs)
+        out = ops.voxel_down_sample_tensor(p32, vs)
+        assert np.array_equal(out["index"], ref["index"]) and np.array_equal(out["points"], ref["points"]), (case, n, vs)
+        k = int(rng.choice([1, 5, 30, 64]))
+        r = float(rng.choice([0.0, 0.015, 0.05]))
+        ri, rd, rc = oracle.knn(pts, pts, k, r)
+        gi, gd, gc = ops.knn(pts, pts, k, r)
+        assert np.array_equal(gc, rc) and np.array_equal(gi, ri) and np.array_equal(gd, rd), (case, n, k, r)
+        src = pts + rng.normal(0, 0.002, pts.shape)
+        dmax = float(rng.choice([0.005, 0.02, 0.3]))
+        rcorr, rn, _ = oracle.correspondences(src, pts, None, dmax)
+        gcorr, gn, _ = ops.correspondences(src, pts, None, dmax)
+        assert np.array_equal(gcorr, rcorr) and gn == rn, (case, n, dmax)
+        if n >= 3:
+            rk = oracle.radius_outlier(pts, 2, 0.02)
+            gk, _ = ops.remove_radius_outlier(pts, 2, 0.02)
+            assert np.array_equal(gk, rk), (case, n)
