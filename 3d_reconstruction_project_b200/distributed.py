@@ -53,13 +53,17 @@ def all_reduce_sums(sums, group=None):
     return sums
 
 
-def icp_loop(accumulate, update, all_reduce=all_reduce_sums, max_passes=1000):
+def icp_loop(accumulate, update, all_reduce=all_reduce_sums, max_passes=1000, check_every=1):
     """The sharded ICP driver: accumulate() -> tensor of 29 sums (local shard), all-reduce, update() -> done flag.
-    Backend-agnostic so that the CPU tests can drive it with a stand-in shard; returns the number of passes."""
+    Backend-agnostic so that the CPU tests can drive it with a stand-in shard; returns the number of passes.
+    check_every > 1: the done flag is read back (a host synchronisation) only every check_every-th pass; the passes in
+    between are enqueued blindly, which is safe because a finished state ignores further accumulate / update calls and every
+    rank sees the same all-reduced sums, hence the same flag."""
     for k in range(max_passes):
         sums = accumulate()
         all_reduce(sums)
-        if update():
+        look = check_every <= 1 or (k % check_every) == check_every - 1
+        if update(look) if check_every > 1 else update():
             return k + 1
     raise RuntimeError("sharded ICP did not terminate")
 
@@ -96,7 +100,11 @@ class ShardedICP:
         N.check(N.lib().b3d_icp_accumulate(self.ctx.handle, self.handle, C.byref(p)))
         return torch.as_tensor(_DevArray(p.value, ICP_SUMS), device=self.ctx.device)
 
-    def update(self):
+    def update(self, look=True):
+        """Applies the update from the (all-reduced) sums. look=False skips reading the done flag back (no host sync)."""
+        if not look:
+            N.check(N.lib().b3d_icp_update(self.ctx.handle, self.handle, None))
+            return False
         done = C.c_int(0)
         N.check(N.lib().b3d_icp_update(self.ctx.handle, self.handle, C.byref(done)))
         return bool(done.value)
@@ -110,8 +118,8 @@ class ShardedICP:
         self.handle = None
         return _result_dict(r, corr[:self.n_local].cpu().numpy())
 
-    def run(self, group=None):
-        icp_loop(self.accumulate, self.update, lambda s: all_reduce_sums(s, group))
+    def run(self, group=None, check_every=2):
+        icp_loop(self.accumulate, self.update, lambda s: all_reduce_sums(s, group), check_every=check_every)
         return self.finish()
 
 
