@@ -85,6 +85,8 @@ SIGNATURES = {
     "b3d_icp_begin": (_i, [_vp, _i, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _d, C.POINTER(_d), _d, _d, _i, C.POINTER(_vp)]),
     "b3d_icp_accumulate": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "b3d_icp_update": (_i, [_vp, _vp, C.POINTER(_i)]),
+    "b3d_icp_set_peers": (_i, [_vp, _vp, _i, _i, C.POINTER(_vp)]),
+    "b3d_icp_pass_peers": (_i, [_vp, _vp, C.POINTER(_i)]),
     "b3d_icp_finish": (_i, [_vp, _vp, C.POINTER(IcpResult), _vp]),
     "b3d_register_depth_pair": (_i, [_vp, C.POINTER(PairParams), _vp, _vp, _i, C.POINTER(PairResult)]),
     "b3d_register_depth_pairs": (_i, [_vp, C.POINTER(PairParams), _vp, _vp, _i, _i, C.POINTER(PairResult)]),

@@ -324,6 +324,11 @@ struct IcpKernelArgs {
     double* cache_box;   // [n_chunks][6]
     int* cache_count;    // [n_chunks], -1 = empty
     int* cache_idx;      // [n_chunks][kStageCap]
+    // peer exchange (one cloud sharded over several GPUs, P == 1): after the local second pass the last block writes its 29
+    // sums into every rank's exchange buffer over NVLink, waits for all ranks' flags of this pass and adds the slots in rank
+    // order -- the all-reduce happens inside the pass kernel, no collective launch in between
+    int peer_world, peer_rank;
+    double* peer_buf[8];
     double reach_factor;  // first-round reach in units of the previous pass's inlier rmse
     int stats;  // count chunks / rounds / staged candidates into g_icp_stats
 };
@@ -591,6 +596,60 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
         A.sums[(int64_t)pair * kIcpSums + threadIdx.x] = t;
     }
     __syncthreads();
+    if (A.peer_world > 1) {
+        // ---- all-reduce over peer memory. Buffer of a rank: slots [2 parities][world][32] doubles, then flags [2][world]
+        // (pass number + 1 as a double). Two parities: a rank can be at most one pass ahead of the slowest reader.
+        const int W = A.peer_world;
+        const unsigned int pass = st->pass_id;
+        const int parity = (int)(pass & 1u);
+        const double stamp = (double)(pass + 1u);
+        if (threadIdx.x < kIcpSums) {
+            const double mine = sm[0][threadIdx.x];
+            for (int r = 0; r < W; ++r) {
+                volatile double* slot = A.peer_buf[r] + ((int64_t)parity * W + A.peer_rank) * 32;
+                slot[threadIdx.x] = mine;
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < W) {
+            volatile double* flag = A.peer_buf[threadIdx.x] + (int64_t)2 * W * 32 + (int64_t)parity * W + A.peer_rank;
+            *flag = stamp;
+        }
+        __shared__ int s_timeout;
+        if (threadIdx.x == 0) s_timeout = 0;
+        __syncthreads();
+        if ((int)threadIdx.x < W) {
+            volatile double* flag = A.peer_buf[A.peer_rank] + (int64_t)2 * W * 32 + (int64_t)parity * W + threadIdx.x;
+            const long long t0c = clock64();
+            while (*flag != stamp) {
+                if (clock64() - t0c > 4000000000ll) {  // ~2 s: a peer never arrived
+                    s_timeout = 1;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        __threadfence_system();
+        if (threadIdx.x < kIcpSums) {
+            double t = 0.0;
+            for (int r = 0; r < W; ++r) {
+                volatile double* slot = A.peer_buf[A.peer_rank] + ((int64_t)parity * W + r) * 32;
+                t += slot[threadIdx.x];
+            }
+            sm[0][threadIdx.x] = t;
+            A.sums[(int64_t)pair * kIcpSums + threadIdx.x] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            st->pass_id = pass + 1u;
+            if (s_timeout) {
+                st->done = 1;
+                st->converged = -1;  // exchange timed out
+            }
+        }
+        if (s_timeout) return;
+    }
     if (threadIdx.x == 0) {
         st->ticket = 0;
 #ifndef B3D_TEST_NO_FINALIZE
@@ -628,6 +687,7 @@ __global__ void icp_init_state_kernel(IcpPairState* state, const double* __restr
     s.done = 0;
     s.converged = 0;
     s.ticket = 0;
+    s.pass_id = 0;
     state[pair] = s;
 }
 
@@ -723,7 +783,7 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
 }
 
 static IcpKernelArgs make_args(const IcpProblem& pb, IcpWork* w, int32_t* corr, bool fused) {
-    IcpKernelArgs A;
+    IcpKernelArgs A{};
     A.kind = pb.kind;
     A.src_sorted = w->chunks.q;
     A.chunk_start = w->chunks.chunk_start.p;
@@ -756,6 +816,11 @@ static IcpKernelArgs make_args(const IcpProblem& pb, IcpWork* w, int32_t* corr, 
     {
         static const int stats_on = getenv("B3D_ICP_STATS") ? 1 : 0;
         A.stats = stats_on;
+    }
+    if (fused && w->peer_world > 1) {
+        A.peer_world = w->peer_world;
+        A.peer_rank = w->peer_rank;
+        for (int r = 0; r < w->peer_world; ++r) A.peer_buf[r] = w->peer_buf[r];
     }
     return A;
 }
@@ -1058,6 +1123,33 @@ int b3d_icp_accumulate(b3d_ctx* ctx, b3d_icp_state* st, double** sums_dev_out) {
     }
     st->pending_sums = true;
     *sums_dev_out = st->work.sums.p;
+    return B3D_OK;
+}
+
+int b3d_icp_set_peers(b3d_ctx* ctx, b3d_icp_state* st, int rank, int world, void* const* peer_bufs_h) {
+    B3D_REQUIRE(ctx != nullptr && st != nullptr && peer_bufs_h != nullptr, "b3d_icp_set_peers: NULL argument");
+    B3D_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "b3d_icp_set_peers: rank %d / world %d out of range (world <= 8)", rank, world);
+    st->work.peer_world = world;
+    st->work.peer_rank = rank;
+    for (int r = 0; r < world; ++r) {
+        B3D_REQUIRE(peer_bufs_h[r] != nullptr, "b3d_icp_set_peers: peer buffer %d is NULL", r);
+        st->work.peer_buf[r] = static_cast<double*>(peer_bufs_h[r]);
+    }
+    return B3D_OK;
+}
+
+int b3d_icp_pass_peers(b3d_ctx* ctx, b3d_icp_state* st, int* done_h) {
+    B3D_REQUIRE(ctx != nullptr && st != nullptr, "b3d_icp_pass_peers: NULL argument");
+    if (st->work.peer_world < 1) return set_error(B3D_E_STATE, "b3d_icp_pass_peers called before b3d_icp_set_peers");
+    B3D_REQUIRE(st->pb.src_off_h[1] > 0, "b3d_icp_pass_peers: every rank needs a non-empty shard of the source");
+    B3D_TRY(ctx->bind());
+    B3D_TRY(icp_pass(ctx, st->pb, &st->work, st->corr.p, true));
+    if (done_h) {
+        IcpPairState s;
+        B3D_TRY(ctx->download(&s, st->work.state.p, sizeof(s)));
+        if (s.converged < 0) return set_error(B3D_E_STATE, "peer exchange timed out: a rank did not arrive within ~2 s");
+        *done_h = s.done;
+    }
     return B3D_OK;
 }
 

@@ -14,8 +14,9 @@ struct IcpPairState {
     long long n_corr;
     int iter;       // updates applied so far
     int done;       // the loop has finished
-    int converged;  // stopped by the relative criteria
+    int converged;  // stopped by the relative criteria (-1: the peer exchange timed out)
     unsigned int ticket;
+    unsigned int pass_id;  // passes executed (stamps of the peer exchange)
 };
 
 struct IcpProblem {
@@ -46,6 +47,8 @@ struct IcpWork {
     DevBuf<double> cache_box;  // staged-set cache of the pass kernel (per chunk)
     DevBuf<int> cache_count, cache_idx;
     int blocks = 1;
+    int peer_world = 0, peer_rank = 0;  // exchange over peer memory (b3d_icp_set_peers)
+    double* peer_buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h /*[P][16] or NULL*/, IcpWork* w);

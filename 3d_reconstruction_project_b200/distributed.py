@@ -118,6 +118,43 @@ class ShardedICP:
         self.handle = None
         return _result_dict(r, corr[:self.n_local].cpu().numpy())
 
+    # ---- fused exchange over peer memory (NVLink): no collective launch between the reduction and the solve ------------
+    def enable_peers(self, group=None):
+        """Allocates this rank's exchange buffer in symmetric memory and maps every peer's buffer (rendezvous over the
+        process group). After this, run_fused() advances the loop with ONE kernel launch per pass on every rank."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world > 8:
+            raise RuntimeError("the fused exchange supports up to 8 ranks (one NVSwitch domain)")
+        n = 2 * world * 32 + 2 * world
+        buf = symm_mem.empty(n, dtype=torch.float64, device=self.ctx.device)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, group=(group or dist.group.WORLD))
+        torch.cuda.synchronize(self.ctx.device)
+        dist.barrier(group)
+        # every rank's buffer as a tensor view in THIS process (peer mapping over NVLink); touching it checks the mapping
+        views = [hdl.get_buffer(r, (n,), torch.float64) for r in range(world)]
+        for v in views:
+            assert float(v.sum().item()) == 0.0
+        ptrs = (C.c_void_p * world)(*[C.c_void_p(v.data_ptr()) for v in views])
+        N.check(N.lib().b3d_icp_set_peers(self.ctx.handle, self.handle, rank, world, ptrs))
+        self._peer = (buf, hdl, views)  # keep the mapping alive
+
+    def pass_fused(self, look=True):
+        if not look:
+            N.check(N.lib().b3d_icp_pass_peers(self.ctx.handle, self.handle, None))
+            return False
+        done = C.c_int(0)
+        N.check(N.lib().b3d_icp_pass_peers(self.ctx.handle, self.handle, C.byref(done)))
+        return bool(done.value)
+
+    def run_fused(self, check_every=2, max_passes=1000):
+        for k in range(max_passes):
+            if self.pass_fused(look=(k % check_every) == check_every - 1):
+                return self.finish()
+        raise RuntimeError("sharded ICP did not terminate")
+
     def run(self, group=None, check_every=2):
         icp_loop(self.accumulate, self.update, lambda s: all_reduce_sums(s, group), check_every=check_every)
         return self.finish()

@@ -189,6 +189,15 @@ int b3d_icp_begin(b3d_ctx* ctx, int kind, const double* src, int64_t ns_local, i
 int b3d_icp_accumulate(b3d_ctx* ctx, b3d_icp_state* st, double** sums_dev_out);
 int b3d_icp_update(b3d_ctx* ctx, b3d_icp_state* st, int* done_h);
 int b3d_icp_finish(b3d_ctx* ctx, b3d_icp_state* st, b3d_icp_result* result_h, int32_t* corr);
+/* Fused variant of accumulate -> all-reduce -> update: every rank owns an exchange buffer of B3D_ICP_PEER_DOUBLES(world)
+ * doubles, zero-initialised, mapped into every other rank's address space (CUDA IPC / symmetric memory over NVLink);
+ * peer_bufs_h[r] is rank r's buffer as seen from THIS process. b3d_icp_pass_peers launches ONE kernel per pass: the last
+ * block writes the 29 local sums into every rank's buffer, waits for all ranks' stamps of this pass, adds the slots in rank
+ * order (identical result on every rank) and applies the update. All ranks must call it the same number of times
+ * (they see the same done flag); world <= 8. done_h may be NULL (no host synchronisation). */
+#define B3D_ICP_PEER_DOUBLES(world) (2 * (world) * 32 + 2 * (world))
+int b3d_icp_set_peers(b3d_ctx* ctx, b3d_icp_state* st, int rank, int world, void* const* peer_bufs_h);
+int b3d_icp_pass_peers(b3d_ctx* ctx, b3d_icp_state* st, int* done_h);
 
 /* ---- whole-path entry points with HOST buffers (what the reference-facing Python classes call; e2e) -------- */
 typedef struct b3d_pair_params {

@@ -179,6 +179,44 @@ def test_stepwise_icp_two_shards_equal_single(b3):
     assert np.array_equal(corr, single["corr"])
 
 
+def test_fused_pass_single_rank_equals_icp(b3):
+    """b3d_icp_pass_peers with a world of one: the pass kernel runs the update itself (one launch per pass, no exchange)
+    and must land on exactly the single-call result."""
+    import ctypes as C
+    import torch
+    from b200recon import _native as N, distributed as dist, ops
+    tgt, nrm = golden_cloud("output_00094")
+    src = oracle.transform(np.linalg.inv(small_rigid()), tgt)[0]
+    single = ops.icp(1, src, tgt, 0.02, tgt_normals=nrm, max_iter=30)
+    sh = dist.ShardedICP(1, src, len(src), tgt, 0.02, tgt_normals=nrm, max_iter=30)
+    buf = torch.zeros(2 * 32 + 2, dtype=torch.float64, device="cuda")
+    ptrs = (C.c_void_p * 1)(C.c_void_p(buf.data_ptr()))
+    N.check(N.lib().b3d_icp_set_peers(sh.ctx.handle, sh.handle, 0, 1, ptrs))
+    res = sh.run_fused(check_every=1)
+    assert np.array_equal(res["transformation"], single["transformation"])
+    assert res["iterations"] == single["iterations"] and res["fitness"] == single["fitness"]
+    assert np.array_equal(res["corr"], single["corr"])
+
+
+def test_fused_peer_exchange_two_gpus(b3):
+    """Config 5 over two GPUs: the all-reduce inside the pass kernel (peer memory) gives the NCCL path's result bit for bit."""
+    import json, os, subprocess, sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = []
+    for k, extra in enumerate(([], ["--fused"])):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", str(29641 + k), os.path.join(root, "tools", "bench_sharded_icp.py"), "--side", "700"] + extra
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out.append(json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1]))
+    for key in ("fitness", "inlier_rmse", "rot_err_rad", "trans_err_m", "iterations", "passes"):
+        assert out[0][key] == out[1][key], key
+    assert out[1]["exchange"].startswith("peer-memory")
+
+
 def test_reproject_disparity_valid_bit_exact(b3):
     from b200recon import ops, synth
     s, _, Q, _ = synth.disparity_pair(2000, 2001, w=408, h=306, scale=0.425)

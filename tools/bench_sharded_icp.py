@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--side", type=int, default=3162)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--dmax", type=float, default=0.005)
+    ap.add_argument("--fused", action="store_true", help="all-reduce inside the pass kernel over peer memory (NVLink) instead of NCCL")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -72,16 +73,23 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    if a.fused and world > 1:
+        sh.enable_peers()
     while True:
         e0, e1, e2 = ev(), ev(), ev()
-        e0.record()
-        sums = sh.accumulate()
-        e1.record()
-        D.all_reduce_sums(sums)
-        e2.record()
-        marks.append((e0, e1, e2))
         look = passes % 2 == 1  # the done flag is read back (host sync) every other pass only
-        done = sh.update(look)
+        e0.record()
+        if a.fused and world > 1:
+            e1.record()
+            e2.record()
+            done = sh.pass_fused(look)
+        else:
+            sums = sh.accumulate()
+            e1.record()
+            D.all_reduce_sums(sums)
+            e2.record()
+            done = sh.update(look)
+        marks.append((e0, e1, e2))
         passes += 1
         if done:
             break
@@ -99,9 +107,12 @@ def main():
     if rank == 0:
         rot, tr = synth.transform_error(res["transformation"], T)
         per_pass = total_ms / passes  # device time of the whole loop (updates and flag reads included), max over ranks
+        fused = a.fused and world > 1
         print(json.dumps({"config": "config5: one cloud sharded by source points, point-to-plane, all-reduce of 29 doubles per pass",
-                          "n_points": n, "n_gpus": world, "passes": passes, "ms_per_pass": per_pass, "accumulate_ms_per_pass": acc_ms / passes,
-                          "allreduce_ms_per_pass": red_ms / passes, "allreduce_share": red_ms / (acc_ms + red_ms),
+                          "n_points": n, "n_gpus": world, "exchange": ("peer-memory, fused in the pass kernel" if fused else "nccl all_reduce"),
+                          "passes": passes, "ms_per_pass": per_pass, "accumulate_ms_per_pass": None if fused else acc_ms / passes,
+                          "allreduce_ms_per_pass": None if fused else red_ms / passes,
+                          "allreduce_share": None if fused else red_ms / (acc_ms + red_ms),
                           "mpoints_per_sec": n / (per_pass * 1e-3) / 1e6, "setup_s": t_setup, "fitness": res["fitness"],
                           "inlier_rmse": res["inlier_rmse"], "rot_err_rad": rot, "trans_err_m": tr, "iterations": res["iterations"]}))
     if world > 1:
