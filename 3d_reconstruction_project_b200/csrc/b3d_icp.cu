@@ -23,6 +23,7 @@ namespace {
 constexpr int kIcpBlock = 128;
 constexpr int kIcpInformation = 3;  // internal kind: G^T G of get_information_matrix_from_point_clouds (rows from the target point)
 constexpr int kIcpMaxGroups = 1024;  // partial-sum groups (blocks) per pair
+constexpr double kIcpReach2 = 1.25;   // second-round reach of the staged search in units of d_max (see the pass kernel)
 
 // ---- small dense helpers (device) ----------------------------------------------------------------------------------
 __device__ void mat4_mul(const double* A, const double* B, double* C) {
@@ -319,11 +320,12 @@ struct IcpKernelArgs {
     double* sums;
     int32_t* corr;
     int fused;
-    // per-chunk cache of the staged candidate set (sorted positions) and of the box it covers: later passes whose box lies
-    // inside re-stage from it without touching the hash grid
-    double* cache_box;   // [n_chunks][6]
-    int* cache_count;    // [n_chunks], -1 = empty
-    int* cache_idx;      // [n_chunks][kStageCap]
+    // sticky correspondences: per source point (sorted position) the nearest target found by its last full search, the
+    // transformed position it was searched from and a lower bound of the distance of every OTHER target point at that
+    // time. While the point has moved less than the slack between the two, the nearest neighbour cannot have changed
+    // and the lane skips the search (exact: same partner, distance recomputed in float64).
+    float4* keep_ref;   // [ns] x, y, z of the query at search time; w = lower bound of the runner-up distance (0 = none)
+    int32_t* keep_pos;  // [ns] sorted target position of the nearest neighbour, -1 = nothing within the searched reach
     // peer exchange (one cloud sharded over several GPUs, P == 1): after the local second pass the last block writes its 29
     // sums into every rank's exchange buffer over NVLink, waits for all ranks' flags of this pass and adds the slots in rank
     // order -- the all-reduce happens inside the pass kernel, no collective launch in between
@@ -379,20 +381,38 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
     const int32_t c_step = groups * (kIcpBlock / 32);
     int32_t c = c0 + blockIdx.x * (kIcpBlock / 32) + warp;
     double4 nsp = make_double4(0.0, 0.0, 0.0, 0.0);
+    float4 nkr = make_float4(0.f, 0.f, 0.f, 0.f);
+    int nkp = -1;
+    int32_t ni = 0;
     bool nvalid = false;
     if (c < c1) {
-        const int32_t i = A.chunk_start[c] + lane;
-        nvalid = i < A.chunk_start[c + 1];
-        if (nvalid) nsp = ld_point(A.src_sorted + i);
+        ni = A.chunk_start[c] + lane;
+        nvalid = ni < A.chunk_start[c + 1];
+        if (nvalid) {
+            nsp = ld_point(A.src_sorted + ni);
+            if (A.keep_ref != nullptr) {
+                nkr = A.keep_ref[ni];
+                nkp = A.keep_pos[ni];
+            }
+        }
     }
     for (; c < c1; c += c_step) {
         const double4 sp = nsp;
+        const float4 kr = nkr;
+        const int kp = nkp;
+        const int32_t si = ni;
         const bool valid = nvalid;
         nvalid = false;
         if (c + c_step < c1) {
-            const int32_t i = A.chunk_start[c + c_step] + lane;
-            nvalid = i < A.chunk_start[c + c_step + 1];
-            if (nvalid) nsp = ld_point(A.src_sorted + i);
+            ni = A.chunk_start[c + c_step] + lane;
+            nvalid = ni < A.chunk_start[c + c_step + 1];
+            if (nvalid) {
+                nsp = ld_point(A.src_sorted + ni);
+                if (A.keep_ref != nullptr) {
+                    nkr = A.keep_ref[ni];
+                    nkp = A.keep_pos[ni];
+                }
+            }
         }
         double e[kIcpRow];
 #pragma unroll
@@ -413,14 +433,43 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
                 px /= w; py /= w; pz /= w;
             }
         }
-        // ---- correspondence: staged warp search (bit-identical to nn_within_query) ------------------------------
+        // ---- correspondence: sticky check, then staged warp search (bit-identical to nn_within_query) --------------
         double d2 = 0.0;
         int idx = 0, pos = -1;
-        {
-            // bounding box of the chunk: reduced in float32 (half the shuffles), widened by the float rounding of the inputs
+        double4 q = make_double4(0.0, 0.0, 0.0, 0.0);  // the partner's point record
+        bool need = valid;
+        if (valid && A.keep_ref != nullptr && kr.w > 0.f) {
+            const double mx = px - (double)kr.x, my = py - (double)kr.y, mz = pz - (double)kr.z;
+            // movement since the last search (+ the float rounding of the stored position)
+            const double moved = sqrt(mx * mx + my * my + mz * mz) + 2.0e-7 * (fabs(px) + fabs(py) + fabs(pz));
+            const double lim = (double)kr.w;
+            if (kp >= 0) {
+                if (moved < lim) {
+                    q = ld_point(A.grid.pts + kp);
+                    const double dk = dist2<double>(px - q.x, py - q.y, pz - q.z);
+                    if (sqrt(dk) * (1.0 + 1e-12) + moved < lim) {  // still strictly nearer than anything else can be
+                        need = false;
+                        pos = kp;
+                        d2 = dk;
+                        idx = point_index(q);
+                    }
+                }
+            } else if (dmax * (1.0 + 1e-12) + moved < lim) {
+                need = false;  // nothing was within lim, nothing can be within d_max now
+            }
+        }
+        if (A.stats) {
+            const unsigned int nm = __ballot_sync(0xffffffffu, need);
+            if (lane == 0) {
+                if (nm == 0u) atomicAdd(&g_icp_stats[6], 1ull);
+                atomicAdd(&g_icp_stats[7], (unsigned long long)__popc(nm));
+            }
+        }
+        if (__any_sync(0xffffffffu, need)) {
+            // bounding box of the lanes that search: reduced in float32 (half the shuffles), widened by the float rounding
             const float bigf = 3.0e38f;
-            float lx = valid ? (float)px : bigf, ly = valid ? (float)py : bigf, lz = valid ? (float)pz : bigf;
-            float hx = valid ? (float)px : -bigf, hy = valid ? (float)py : -bigf, hz = valid ? (float)pz : -bigf;
+            float lx = need ? (float)px : bigf, ly = need ? (float)py : bigf, lz = need ? (float)pz : bigf;
+            float hx = need ? (float)px : -bigf, hy = need ? (float)py : -bigf, hz = need ? (float)pz : -bigf;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o));
@@ -433,38 +482,17 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
             const double wid = 2.0e-7;  // relative rounding of the float conversion, with margin
             const double bl[3] = {(double)lx - wid * fabs((double)lx), (double)ly - wid * fabs((double)ly), (double)lz - wid * fabs((double)lz)};
             const double bh[3] = {(double)hx + wid * fabs((double)hx), (double)hy + wid * fabs((double)hy), (double)hz + wid * fabs((double)hz)};
+            double others2 = 0.0;    // lower bound of the squared distance of every staged candidate but the winner
+            double reach_used = 0.0;  // every target point within this distance of the query was looked at (0: unknown)
             for (int round = 0; round < 2; ++round) {
-                const double reach = round == 0 ? reach1 : dmax;
+                // second round: d_max, dilated so that a lane that finds nothing keeps some slack before it has to look again
+                const double reach = round == 0 ? reach1 : dmax * kIcpReach2;
                 if (round == 1 && !(reach1 < dmax)) break;
                 const double pad = reach * (1.0 + 1e-9) + 1e-12;
                 const double lo[3] = {bl[0] - pad, bl[1] - pad, bl[2] - pad}, hi[3] = {bh[0] + pad, bh[1] + pad, bh[2] + pad};
                 const double center[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
                 const float half_extent = (float)(0.5 * fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2])) * 1.0001f;
-                int count = -2;
-                if (round == 0 && A.cache_count != nullptr) {
-                    const int nc = A.cache_count[c];
-                    if (nc >= 0) {
-                        const double* cb = A.cache_box + 6 * (int64_t)c;
-                        if (lo[0] >= cb[0] && lo[1] >= cb[1] && lo[2] >= cb[2] && hi[0] <= cb[3] && hi[1] <= cb[4] && hi[2] <= cb[5]) {
-                            count = warp_stage_cached(A.grid, A.cache_idx + (int64_t)c * kStageCap, nc, lo, hi, center, cand, cand_pos);
-                            if (A.stats && lane == 0) atomicAdd(&g_icp_stats[6], 1ull);
-                        }
-                    }
-                }
-                if (count == -2) {
-                    count = warp_stage_box(A.grid, pair, lo, hi, center, cand, cand_pos, &s_stage[warp]);
-                    if (round == 0 && A.cache_count != nullptr && count >= 0) {
-                        // remember this staged set for the coming passes
-                        int* ci = A.cache_idx + (int64_t)c * kStageCap;
-                        for (int j = lane; j < count; j += 32) ci[j] = cand_pos[j];
-                        if (lane == 0) {
-                            double* cbw = A.cache_box + 6 * (int64_t)c;
-                            cbw[0] = lo[0]; cbw[1] = lo[1]; cbw[2] = lo[2];
-                            cbw[3] = hi[0]; cbw[4] = hi[1]; cbw[5] = hi[2];
-                        }
-                        if (lane == 0) A.cache_count[c] = count;
-                    }
-                }
+                const int count = warp_stage_box(A.grid, pair, lo, hi, center, cand, cand_pos, &s_stage[warp]);
                 if (A.stats && lane == 0) {
                     atomicAdd(&g_icp_stats[round == 0 ? 0 : 1], 1ull);
                     if (count < 0) atomicAdd(&g_icp_stats[2], 1ull);
@@ -474,23 +502,37 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
                     atomicAdd(&g_icp_stats[5], (unsigned long long)(1.0e4 * fmax(fmax(ex, ey), ez)));  // longest edge in 0.1 mm
                 }
                 if (count < 0) {
-                    // the box is too crowded for the staging buffer: per-lane walk of the grid
-                    if (valid) pos = nn_within_query<double>(A.grid, pair, px, py, pz, A.r2, A.rmax, &d2, &idx);
+                    // the box is too crowded for the staging buffer: per-lane walk of the grid (no runner-up bound)
+                    if (need) {
+                        pos = nn_within_query<double>(A.grid, pair, px, py, pz, A.r2, A.rmax, &d2, &idx);
+                        if (pos >= 0) q = ld_point(A.grid.pts + pos);
+                    }
+                    reach_used = 0.0;
                     break;
                 }
-                pos = -1;
-                if (valid) pos = staged_nearest(A.grid, cand, cand_pos, count, center, half_extent, px, py, pz, &d2, &idx);
+                if (need) {
+                    pos = staged_nearest(A.grid, cand, cand_pos, count, center, half_extent, px, py, pz, &d2, &idx, &q, &others2);
+                    if (pos < 0) others2 = 3.0e38;
+                }
+                reach_used = reach;
                 __syncwarp();
-                const bool certain = !valid || !(reach < dmax) || (pos >= 0 && d2 <= reach * reach);
+                const bool certain = !need || !(reach < dmax) || (pos >= 0 && d2 <= reach * reach);
                 if (__all_sync(0xffffffffu, certain)) break;
             }
-            if (pos >= 0 && !(d2 < A.r2)) pos = -1;
+            if (need && A.keep_ref != nullptr) {
+                // what this search proved: the nearest point (if any within reach_used) and that every other point is at
+                // least min(runner-up, reach_used) away; stored rounded down
+                float lbf = 0.f;
+                if (reach_used > 0.0) lbf = (float)(fmin(sqrt(others2), reach_used) * (1.0 - 1.0e-6));
+                A.keep_ref[si] = make_float4((float)px, (float)py, (float)pz, lbf);
+                A.keep_pos[si] = pos;
+            }
         }
+        if (pos >= 0 && !(d2 < A.r2)) pos = -1;
         if (valid) {
             if (A.corr != nullptr) A.corr[oi] = pos >= 0 ? idx - t0 : -1;
             if (pos >= 0) {
                 matched = true;
-                const double4 q = ld_point(A.grid.pts + pos);
                 e[7] = 1.0;
                 e[8] = d2;
                 if (KIND == kIcpInformation) {
@@ -755,18 +797,16 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
     // order the source points along a Morton curve of the target lattice and cut them into compact warp chunks
     B3D_TRY(build_query_chunks(ctx, pb.src, pb.src_off, pb.src_off_h, g.sort, reinterpret_cast<const double*>(w->state.p),
                                (int)(sizeof(IcpPairState) / sizeof(double)), &w->chunks));
-    // staged-set cache (skipped for very large problems: 1.6 KB per chunk)
-    w->cache_box.release();
-    w->cache_count.release();
-    w->cache_idx.release();
+    // sticky correspondences (20 bytes per source point); w = 0 marks "never searched"
+    w->keep_ref.release();
+    w->keep_pos.release();
     {
-        const size_t nc = (size_t)std::max(w->chunks.n_chunks, 1);
-        static const bool cache_off = getenv("B3D_ICP_NO_CACHE") != nullptr;
-        if (!cache_off && nc * (size_t)kStageCap * sizeof(int) <= ((size_t)6 << 30)) {
-            B3D_TRY(w->cache_box.alloc(ctx, nc * 6));
-            B3D_TRY(w->cache_count.alloc(ctx, nc));
-            B3D_TRY(w->cache_idx.alloc(ctx, nc * (size_t)kStageCap));
-            B3D_CUDA(cudaMemsetAsync(w->cache_count.p, 0xff, nc * sizeof(int), ctx->stream));
+        static const bool sticky_off = getenv("B3D_ICP_NO_STICKY") != nullptr;
+        const size_t ns = (size_t)std::max<int32_t>(pb.src_off_h[P], 1);
+        if (!sticky_off) {
+            B3D_TRY(w->keep_ref.alloc(ctx, ns));
+            B3D_TRY(w->keep_pos.alloc(ctx, ns));
+            B3D_CUDA(cudaMemsetAsync(w->keep_ref.p, 0, ns * sizeof(float4), ctx->stream));
         }
     }
     // partial-sum groups per pair depend only on that pair's own chunk count (results do not depend on the batch)
@@ -810,9 +850,8 @@ static IcpKernelArgs make_args(const IcpProblem& pb, IcpWork* w, int32_t* corr, 
         static const double rf = getenv("B3D_ICP_REACH") ? atof(getenv("B3D_ICP_REACH")) : 2.5;
         A.reach_factor = rf;
     }
-    A.cache_box = w->cache_box.p;
-    A.cache_count = w->cache_count.p;
-    A.cache_idx = w->cache_idx.p;
+    A.keep_ref = w->keep_ref.p;
+    A.keep_pos = w->keep_pos.p;
     {
         static const int stats_on = getenv("B3D_ICP_STATS") ? 1 : 0;
         A.stats = stats_on;

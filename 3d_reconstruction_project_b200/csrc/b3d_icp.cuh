@@ -44,8 +44,8 @@ struct IcpWork {
     DevBuf<double> tgt_nrm_sorted, tgt_cov_sorted;
     QueryChunks chunks;  // sources in Morton order of the target lattice, cut into compact warp chunks
     DevBuf<int64_t> ns_global;
-    DevBuf<double> cache_box;  // staged-set cache of the pass kernel (per chunk)
-    DevBuf<int> cache_count, cache_idx;
+    DevBuf<float4> keep_ref;   // sticky correspondences of the pass kernel (per source point, sorted order)
+    DevBuf<int32_t> keep_pos;
     int blocks = 1;
     int peer_world = 0, peer_rank = 0;  // exchange over peer memory (b3d_icp_set_peers)
     double* peer_buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -189,13 +189,14 @@ __device__ __forceinline__ int warp_stage_cached(const GridView<double>& g, cons
     return kept;
 }
 
-// Nearest staged candidate of q (exact (d2, index) rule), or -1. d2_out / idx_out as nn_within_query.
+// Nearest staged candidate of q (exact (d2, index) rule), or -1. d2_out / idx_out as nn_within_query; pt_out = the winner's
+// point record; others_lb_d2 = a lower bound of the squared distance of every other staged candidate (3e38 when alone).
 // Scan in float32 on t = |c|^2 - 2 q.c  (= d2 - |q|^2; offsets from the box centre, |.| <= half_extent): three FMAs per
 // candidate. The rounding error of t is below 4e-6 * half_extent^2; every candidate within twice that of the smallest t is
 // re-evaluated in float64 with the exact rule, so the result is bit-identical to the per-lane grid walk.
 __device__ __forceinline__ int staged_nearest(const GridView<double>& g, const float4* __restrict__ cand, const int* __restrict__ cand_pos,
                                               int count, const double (&center)[3], float half_extent, double qx, double qy, double qz,
-                                              double* d2_out, int* idx_out) {
+                                              double* d2_out, int* idx_out, double4* pt_out = nullptr, double* others_lb_d2 = nullptr) {
     const float fx = -2.0f * (float)(qx - center[0]), fy = -2.0f * (float)(qy - center[1]), fz = -2.0f * (float)(qz - center[2]);
     float best = 3.0e38f, second = 3.0e38f;
     int bi = -1;
@@ -214,7 +215,8 @@ __device__ __forceinline__ int staged_nearest(const GridView<double>& g, const f
     double4 pt = ld_point(g.pts + pos);
     double bd = dist2<double>(qx - pt.x, qy - pt.y, qz - pt.z);
     int bidx = point_index(pt);
-    if (second <= band) {
+    const bool ambiguous = second <= band;
+    if (ambiguous) {
         // more than one candidate inside the float rounding band of the best: decide in float64
         for (int i = 0; i < count; ++i) {
             const float4 c = cand[i];
@@ -224,12 +226,23 @@ __device__ __forceinline__ int staged_nearest(const GridView<double>& g, const f
                 const double4 q2 = ld_point(g.pts + p2);
                 const double d2 = dist2<double>(qx - q2.x, qy - q2.y, qz - q2.z);
                 const int i2 = point_index(q2);
-                if (d2 < bd || (d2 == bd && i2 < bidx)) { bd = d2; bidx = i2; pos = p2; }
+                if (d2 < bd || (d2 == bd && i2 < bidx)) { bd = d2; bidx = i2; pos = p2; pt = q2; }
             }
         }
     }
     *d2_out = bd;
     *idx_out = bidx;
+    if (pt_out != nullptr) *pt_out = pt;
+    if (others_lb_d2 != nullptr) {
+        // lower bound of the squared distance of every OTHER staged candidate: the second-smallest t of the float scan
+        // turned back into a distance (d2 = t + |q - center|^2) minus the rounding band; never below the winner's d2
+        double lb = bd;
+        if (!ambiguous) {
+            const double cx = qx - center[0], cy = qy - center[1], cz = qz - center[2];
+            lb = fmax(bd, (cx * cx + cy * cy + cz * cz) + (double)second - 8.0e-6 * (double)half_extent * (double)half_extent);
+        }
+        *others_lb_d2 = lb;
+    }
     return pos;
 }
 

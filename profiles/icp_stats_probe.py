@@ -22,8 +22,9 @@ torch.cuda.synchronize()
 out = (C.c_ulonglong * 8)()
 L.b3d_debug_icp_stats(out, 1)
 c1, c2, ovf, cand, vol, edge = [int(v) for v in out[:6]]
-print("cache hits", int(out[6]), "of", c1, "first-round stagings")
-print("cache hits", int(out[6]))
+kept_chunks, searched_lanes = int(out[6]), int(out[7])
+print(f"chunks visited {kept_chunks + c1}: {kept_chunks} kept every partner without a search ({100.0 * kept_chunks / max(kept_chunks + c1, 1):.1f} %), "
+      f"{c1} searched for {searched_lanes / max(c1, 1):.1f} lanes on average")
 ns = sum(r["m_source"] for r in res)
 its = [r["iterations"] for r in res]
 print(f"pairs {P}, source points {ns}, iterations {its}")
