@@ -23,7 +23,7 @@ namespace {
 constexpr int kIcpBlock = 128;
 constexpr int kIcpInformation = 3;  // internal kind: G^T G of get_information_matrix_from_point_clouds (rows from the target point)
 constexpr int kIcpMaxGroups = 1024;  // partial-sum groups (blocks) per pair
-constexpr double kIcpReach2 = 1.25;   // second-round reach of the staged search in units of d_max (see the pass kernel)
+constexpr double kIcpReach2 = 1.25;   // search radius of a lane that found nothing last time, in units of d_max (see the pass kernel)
 
 // ---- small dense helpers (device) ----------------------------------------------------------------------------------
 __device__ void mat4_mul(const double* A, const double* B, double* C) {
@@ -331,7 +331,6 @@ struct IcpKernelArgs {
     // order -- the all-reduce happens inside the pass kernel, no collective launch in between
     int peer_world, peer_rank;
     double* peer_buf[8];
-    double reach_factor;  // first-round reach in units of the previous pass's inlier rmse
     int stats;  // count chunks / rounds / staged candidates into g_icp_stats
 };
 
@@ -363,11 +362,7 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
     icp_sum_operands(KIND, lane, op_p, op_q);
     double (*rows)[kIcpRow] = srow[warp];
     double acc = 0.0;  // lane j: running total of sum j
-    // first-round reach of the staged search: a few times the previous pass's inlier rmse (most partners of a nearly
-    // converged pass are that close); lanes that are not certain after it trigger a second round at d_max
     const double dmax = sqrt(A.r2);
-    double reach1 = dmax;
-    if (st->iter > 0) reach1 = fmin(dmax, fmax(A.reach_factor * st->rmse, 0.2 * dmax));
     float4* cand = s_cand[warp];
     int* cand_pos = s_cand_pos[warp];
     // affine transforms (last row 0 0 0 1) need no perspective division: x / 1.0 == x exactly
@@ -433,29 +428,36 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
                 px /= w; py /= w; pz /= w;
             }
         }
-        // ---- correspondence: sticky check, then staged warp search (bit-identical to nn_within_query) --------------
+        // ---- correspondence: sticky check, then a staged warp search bounded by the previous partner -----------------
+        // (bit-identical to nn_within_query). A lane that had a partner in the last pass knows an upper bound of its
+        // nearest-neighbour distance -- the distance u to that partner now -- so its search ball has radius u (+ a slack
+        // that buys the sticky test room for the next pass) instead of d_max; one round, no guessing.
         double d2 = 0.0;
         int idx = 0, pos = -1;
         double4 q = make_double4(0.0, 0.0, 0.0, 0.0);  // the partner's point record
         bool need = valid;
-        if (valid && A.keep_ref != nullptr && kr.w > 0.f) {
+        double reach = dmax;  // this lane's search radius
+        if (valid && A.keep_ref != nullptr) {
             const double mx = px - (double)kr.x, my = py - (double)kr.y, mz = pz - (double)kr.z;
             // movement since the last search (+ the float rounding of the stored position)
             const double moved = sqrt(mx * mx + my * my + mz * mz) + 2.0e-7 * (fabs(px) + fabs(py) + fabs(pz));
-            const double lim = (double)kr.w;
+            const double lim = (double)kr.w;  // every other target point was at least this far from the stored position (0: unknown)
             if (kp >= 0) {
-                if (moved < lim) {
-                    q = ld_point(A.grid.pts + kp);
-                    const double dk = dist2<double>(px - q.x, py - q.y, pz - q.z);
-                    if (sqrt(dk) * (1.0 + 1e-12) + moved < lim) {  // still strictly nearer than anything else can be
-                        need = false;
-                        pos = kp;
-                        d2 = dk;
-                        idx = point_index(q);
-                    }
+                q = ld_point(A.grid.pts + kp);
+                const double dk = dist2<double>(px - q.x, py - q.y, pz - q.z);
+                const double u = sqrt(dk);
+                if (u * (1.0 + 1e-12) + moved < lim) {  // still strictly nearer than anything else can be
+                    need = false;
+                    pos = kp;
+                    d2 = dk;
+                    idx = point_index(q);
+                } else {
+                    const double slack = fmin(fmax(0.5 * moved, 0.01 * dmax), 0.1 * dmax);
+                    reach = fmin(u * (1.0 + 1e-9) + slack, dmax);  // nothing beyond d_max counts anyway
                 }
-            } else if (dmax * (1.0 + 1e-12) + moved < lim) {
-                need = false;  // nothing was within lim, nothing can be within d_max now
+            } else if (lim > 0.0) {
+                if (dmax * (1.0 + 1e-12) + moved < lim) need = false;  // nothing was within lim, nothing can be within d_max now
+                else reach = dmax * kIcpReach2;  // dilated: if it finds nothing again the lane keeps some slack
             }
         }
         if (A.stats) {
@@ -466,10 +468,11 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
             }
         }
         if (__any_sync(0xffffffffu, need)) {
-            // bounding box of the lanes that search: reduced in float32 (half the shuffles), widened by the float rounding
+            // bounding box of the search balls: reduced in float32 (half the shuffles), widened by the float rounding
             const float bigf = 3.0e38f;
-            float lx = need ? (float)px : bigf, ly = need ? (float)py : bigf, lz = need ? (float)pz : bigf;
-            float hx = need ? (float)px : -bigf, hy = need ? (float)py : -bigf, hz = need ? (float)pz : -bigf;
+            const float rf = (float)reach * 1.000001f;
+            float lx = need ? (float)px - rf : bigf, ly = need ? (float)py - rf : bigf, lz = need ? (float)pz - rf : bigf;
+            float hx = need ? (float)px + rf : -bigf, hy = need ? (float)py + rf : -bigf, hz = need ? (float)pz + rf : -bigf;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o));
@@ -479,51 +482,40 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
                 hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o));
                 hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
             }
-            const double wid = 2.0e-7;  // relative rounding of the float conversion, with margin
-            const double bl[3] = {(double)lx - wid * fabs((double)lx), (double)ly - wid * fabs((double)ly), (double)lz - wid * fabs((double)lz)};
-            const double bh[3] = {(double)hx + wid * fabs((double)hx), (double)hy + wid * fabs((double)hy), (double)hz + wid * fabs((double)hz)};
-            double others2 = 0.0;    // lower bound of the squared distance of every staged candidate but the winner
-            double reach_used = 0.0;  // every target point within this distance of the query was looked at (0: unknown)
-            for (int round = 0; round < 2; ++round) {
-                // second round: d_max, dilated so that a lane that finds nothing keeps some slack before it has to look again
-                const double reach = round == 0 ? reach1 : dmax * kIcpReach2;
-                if (round == 1 && !(reach1 < dmax)) break;
-                const double pad = reach * (1.0 + 1e-9) + 1e-12;
-                const double lo[3] = {bl[0] - pad, bl[1] - pad, bl[2] - pad}, hi[3] = {bh[0] + pad, bh[1] + pad, bh[2] + pad};
-                const double center[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
-                const float half_extent = (float)(0.5 * fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2])) * 1.0001f;
-                const int count = warp_stage_box(A.grid, pair, lo, hi, center, cand, cand_pos, &s_stage[warp]);
-                if (A.stats && lane == 0) {
-                    atomicAdd(&g_icp_stats[round == 0 ? 0 : 1], 1ull);
-                    if (count < 0) atomicAdd(&g_icp_stats[2], 1ull);
-                    else atomicAdd(&g_icp_stats[3], (unsigned long long)count);
-                    const double ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
-                    atomicAdd(&g_icp_stats[4], (unsigned long long)(1.0e6 * ex * ey * ez));  // box volume in cm^3
-                    atomicAdd(&g_icp_stats[5], (unsigned long long)(1.0e4 * fmax(fmax(ex, ey), ez)));  // longest edge in 0.1 mm
-                }
-                if (count < 0) {
-                    // the box is too crowded for the staging buffer: per-lane walk of the grid (no runner-up bound)
-                    if (need) {
-                        pos = nn_within_query<double>(A.grid, pair, px, py, pz, A.r2, A.rmax, &d2, &idx);
-                        if (pos >= 0) q = ld_point(A.grid.pts + pos);
-                    }
-                    reach_used = 0.0;
-                    break;
-                }
-                if (need) {
-                    pos = staged_nearest(A.grid, cand, cand_pos, count, center, half_extent, px, py, pz, &d2, &idx, &q, &others2);
-                    if (pos < 0) others2 = 3.0e38;
-                }
-                reach_used = reach;
-                __syncwarp();
-                const bool certain = !need || !(reach < dmax) || (pos >= 0 && d2 <= reach * reach);
-                if (__all_sync(0xffffffffu, certain)) break;
+            const double wid = 4.0e-7;  // relative rounding of the float conversions and the float add, with margin
+            const double pad = 1e-12;
+            const double lo[3] = {(double)lx - wid * fabs((double)lx) - pad, (double)ly - wid * fabs((double)ly) - pad, (double)lz - wid * fabs((double)lz) - pad};
+            const double hi[3] = {(double)hx + wid * fabs((double)hx) + pad, (double)hy + wid * fabs((double)hy) + pad, (double)hz + wid * fabs((double)hz) + pad};
+            const double center[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
+            const float half_extent = (float)(0.5 * fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2])) * 1.0001f;
+            double others2 = 3.0e38;  // lower bound of the squared distance of every staged candidate but the winner
+            bool bounded = true;      // every target point within `reach` of the query was looked at
+            const int count = warp_stage_box(A.grid, pair, lo, hi, center, cand, cand_pos, &s_stage[warp]);
+            if (A.stats && lane == 0) {
+                atomicAdd(&g_icp_stats[0], 1ull);
+                if (count < 0) atomicAdd(&g_icp_stats[2], 1ull);
+                else atomicAdd(&g_icp_stats[3], (unsigned long long)count);
+                const double ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+                atomicAdd(&g_icp_stats[4], (unsigned long long)(1.0e6 * ex * ey * ez));  // box volume in cm^3
+                atomicAdd(&g_icp_stats[5], (unsigned long long)(1.0e4 * fmax(fmax(ex, ey), ez)));  // longest edge in 0.1 mm
             }
+            if (count < 0) {
+                // the box is too crowded for the staging buffer: per-lane walk of the grid (no runner-up bound)
+                if (need) {
+                    pos = nn_within_query<double>(A.grid, pair, px, py, pz, A.r2, A.rmax, &d2, &idx);
+                    if (pos >= 0) q = ld_point(A.grid.pts + pos);
+                }
+                bounded = false;
+            } else if (need) {
+                pos = staged_nearest(A.grid, cand, cand_pos, count, center, half_extent, px, py, pz, &d2, &idx, &q, &others2);
+                if (pos < 0) others2 = 3.0e38;
+            }
+            __syncwarp();
             if (need && A.keep_ref != nullptr) {
-                // what this search proved: the nearest point (if any within reach_used) and that every other point is at
-                // least min(runner-up, reach_used) away; stored rounded down
+                // what this search proved: the nearest point (if any within reach) and that every other point is at least
+                // min(runner-up, reach) away; stored rounded down
                 float lbf = 0.f;
-                if (reach_used > 0.0) lbf = (float)(fmin(sqrt(others2), reach_used) * (1.0 - 1.0e-6));
+                if (bounded) lbf = (float)(fmin(sqrt(others2), reach) * (1.0 - 1.0e-6));
                 A.keep_ref[si] = make_float4((float)px, (float)py, (float)pz, lbf);
                 A.keep_pos[si] = pos;
             }
@@ -807,6 +799,7 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
             B3D_TRY(w->keep_ref.alloc(ctx, ns));
             B3D_TRY(w->keep_pos.alloc(ctx, ns));
             B3D_CUDA(cudaMemsetAsync(w->keep_ref.p, 0, ns * sizeof(float4), ctx->stream));
+            B3D_CUDA(cudaMemsetAsync(w->keep_pos.p, 0xff, ns * sizeof(int32_t), ctx->stream));
         }
     }
     // partial-sum groups per pair depend only on that pair's own chunk count (results do not depend on the batch)
@@ -846,10 +839,6 @@ static IcpKernelArgs make_args(const IcpProblem& pb, IcpWork* w, int32_t* corr, 
     A.sums = w->sums.p;
     A.corr = corr;
     A.fused = fused ? 1 : 0;
-    {
-        static const double rf = getenv("B3D_ICP_REACH") ? atof(getenv("B3D_ICP_REACH")) : 2.5;
-        A.reach_factor = rf;
-    }
     A.keep_ref = w->keep_ref.p;
     A.keep_pos = w->keep_pos.p;
     {

@@ -40,8 +40,8 @@ for rep in range(2):  # the second repetition is the warm one
             break
     res = sh.finish()
 print(f"source {len(src)}, target {len(tgt)}, iterations {res['iterations']}, fitness {res['fitness']:.4f}, rmse {res['inlier_rmse'] * 1e3:.3f} mm")
-print("pass  us     chunks  kept%  lanes/searched-chunk  round2%  overflow  cand/staging  edge_cm")
+print("pass  us     chunks  kept%  lanes/searched-chunk  overflow  cand/staging  edge_cm")
 for k, us, o in rows:
     c1, c2, ovf, cand, vol, edge, kept, lanes = o
-    print(f"{k:3d} {us:7.1f} {kept + c1:7d} {100.0 * kept / max(kept + c1, 1):6.1f} {lanes / max(c1, 1):10.1f} {100.0 * c2 / max(c1, 1):14.1f} {ovf:8d} "
+    print(f"{k:3d} {us:7.1f} {kept + c1:7d} {100.0 * kept / max(kept + c1, 1):6.1f} {lanes / max(c1, 1):10.1f} {ovf:8d} "
           f"{cand / max(c1 + c2 - ovf, 1):10.1f} {edge / max(c1 + c2, 1) / 100:10.2f}")

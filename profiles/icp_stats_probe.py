@@ -28,7 +28,7 @@ print(f"chunks visited {kept_chunks + c1}: {kept_chunks} kept every partner with
 ns = sum(r["m_source"] for r in res)
 its = [r["iterations"] for r in res]
 print(f"pairs {P}, source points {ns}, iterations {its}")
-print(f"round-1 chunks {c1}, round-2 chunks {c2} ({100.0 * c2 / max(c1, 1):.1f} %), overflows {ovf} ({100.0 * ovf / max(c1 + c2, 1):.2f} %)")
+print(f"staging calls {c1}, overflows {ovf} ({100.0 * ovf / max(c1, 1):.2f} %)")
 print(f"staged candidates per staging call {cand / max(c1 + c2 - ovf, 1):.1f}, mean box volume {vol / max(c1 + c2, 1):.1f} cm^3, mean longest edge {edge / max(c1 + c2, 1) / 100:.2f} cm")
 out = (C.c_ulonglong * 8)()
 L.b3d_debug_normals_stats(out, 1)
