@@ -74,6 +74,7 @@ SIGNATURES = {
     "b3d_estimate_normals_tensor": (_i, [_vp, _vp, _i64, _i, _f, _vp]),
     "b3d_covariances_from_normals": (_i, [_vp, _vp, _i64, _d, _vp]),
     "b3d_compute_fpfh": (_i, [_vp, _vp, _vp, _i64, _i, _d, _vp]),
+    "b3d_orient_normals_consistent_tangent_plane": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
     "b3d_statistical_outlier": (_i, [_vp, _vp, _i64, _i, _d, _vp, _vp, _pi64]),
     "b3d_radius_outlier": (_i, [_vp, _vp, _i64, _i, _d, _vp, _vp, _pi64]),
     "b3d_gather_rows_f64": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),

@@ -457,7 +457,8 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
                 }
             } else if (lim > 0.0) {
                 if (dmax * (1.0 + 1e-12) + moved < lim) need = false;  // nothing was within lim, nothing can be within d_max now
-                else reach = dmax * kIcpReach2;  // dilated: if it finds nothing again the lane keeps some slack
+                // dilated once the cloud has nearly stopped moving: if the lane finds nothing again it keeps some slack
+                else if (moved < 0.5 * (kIcpReach2 - 1.0) * dmax) reach = dmax * kIcpReach2;
             }
         }
         if (A.stats) {

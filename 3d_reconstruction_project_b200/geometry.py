@@ -173,6 +173,16 @@ class PointCloud:
         self._normals = Vector3dVector(ops.estimate_normals_legacy(np.asarray(self._points), k, r, prior=prior, device=self.device))
         return self
 
+    def orient_normals_consistent_tangent_plane(self, k, lambda_penalty=0.0, cos_alpha_tol=1.0):
+        """normal_estimation.py:21 (k = 100). In place. Only the published algorithm (lambda = 0, cos_alpha_tol = 1) is built."""
+        if lambda_penalty != 0.0 or cos_alpha_tol != 1.0:
+            raise RuntimeError("orient_normals_consistent_tangent_plane: lambda / cos_alpha_tol variants are not supported on this path")
+        if not self.has_normals():
+            raise RuntimeError("No normals in the PointCloud. Call EstimateNormals() first.")
+        nrm, _ = ops.orient_normals_consistent_tangent_plane(np.asarray(self._points), np.asarray(self._normals), int(k), device=self.device)
+        self._normals = Vector3dVector(nrm)
+        return self
+
     def estimate_covariances_from_normals(self, eps=1e-3):
         """What registration_generalized_icp does first (test/GICP1.py:99-102): normals (KNN 20 if absent) -> C = R diag(eps,1,1) R^T."""
         if not self.has_normals():

@@ -173,6 +173,21 @@ def covariances_from_normals(normals, eps=1e-3, device=0, as_tensor=False):
     return _out(cov, as_tensor)
 
 
+def orient_normals_consistent_tangent_plane(points, normals, k=100, device=0, as_tensor=False):
+    """PointCloud.orient_normals_consistent_tangent_plane(k) -- normal_estimation.py:21. -> (oriented normals f64 [n,3], flipped bool [n])"""
+    ctx = get_context(device)
+    p = ctx.to_device(points, torch.float64)
+    _check_n3(p, "points")
+    if normals is None:
+        raise RuntimeError("No normals in the PointCloud. Call EstimateNormals() first.")
+    nr = ctx.to_device(normals, torch.float64).clone()
+    _check_n3(nr, "normals")
+    fl = ctx.empty((max(p.shape[0], 1),), torch.uint8)
+    N.check(N.lib().b3d_orient_normals_consistent_tangent_plane(ctx.handle, ptr(p), ptr(nr), p.shape[0], int(k), ptr(fl)))
+    fl = fl[:p.shape[0]].bool()
+    return _out(nr, as_tensor), _out(fl, as_tensor)
+
+
 def compute_fpfh(points, normals, max_nn, radius, device=0, as_tensor=False):
     """o3d.pipelines.registration.compute_fpfh_feature(pcd, KDTreeSearchParamHybrid(radius, max_nn)) -- test/mini1.py:244-250.
     -> [N, 33] float64 (the transpose of Open3D's Feature.data)."""

@@ -209,6 +209,17 @@ def fpfh(points, normals, max_nn, radius):
     return out
 
 
+def orient_normals(points, normals, k=100):
+    """PointCloud.orient_normals_consistent_tangent_plane(k) -- normal_estimation.py:21. -> (oriented normals, flipped mask)"""
+    points = _c(points, np.float64)
+    out = np.array(normals, dtype=np.float64, order="C", copy=True)
+    flipped = np.zeros(len(points), np.uint8)
+    rc = lib().orc_orient_normals(_p(points), _p(out), C.c_int64(len(points)), int(k), _p(flipped))
+    if rc != 0:
+        raise RuntimeError("Not enough points to create a tetrahedral mesh.")
+    return out, flipped.astype(bool)
+
+
 P2P, P2L, GICP = 0, 1, 2
 
 

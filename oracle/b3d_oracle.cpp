@@ -1232,4 +1232,123 @@ int orc_icp(int kind, const double* src, int64_t ns, const double* src_cov, cons
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// PointCloud::OrientNormalsConsistentTangentPlane(k) -- normal_estimation.py:21 (k = 100).  PARITY UNPINNED.
+// Restated from the upstream routine (Hoppe et al.): Riemannian graph = Euclidean minimum spanning tree + k-NN edges,
+// weight 1 - |n_i . n_j|; Kruskal; queue walk from the first point of largest z (turned towards +z), a child is flipped
+// when its dot product with the parent is negative. Differences that cannot be restated here: upstream obtains the
+// Euclidean tree through Qhull's Delaunay mesh and skips k-NN edges that are Delaunay edges; std::sort's order among equal
+// weights is unspecified (here: (weight, min end, max end)). The tree below is exact (Prim on the complete graph).
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct OEdge { double w; int32_t a, b; };
+inline bool oedge_less(const OEdge& x, const OEdge& y) {
+    if (x.w != y.w) return x.w < y.w;
+    const int32_t xl = std::min(x.a, x.b), xh = std::max(x.a, x.b), yl = std::min(y.a, y.b), yh = std::max(y.a, y.b);
+    if (xl != yl) return xl < yl;
+    return xh < yh;
+}
+int32_t uf_find(std::vector<int32_t>& p, int32_t x) {
+    while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; }
+    return x;
+}
+}  // namespace
+
+int orc_orient_normals(const double* pts, double* nrm, int64_t n, int k, uint8_t* flipped) {
+    if (n < 4) return -1;
+    // Euclidean minimum spanning tree: Prim, order (d2, min end, max end)
+    std::vector<OEdge> edges;
+    edges.reserve((size_t)n * (k + 1));
+    {
+        std::vector<OEdge> best(n);
+        std::vector<char> in(n, 0);
+        in[0] = 1;
+        for (int64_t v = 1; v < n; ++v) {
+            const double dx = pts[3 * v] - pts[0], dy = pts[3 * v + 1] - pts[1], dz = pts[3 * v + 2] - pts[2];
+            best[v] = OEdge{(dx * dx + dy * dy) + dz * dz, 0, (int32_t)v};
+        }
+        for (int64_t step = 1; step < n; ++step) {
+            int64_t pick = -1;
+            for (int64_t v = 0; v < n; ++v)
+                if (!in[v] && (pick < 0 || oedge_less(best[v], best[pick]))) pick = v;
+            in[pick] = 1;
+            edges.push_back(best[pick]);
+            const double* p = pts + 3 * pick;
+#pragma omp parallel for schedule(static)
+            for (int64_t v = 0; v < n; ++v) {
+                if (in[v]) continue;
+                const double dx = pts[3 * v] - p[0], dy = pts[3 * v + 1] - p[1], dz = pts[3 * v + 2] - p[2];
+                const OEdge e{(dx * dx + dy * dy) + dz * dz, (int32_t)pick, (int32_t)v};
+                if (oedge_less(e, best[v])) best[v] = e;
+            }
+        }
+    }
+    auto nweight = [&](int32_t a, int32_t b) {
+        const double d = (nrm[3 * a] * nrm[3 * b] + nrm[3 * a + 1] * nrm[3 * b + 1]) + nrm[3 * a + 2] * nrm[3 * b + 2];
+        return 1.0 - std::abs(d);
+    };
+    for (auto& e : edges) e.w = nweight(e.a, e.b);
+    // k nearest neighbours (the point itself skipped)
+    {
+        KdTree<double> tree;
+        tree.build(pts, n);
+        const int kk = (int)std::min<int64_t>(k, n);
+        std::vector<int32_t> nb((size_t)n * kk, -1);
+#pragma omp parallel
+        {
+            std::vector<KdTree<double>::Cand> heap(kk);
+#pragma omp for schedule(dynamic, 256)
+            for (int64_t i = 0; i < n; ++i) {
+                const int c = hybrid<double>(tree, pts + 3 * i, kk, 0.0, heap.data());
+                for (int j = 0; j < c; ++j) nb[i * kk + j] = (int32_t)heap[j].i;
+            }
+        }
+        for (int64_t i = 0; i < n; ++i)
+            for (int j = 0; j < kk; ++j) {
+                const int32_t u = nb[i * kk + j];
+                if (u >= 0 && u != i) edges.push_back(OEdge{nweight((int32_t)i, u), (int32_t)i, u});
+            }
+    }
+    std::sort(edges.begin(), edges.end(), oedge_less);
+    std::vector<int32_t> parent(n);
+    for (int64_t i = 0; i < n; ++i) parent[i] = (int32_t)i;
+    std::vector<std::vector<int32_t>> adj(n);
+    for (const auto& e : edges) {
+        const int32_t ra = uf_find(parent, e.a), rb = uf_find(parent, e.b);
+        if (ra == rb) continue;
+        parent[ra] = rb;
+        adj[e.a].push_back(e.b);
+        adj[e.b].push_back(e.a);
+    }
+    int64_t v0 = 0;
+    double max_z = -std::numeric_limits<double>::infinity();
+    for (int64_t i = 0; i < n; ++i)
+        if (pts[3 * i + 2] > max_z) { max_z = pts[3 * i + 2]; v0 = i; }
+    std::vector<char> visited(n, 0);
+    std::vector<int32_t> queue;
+    queue.reserve(n);
+    for (int64_t i = 0; i < n; ++i) flipped[i] = 0;
+    auto orient = [&](const double* n0, int64_t c) {
+        double* n1 = nrm + 3 * c;
+        if ((n0[0] * n1[0] + n0[1] * n1[1]) + n0[2] * n1[2] < 0.0) {
+            n1[0] *= -1.0; n1[1] *= -1.0; n1[2] *= -1.0;
+            flipped[c] = 1;
+        }
+    };
+    const double up[3] = {0.0, 0.0, 1.0};
+    orient(up, v0);
+    queue.push_back((int32_t)v0);
+    visited[v0] = 1;
+    for (size_t h = 0; h < queue.size(); ++h) {
+        const int32_t v = queue[h];
+        for (int32_t u : adj[v]) {
+            if (visited[u]) continue;
+            visited[u] = 1;
+            orient(nrm + 3 * v, u);
+            queue.push_back(u);
+        }
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -436,6 +436,38 @@ def test_icp_batch_equals_single_calls(ops):
         assert np.array_equal(res[i]["corr"], ref["corr"])
 
 
+def test_orient_normals_consistent_tangent_plane(ops):
+    """normal_estimation.py:21: orient_normals_consistent_tangent_plane(100). Same unoriented normals into the CUDA path and the
+    oracle (Prim + Kruskal + queue walk): the set of flipped normals must be identical."""
+    rng = np.random.default_rng(7)
+    pts, nrm = golden_cloud("output_00094")
+    nrm = nrm * np.where(rng.random(len(nrm)) < 0.5, -1.0, 1.0)[:, None]  # scramble the signs
+    for k in (100, 12):
+        ref, ref_flip = oracle.orient_normals(pts, nrm, k)
+        out, flip = ops.orient_normals_consistent_tangent_plane(pts, nrm, k)
+        assert np.array_equal(flip, ref_flip), int((flip != ref_flip).sum())
+        assert np.array_equal(out, ref)
+        assert np.array_equal(out, np.where(flip[:, None], -nrm, nrm))
+    # two separate pieces (the k-NN graph is disconnected: the Euclidean tree has to bridge the gap) + exact ties on a lattice
+    g = np.stack(np.meshgrid(np.arange(24), np.arange(24), indexing="ij"), -1).reshape(-1, 2) * 0.01
+    plane = np.column_stack([g, 0.02 * np.sin(8 * g[:, 0])])
+    pn = np.column_stack([-0.16 * np.cos(8 * g[:, 0]), np.zeros(len(g)), np.ones(len(g))])
+    pn /= np.linalg.norm(pn, axis=1, keepdims=True)
+    sph = rng.normal(size=(700, 3))
+    sph /= np.linalg.norm(sph, axis=1, keepdims=True)
+    both = np.concatenate([plane, 0.05 * sph + [0.1, 0.1, 0.6]])
+    bn = np.concatenate([pn, sph]) * np.where(rng.random(len(both)) < 0.5, -1.0, 1.0)[:, None]
+    ref, ref_flip = oracle.orient_normals(both, bn, 10)
+    out, flip = ops.orient_normals_consistent_tangent_plane(both, bn, 10)
+    assert np.array_equal(flip, ref_flip), int((flip != ref_flip).sum())
+    # the sphere ends up pointing outwards (its top looks at +z) and the sheet follows it across the gap
+    assert (np.einsum("ij,ij->i", out[len(plane):], sph) > 0).all()
+    with pytest.raises(RuntimeError, match="Not enough points"):
+        ops.orient_normals_consistent_tangent_plane(pts[:3], nrm[:3], 100)
+    with pytest.raises(RuntimeError, match="No normals"):
+        ops.orient_normals_consistent_tangent_plane(pts, None, 100)
+
+
 def test_fpfh_features(ops):
     """compute_fpfh_feature(Hybrid(0.1, 100)) as in test/mini1.py:244-250 on a fixture cloud with its own normals."""
     pts, nrm = golden_cloud("output_00094")
