@@ -20,9 +20,12 @@ __device__ unsigned long long g_icp_stats[8];
 
 namespace {
 
-constexpr int kIcpBlock = 128;
+#ifndef B3D_ICP_BLOCK
+#define B3D_ICP_BLOCK 128
+#endif
+constexpr int kIcpBlock = B3D_ICP_BLOCK;  // threads per block of the pass kernel (a warp works alone; the block only shares the partial sum)
 constexpr int kIcpInformation = 3;  // internal kind: G^T G of get_information_matrix_from_point_clouds (rows from the target point)
-constexpr int kIcpMaxGroups = 1024;  // partial-sum groups (blocks) per pair
+constexpr int kIcpMaxGroups = 1024 * (128 / kIcpBlock);  // partial-sum groups (blocks) per pair
 constexpr double kIcpReach2 = 1.25;   // search radius of a lane that found nothing last time, in units of d_max (see the pass kernel)
 
 // ---- small dense helpers (device) ----------------------------------------------------------------------------------
@@ -339,7 +342,7 @@ struct IcpKernelArgs {
 // Every lane produces its 29 contributions; a transpose-reduce leaves value j's warp total in lane j, which is the only
 // accumulator a thread keeps (instead of 29 live doubles across the search loop).
 #ifndef B3D_ICP_MIN_BLOCKS
-#define B3D_ICP_MIN_BLOCKS 4
+#define B3D_ICP_MIN_BLOCKS (512 / B3D_ICP_BLOCK)
 #endif
 template <int KIND>
 __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel(IcpKernelArgs A) {

@@ -11,8 +11,8 @@
 // over edge (a, b) fixes the relation of the two representatives to sgn[a] sgn[b] sign(n_a . n_b). The product of the
 // flips along a tree path does not depend on the order of the walk, so the result equals the queue traversal's.
 // The Euclidean tree is searched among the k nearest neighbours first; what the k-NN graph leaves disconnected is joined by
-// exact nearest-foreign-point queries (grid walk, whole-cloud scan when the gap is wider than the ring budget) issued by
-// every component but the largest.
+// exact nearest-foreign-point queries issued by every component but the largest: brute force over tiles of the Morton-sorted
+// cloud, pruned by tile bounding boxes against a sampled upper bound of the component's distance to the rest.
 #include "b3d_common.cuh"
 #include "b3d_search.cuh"
 
@@ -44,6 +44,17 @@ __global__ void __launch_bounds__(64) orient_neighbors_kernel(GridView<double> g
         nb[oi * k + j] = u;
         nd[oi * k + j] = d;
     }
+}
+
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
 }
 
 __device__ __forceinline__ double normal_weight(const double* __restrict__ nrm, int a, int b) {
@@ -204,46 +215,137 @@ __global__ void comp_largest_kernel(int64_t n, const int32_t* __restrict__ comp,
     atomicMax(largest, ((unsigned long long)(unsigned int)size[c] << 32) | (unsigned int)(0x7fffffff - (int)c));
 }
 
-// Nearest point of another component for every point outside the largest component: (d2, edge id) order.
-__global__ void __launch_bounds__(128) foreign_nearest_kernel(GridView<double> g, const int32_t* __restrict__ off, int rmax, const int32_t* __restrict__ comp,
-                                                              const unsigned long long* __restrict__ largest, int32_t* __restrict__ fnb, double* __restrict__ fd) {
+// Upper bound of every small component's distance to the rest: each of its points against a strided sample of the cloud.
+// The bound is attained by a real pair, so the component's true minimum crossing edge is not longer.
+__global__ void __launch_bounds__(128) foreign_bound_kernel(GridView<double> g, int stride, const int32_t* __restrict__ comp,
+                                                            const unsigned long long* __restrict__ largest, unsigned long long* __restrict__ ub) {
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= g.n) return;
     const double4 q = ld_point(g.pts + pos);
-    const int v = point_index(q);
-    const int cv = comp[v];
-    const int big = 0x7fffffff - (int)(*largest & 0xffffffffu);
-    fnb[v] = -1;
-    fd[v] = 0.0;
-    if (cv == big) return;
+    const int cv = comp[point_index(q)];
+    if (cv == 0x7fffffff - (int)(*largest & 0xffffffffu)) return;
     double bd = 1.0e300;
-    int bu = -1;
-    auto visit = [&](int, const double4& pt) {
-        const int u = point_index(pt);
-        if (comp[u] == cv) return;
+    for (int p = 0; p < g.n; p += stride) {
+        const double4 pt = ld_point(g.pts + p);
         const double d2 = dist2<double>(q.x - pt.x, q.y - pt.y, q.z - pt.z);
-        if (d2 < bd || (d2 == bd && edge_id(v, u) < edge_id(v, bu))) {
-            bd = d2;
-            bu = u;
-        }
-    };
-    auto thr = [&]() -> double { return bd; };
-    const int last = grid_walk<double>(g, 0, q.x, q.y, q.z, rmax, visit, thr);
-    // certain only if the best is closer than the part of space the walk has not seen
-    const Lattice L = g.lat[0];
-    const double h = L.cell;
-    const double ux = (q.x - L.ox) / h, uy = (q.y - L.oy) / h, uz = (q.z - L.oz) / h;
-    const double fx = ux - floor(ux), fy = uy - floor(uy), fz = uz - floor(uz);
-    const double face = fmin(fmin(fmin(fx, 1.0 - fx), fmin(fy, 1.0 - fy)), fmin(fz, 1.0 - fz));
-    const double bound = ((double)last + face) * h;
-    if (!(bd < bound * bound * (1.0 - 1e-9))) {
-        bd = 1.0e300;
-        bu = -1;
-        const int s = off[0], e = off[1];
-        for (int p = s; p < e; ++p) visit(p, ld_point(g.pts + p));
+        if (d2 < bd && comp[point_index(pt)] != cv) bd = d2;
     }
-    fnb[v] = bu;
-    fd[v] = bu >= 0 ? bd : 0.0;
+    if (bd < 1.0e300) atomicMin(&ub[cv], (unsigned long long)__double_as_longlong(bd));
+}
+
+// Tiles of kTile consecutive points of the sorted (Morton) order are spatially compact: their bounding box and, when all
+// of them belong to one component, that component.
+constexpr int kTile = 128;
+__global__ void __launch_bounds__(kTile) tile_info_kernel(GridView<double> g, const int32_t* __restrict__ comp, double* __restrict__ tile_box,
+                                                          int32_t* __restrict__ tile_comp) {
+    const int t = blockIdx.x;
+    const int p = t * kTile + threadIdx.x;
+    const bool valid = p < g.n;
+    double lo[3] = {1.0e300, 1.0e300, 1.0e300}, hi[3] = {-1.0e300, -1.0e300, -1.0e300};
+    int c = -1;
+    if (valid) {
+        const double4 pt = ld_point(g.pts + p);
+        lo[0] = hi[0] = pt.x; lo[1] = hi[1] = pt.y; lo[2] = hi[2] = pt.z;
+        c = comp[point_index(pt)];
+    }
+    __shared__ double s_lo[3][kTile / 32], s_hi[3][kTile / 32];
+    __shared__ int s_c[kTile / 32], s_mixed[kTile / 32];
+    const int c_first = __shfl_sync(0xffffffffu, c, 0);
+    const bool mixed = __any_sync(0xffffffffu, valid && c != c_first);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = warp_min_d(lo[a]);
+        hi[a] = warp_max_d(hi[a]);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        for (int a = 0; a < 3; ++a) { s_lo[a][warp] = lo[a]; s_hi[a][warp] = hi[a]; }
+        s_c[warp] = c_first;
+        s_mixed[warp] = mixed ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int cc = s_c[0];
+        bool mx = s_mixed[0] != 0;
+        for (int w = 1; w < kTile / 32; ++w) {
+            if (s_c[w] < 0) continue;  // a warp past the end of the cloud
+            if (s_mixed[w] || s_c[w] != cc) mx = true;
+        }
+        for (int a = 0; a < 3; ++a) {
+            double l = s_lo[a][0], h = s_hi[a][0];
+            for (int w = 1; w < kTile / 32; ++w) { l = fmin(l, s_lo[a][w]); h = fmax(h, s_hi[a][w]); }
+            tile_box[6 * t + a] = l;
+            tile_box[6 * t + 3 + a] = h;
+        }
+        tile_comp[t] = mx ? -1 : cc;
+    }
+}
+
+// Nearest point of another component for every point outside the largest component, (d2, edge id) order: brute force over
+// the tiles, skipping every tile that lies in the point's own component or farther than the best so far (which starts at
+// the component's sampled bound: points that cannot carry the component's minimum edge report nothing).
+__global__ void __launch_bounds__(kTile) foreign_nearest_kernel(GridView<double> g, const int32_t* __restrict__ comp, const unsigned long long* __restrict__ largest,
+                                                                const unsigned long long* __restrict__ ub, const double* __restrict__ tile_box,
+                                                                const int32_t* __restrict__ tile_comp, int n_tiles, int32_t* __restrict__ fnb,
+                                                                double* __restrict__ fd) {
+    __shared__ double4 s_pt[kTile];
+    __shared__ int s_comp[kTile];
+    const int pos = blockIdx.x * kTile + threadIdx.x;
+    const int big = 0x7fffffff - (int)(*largest & 0xffffffffu);
+    double4 q = make_double4(0.0, 0.0, 0.0, 0.0);
+    int v = -1, cv = big;
+    if (pos < g.n) {
+        q = ld_point(g.pts + pos);
+        v = point_index(q);
+        cv = comp[v];
+        fnb[v] = -1;
+        fd[v] = 0.0;
+    }
+    const bool need = cv != big;
+    if (!__syncthreads_or(need ? 1 : 0)) return;
+    double bd = 1.0e300;
+    if (need) {
+        const unsigned long long ubits = ub[cv];
+        if (ubits != kNoEdge) bd = __longlong_as_double((long long)ubits);
+    }
+    int bu = -1;
+    for (int t = 0; t < n_tiles; ++t) {
+        bool skip = !need || tile_comp[t] == cv;
+        if (!skip) {
+            const double* bx = tile_box + 6 * t;
+            const double dx = fmax(fmax(bx[0] - q.x, q.x - bx[3]), 0.0), dy = fmax(fmax(bx[1] - q.y, q.y - bx[4]), 0.0), dz = fmax(fmax(bx[2] - q.z, q.z - bx[5]), 0.0);
+            skip = dist2<double>(dx, dy, dz) * (1.0 - 1e-12) > bd;
+        }
+        if (__syncthreads_and(skip ? 1 : 0)) continue;
+        const int p = t * kTile + threadIdx.x;
+        if (p < g.n) {
+            const double4 pt = ld_point(g.pts + p);
+            s_pt[threadIdx.x] = pt;
+            s_comp[threadIdx.x] = comp[point_index(pt)];
+        } else {
+            s_comp[threadIdx.x] = -2;
+        }
+        __syncthreads();
+        if (!skip) {
+            for (int j = 0; j < kTile; ++j) {
+                const int cu = s_comp[j];
+                if (cu == cv || cu == -2) continue;
+                const double4 pt = s_pt[j];
+                const double d2 = dist2<double>(q.x - pt.x, q.y - pt.y, q.z - pt.z);
+                if (d2 > bd) continue;
+                const int u = point_index(pt);
+                if (d2 < bd || edge_id(v, u) < edge_id(v, bu)) {
+                    bd = d2;
+                    bu = u;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (need && bu >= 0) {
+        fnb[v] = bu;
+        fd[v] = bd;
+    }
 }
 
 // first index of the largest z (the library's loop keeps the first maximum): reduce on order-preserving bits of z, then
@@ -391,7 +493,13 @@ extern "C" int b3d_orient_normals_consistent_tangent_plane(b3d_ctx* ctx, const d
             // the k-NN graph is not connected: every component but the largest looks for its nearest foreign point
             DevBuf<int32_t> size, fnb;
             DevBuf<double> fd;
-            DevBuf<unsigned long long> largest;
+            DevBuf<unsigned long long> largest, ub;
+            DevBuf<double> tile_box;
+            DevBuf<int32_t> tile_comp;
+            const int n_tiles = (int)((n + kTile - 1) / kTile);
+            B3D_TRY(tile_box.alloc(ctx, (size_t)n_tiles * 6));
+            B3D_TRY(tile_comp.alloc(ctx, n_tiles));
+            B3D_TRY(ub.alloc(ctx, n));
             B3D_TRY(size.alloc(ctx, n));
             B3D_TRY(fnb.alloc(ctx, n));
             B3D_TRY(fd.alloc(ctx, n));
@@ -403,7 +511,11 @@ extern "C" int b3d_orient_normals_consistent_tangent_plane(b3d_ctx* ctx, const d
                 B3D_CUDA(cudaMemsetAsync(largest.p, 0, sizeof(unsigned long long), ctx->stream));
                 B3D_LAUNCH(ctx, comp_size_kernel, vb, 256, 0, n, f.comp.p, size.p);
                 B3D_LAUNCH(ctx, comp_largest_kernel, vb, 256, 0, n, f.comp.p, size.p, largest.p);
-                B3D_LAUNCH(ctx, foreign_nearest_kernel, (int)((n + 127) / 128), 128, 0, grid.view(), seg.off, rmax, f.comp.p, largest.p, fnb.p, fd.p);
+                B3D_CUDA(cudaMemsetAsync(ub.p, 0xff, n * sizeof(unsigned long long), ctx->stream));
+                const int stride = (int)std::max<int64_t>(1, n / 4096);
+                B3D_LAUNCH(ctx, foreign_bound_kernel, (int)((n + 127) / 128), 128, 0, grid.view(), stride, f.comp.p, largest.p, ub.p);
+                B3D_LAUNCH(ctx, tile_info_kernel, n_tiles, kTile, 0, grid.view(), f.comp.p, tile_box.p, tile_comp.p);
+                B3D_LAUNCH(ctx, foreign_nearest_kernel, n_tiles, kTile, 0, grid.view(), f.comp.p, largest.p, ub.p, tile_box.p, tile_comp.p, n_tiles, fnb.p, fd.p);
                 EdgeList bridge{nullptr, fnb.p, fd.p, n, 1};
                 B3D_TRY(boruvka_round(ctx, &f, &bridge, 1, nullptr, tree_a.p, tree_b.p, &hooks));
             }
