@@ -985,8 +985,9 @@ static int setup_single(b3d_ctx* ctx, b3d_icp_state* st, int kind, const double*
 
 extern "C" {
 
-// [0] first-round chunks, [1] second-round chunks, [2] staging overflows (per-lane fallback), [3] staged candidates,
-// [4] sum of box volumes (cm^3), [5] sum of longest box edges (0.1 mm). Debug aid, not part of the public header.
+// [0] chunks that staged a search, [1] unused, [2] staging overflows (per-lane fallback), [3] staged candidates, [4] sum of box
+// volumes (cm^3), [5] sum of longest box edges (0.1 mm), [6] chunks whose lanes all kept their partner without a search,
+// [7] lanes that searched. Debug aid (B3D_ICP_STATS=1), not part of the public header.
 int b3d_debug_icp_stats(unsigned long long* out8, int reset) {
     if (out8 && cudaMemcpyFromSymbol(out8, g_icp_stats, 8 * sizeof(unsigned long long)) != cudaSuccess) return B3D_E_CUDA;
     if (reset) {

@@ -157,38 +157,6 @@ __device__ __forceinline__ int warp_stage_box(const GridView<double>& g, int clo
     return total;
 }
 
-// Re-stages a chunk from a cached list of sorted positions (the staged set of an earlier pass whose box contained the
-// current one): no cell range, no hash probes, no prefix -- one coalesced index read and one gather per candidate,
-// filtered to the current box. Returns the number of candidates kept (<= cap by construction).
-__device__ __forceinline__ int warp_stage_cached(const GridView<double>& g, const int* __restrict__ cached, int n_cached, const double (&lo)[3],
-                                                 const double (&hi)[3], const double (&center)[3], float4* __restrict__ cand,
-                                                 int* __restrict__ cand_pos) {
-    const int lane = threadIdx.x & 31;
-    int kept = 0;
-    for (int jb = 0; jb < n_cached; jb += 32) {
-        const int j = jb + lane;
-        bool inside = false;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        int pp = 0;
-        if (j < n_cached) {
-            pp = __ldg(cached + j);
-            const double4 pt = ld_point(g.pts + pp);
-            inside = pt.x >= lo[0] && pt.x <= hi[0] && pt.y >= lo[1] && pt.y <= hi[1] && pt.z >= lo[2] && pt.z <= hi[2];
-            const float rx = (float)(pt.x - center[0]), ry = (float)(pt.y - center[1]), rz = (float)(pt.z - center[2]);
-            v = make_float4(rx, ry, rz, fmaf(rz, rz, fmaf(ry, ry, rx * rx)));
-        }
-        const unsigned int m = __ballot_sync(0xffffffffu, inside);
-        if (inside) {
-            const int slot = kept + __popc(m & ((1u << lane) - 1u));
-            cand[slot] = v;
-            cand_pos[slot] = pp;
-        }
-        kept += __popc(m);
-    }
-    __syncwarp();
-    return kept;
-}
-
 // Nearest staged candidate of q (exact (d2, index) rule), or -1. d2_out / idx_out as nn_within_query; pt_out = the winner's
 // point record; others_lb_d2 = a lower bound of the squared distance of every other staged candidate (3e38 when alone).
 // Scan in float32 on t = |c|^2 - 2 q.c  (= d2 - |q|^2; offsets from the box centre, |.| <= half_extent): three FMAs per

@@ -84,6 +84,41 @@ def test_pair_pipeline_config2_full_size(b3):
         assert np.linalg.norm(host[i]["transformation"][:3, 3] - T_true[i][:3, 3]) < 5e-3
 
 
+def test_sticky_correspondences_change_nothing(b3):
+    """The pass kernel skips the search of a lane whose partner provably cannot have changed and bounds the others by the
+    previous partner's distance. With that switched off (B3D_ICP_NO_STICKY: every pass searches every lane at d_max) a
+    full-size config-2 registration must come out bit for bit the same, correspondence set included."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, json, hashlib; sys.path.insert(0, %r); import numpy as np\n"
+        "from b200recon import ops, synth\n"
+        "cam = synth.D435; out = []\n"
+        "for seed in (1000, 3004):\n"
+        "    ds, dt, _ = synth.depth_pair(seed, seed + 1, cam)\n"
+        "    cl = []\n"
+        "    for d in (ds, dt):\n"
+        "        x = ops.deproject_z16(d, cam['fx'], cam['fy'], cam['ppx'], cam['ppy'], cam['depth_scale'])\n"
+        "        cl.append(np.ascontiguousarray(ops.voxel_down_sample_tensor(x[x[:, 2] > 0], 0.005)['points'], dtype=np.float64))\n"
+        "    nrm = ops.estimate_normals_legacy(cl[1], 30, 0.01)\n"
+        "    for kind in (1, 0):\n"
+        "        r = ops.icp(kind, cl[0], cl[1], 0.02, tgt_normals=nrm, max_iter=30)\n"
+        "        out.append([r['transformation'].tobytes().hex(), r['fitness'], r['inlier_rmse'], r['iterations'],\n"
+        "                    hashlib.sha1(np.ascontiguousarray(r['corr']).tobytes()).hexdigest()])\n"
+        "print(json.dumps(out))\n" % root)
+    runs = []
+    for off in (False, True):
+        env = dict(os.environ)
+        env.pop("B3D_ICP_NO_STICKY", None)
+        if off:
+            env["B3D_ICP_NO_STICKY"] = "1"
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env, cwd=root)
+        assert r.returncode == 0, r.stderr[-2000:]
+        runs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert runs[0] == runs[1]
+    assert all(row[3] >= 3 for row in runs[0])
+
+
 def test_capture_and_alignment_classes(b3):
     """The reference's scan loop (main.py:34-49) over replayed fixture frames: capture -> align -> accumulate."""
     from b200recon import synth
