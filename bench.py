@@ -298,10 +298,10 @@ def main():
         if top:
             b = kernel_bytes(top["name"], N_raw, Ms + Mt, Mt, Ms, n_corr, icp_bpl)
             ach = top["gbps"] if top["gbps"] is not None else 0.0
-            # DRAM traffic of one full-batch launch of the dominant kernel from the committed `ncu --set full` capture of this
-            # command (profiles/r01k_ncu_icp_pass_p64_digest.txt: dram__bytes_read.sum + dram__bytes_write.sum; an early pass,
-            # which also writes the staged-set cache)
-            traffic = {"icp_pass_kernel": 2.495721e9 + 520.64768e6}.get(top["name"]) if P == 64 else None
+            # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture of this command
+            # (profiles/r01l_ncu_icp_pass_p64_step_digest.txt: dram__bytes_read.sum + dram__bytes_write.sum over the ten
+            # passes of one 64-pair step = 17.25 GB + 1.77 GB, divided by the ten launches -- per launch, like `achieved`)
+            traffic = {"icp_pass_kernel": 19.02256e9 / 10.0}.get(top["name"]) if P == 64 else None
             roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                         "peak_source": peak_src, "algorithmic_bytes_per_launch": b, "avg_launch_us": top["avg_us"], "share_of_step": top["share"]}
         # whole-pipeline roofline: compulsory bytes of every stage (SURVEY 8d "pipeline per pair") over the device-timed step
