@@ -29,6 +29,11 @@ class IcpResult(C.Structure):
                 ("iterations", C.c_int32), ("converged", C.c_int32), ("n_correspondences", C.c_int64)]
 
 
+class RansacResult(C.Structure):
+    _fields_ = [("transformation", C.c_double * 16), ("fitness", C.c_double), ("inlier_rmse", C.c_double),
+                ("n_correspondences", C.c_int64), ("iterations", C.c_int64), ("validated", C.c_int64)]
+
+
 class PairParams(C.Structure):
     _fields_ = [("w", C.c_int), ("h", C.c_int), ("fx", C.c_float), ("fy", C.c_float), ("ppx", C.c_float), ("ppy", C.c_float),
                 ("depth_scale", C.c_float), ("voxel_size", C.c_float), ("normals_max_nn", C.c_int), ("normals_radius", C.c_double),
@@ -75,6 +80,8 @@ SIGNATURES = {
     "b3d_covariances_from_normals": (_i, [_vp, _vp, _i64, _d, _vp]),
     "b3d_compute_fpfh": (_i, [_vp, _vp, _vp, _i64, _i, _d, _vp]),
     "b3d_orient_normals_consistent_tangent_plane": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
+    "b3d_match_features": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _vp]),
+    "b3d_ransac_correspondence": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _d, _i, _d, _d, _i64, _d, C.c_uint64, _vp]),
     "b3d_statistical_outlier": (_i, [_vp, _vp, _i64, _i, _d, _vp, _vp, _pi64]),
     "b3d_radius_outlier": (_i, [_vp, _vp, _i64, _i, _d, _vp, _vp, _pi64]),
     "b3d_gather_rows_f64": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),

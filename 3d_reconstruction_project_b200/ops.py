@@ -199,6 +199,36 @@ def compute_fpfh(points, normals, max_nn, radius, device=0, as_tensor=False):
     return _out(out, as_tensor)
 
 
+def match_features(feat_a, feat_b, device=0, as_tensor=False):
+    """Nearest feature of feat_b ([nb, dim]) for every row of feat_a ([na, dim]): the k-d tree search on FPFH features inside
+    registration_ransac_based_on_feature_matching -- test/mini1.py:269. -> int32 [na]"""
+    ctx = get_context(device)
+    a, b = ctx.to_device(feat_a, torch.float64), ctx.to_device(feat_b, torch.float64)
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1]:
+        raise ValueError("features must be [n, dim] arrays of the same dimension")
+    out = ctx.empty((max(a.shape[0], 1),), torch.int32)
+    N.check(N.lib().b3d_match_features(ctx.handle, ptr(a), a.shape[0], ptr(b), b.shape[0], int(a.shape[1]), ptr(out)))
+    return _out(out[:a.shape[0]], as_tensor)
+
+
+def ransac_correspondence(src, tgt, corres, max_dist, ransac_n=3, edge_similarity=0.0, checker_distance=0.0, max_iteration=100000,
+                          confidence=0.999, seed=0, device=0):
+    """registration_ransac_based_on_correspondence (point-to-point estimation) -- the loop behind test/mini1.py:269-281.
+    corres: int [nc, 2] (source index, target index)."""
+    ctx = get_context(device)
+    s, t = ctx.to_device(src, torch.float64), ctx.to_device(tgt, torch.float64)
+    _check_n3(s, "source points")
+    _check_n3(t, "target points")
+    c = ctx.to_device(np.ascontiguousarray(np.asarray(corres).reshape(-1, 2), dtype=np.int32) if not isinstance(corres, torch.Tensor) else corres,
+                      torch.int32)
+    r = N.RansacResult()
+    N.check(N.lib().b3d_ransac_correspondence(ctx.handle, ptr(s), s.shape[0], ptr(t), t.shape[0], ptr(c), c.shape[0], float(max_dist), int(ransac_n),
+                                              float(edge_similarity), float(checker_distance), int(max_iteration), float(confidence),
+                                              C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), C.byref(r)))
+    return dict(transformation=np.array(r.transformation[:], dtype=np.float64).reshape(4, 4), fitness=r.fitness, inlier_rmse=r.inlier_rmse,
+                n_corr=int(r.n_correspondences), iterations=int(r.iterations), validated=int(r.validated))
+
+
 def _outlier(fn, points, a, b, device, as_tensor):
     ctx = get_context(device)
     p = ctx.to_device(points, torch.float64)

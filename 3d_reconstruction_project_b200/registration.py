@@ -132,3 +132,78 @@ def compute_fpfh_feature(input, search_param):
         raise RuntimeError("compute_fpfh_feature: only KDTreeSearchParamHybrid / KDTreeSearchParamKNN are supported")
     f = ops.compute_fpfh(np.asarray(pcd.points), np.asarray(pcd.normals), k, r, device=pcd.device)
     return Feature(np.ascontiguousarray(f.T))
+
+
+# ---- global registration from feature matches (test/mini1.py:269-281, test/check2.py:132-144, test/check3.py:181) ----------
+class CorrespondenceCheckerBasedOnEdgeLength:
+    def __init__(self, similarity_threshold=0.9):
+        self.similarity_threshold = float(similarity_threshold)
+
+
+class CorrespondenceCheckerBasedOnDistance:
+    def __init__(self, distance_threshold):
+        self.distance_threshold = float(distance_threshold)
+
+
+class RANSACConvergenceCriteria:
+    def __init__(self, max_iteration=100000, confidence=0.999):
+        self.max_iteration, self.confidence = int(max_iteration), float(confidence)
+
+
+def _feature_rows(f):
+    """Feature / [dim, N] array (Open3D's layout) -> [N, dim] rows."""
+    data = f.data if isinstance(f, Feature) else f
+    return np.ascontiguousarray(np.asarray(data, dtype=np.float64).T)
+
+
+def _checker_params(checkers):
+    edge, dist = 0.0, 0.0
+    for c in checkers or []:
+        if isinstance(c, CorrespondenceCheckerBasedOnEdgeLength):
+            edge = c.similarity_threshold
+        elif isinstance(c, CorrespondenceCheckerBasedOnDistance):
+            dist = c.distance_threshold
+        else:
+            raise RuntimeError("only CorrespondenceCheckerBasedOnEdgeLength / CorrespondenceCheckerBasedOnDistance are supported on this path")
+    return edge, dist
+
+
+def registration_ransac_based_on_correspondence(source, target, corres, max_correspondence_distance, estimation_method=None, ransac_n=3,
+                                                checkers=None, criteria=None, seed=0):
+    """Hypotheses from ransac_n random correspondences, cheap checkers, validation of the survivors against the whole target;
+    the best (fitness, then rmse) wins. `seed` selects the random picks (the library seeds from the system unless told)."""
+    source, target = as_cloud(source), as_cloud(target)
+    estimation_method = estimation_method or TransformationEstimationPointToPoint(False)
+    if not isinstance(estimation_method, TransformationEstimationPointToPoint):
+        raise RuntimeError("RANSAC registration is built for TransformationEstimationPointToPoint (the reference's choice)")
+    criteria = criteria or RANSACConvergenceCriteria()
+    edge, dist = _checker_params(checkers)
+    sp, tp = np.asarray(source.points), np.asarray(target.points)
+    r = ops.ransac_correspondence(sp, tp, corres, max_correspondence_distance, ransac_n, edge, dist, criteria.max_iteration, criteria.confidence,
+                                  seed, device=source.device)
+    if r["n_corr"] == 0:
+        return RegistrationResult(dict(transformation=np.eye(4), fitness=0.0, inlier_rmse=0.0, iterations=r["iterations"], converged=False, corr=None))
+    # GetRegistrationResultAndCorrespondences at the winning transform: fitness, rmse and the correspondence set
+    ev = evaluate_registration(source, target, max_correspondence_distance, r["transformation"])
+    ev.iterations = r["iterations"]
+    return ev
+
+
+def registration_ransac_based_on_feature_matching(source, target, source_feature, target_feature, mutual_filter, max_correspondence_distance,
+                                                  estimation_method=None, ransac_n=3, checkers=None, criteria=None, seed=0):
+    """test/mini1.py:269-281 (ransac_n=4, edge length 0.9 + distance checkers, 4 000 000 iterations at confidence 0.999)."""
+    source, target = as_cloud(source), as_cloud(target)
+    if ransac_n < 3 or max_correspondence_distance <= 0:
+        return RegistrationResult(dict(transformation=np.eye(4), fitness=0.0, inlier_rmse=0.0, iterations=0, converged=False, corr=None))
+    fs, ft = _feature_rows(source_feature), _feature_rows(target_feature)
+    if len(fs) != len(source.points) or len(ft) != len(target.points):
+        raise RuntimeError("feature count does not match the point count")
+    ij = ops.match_features(fs, ft, device=source.device)
+    corres = np.stack([np.arange(len(ij), dtype=np.int32), ij], axis=1)
+    if mutual_filter:
+        ji = ops.match_features(ft, fs, device=source.device)
+        keep = ji[ij] == np.arange(len(ij))
+        if int(keep.sum()) >= ransac_n:  # too few mutual matches: fall back to all of them, like the library
+            corres = corres[keep]
+    return registration_ransac_based_on_correspondence(source, target, corres, max_correspondence_distance, estimation_method, ransac_n,
+                                                       checkers, criteria, seed)

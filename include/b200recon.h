@@ -131,6 +131,27 @@ int b3d_orient_normals_consistent_tangent_plane(b3d_ctx* ctx, const double* xyz,
  * out: float64 [n, 33] row-major (Open3D's Feature.data is its transpose). */
 int b3d_compute_fpfh(b3d_ctx* ctx, const double* xyz, const double* normals, int64_t n, int max_nn, double radius, double* out);
 
+/* ---- global registration from feature matches ------------------------------------------------ */
+/* Nearest feature of feat_b for every feature of feat_a (squared L2 in float64, ties to the smallest index): the
+ * correspondence search inside registration_ransac_based_on_feature_matching -- test/mini1.py:269, test/check2.py:132.
+ * Features are row-major [n, dim] (b3d_compute_fpfh's layout), dim <= 64. nn_out: int32 [na] (-1 when nb == 0). */
+int b3d_match_features(b3d_ctx* ctx, const double* feat_a, int64_t na, const double* feat_b, int64_t nb, int dim, int32_t* nn_out);
+typedef struct b3d_ransac_result {
+    double transformation[16]; /* row-major; identity when nothing was found */
+    double fitness, inlier_rmse;
+    int64_t n_correspondences; /* inliers of the best hypothesis over the whole source cloud */
+    int64_t iterations;        /* hypotheses drawn before the confidence criterion (or max_iteration) stopped the loop */
+    int64_t validated;         /* hypotheses that passed the checkers and were validated against the target */
+} b3d_ransac_result;
+/* registration_ransac_based_on_correspondence with TransformationEstimationPointToPoint(False) -- the loop behind
+ * registration_ransac_based_on_feature_matching (test/mini1.py:269-281). corres: device int32 [nc, 2] (source index, target
+ * index). edge_similarity / checker_distance <= 0 switch the CorrespondenceCheckerBasedOnEdgeLength / ...BasedOnDistance off.
+ * Hypothesis i is a pure function of (seed, i); the result is what a single-threaded run of the library's loop gives with
+ * those picks. ransac_n in [3, 8]; like upstream, ransac_n < 3 or max_dist <= 0 gives the empty result. */
+int b3d_ransac_correspondence(b3d_ctx* ctx, const double* src, int64_t ns, const double* tgt, int64_t nt, const int32_t* corres, int64_t nc,
+                              double max_dist, int ransac_n, double edge_similarity, double checker_distance, int64_t max_iteration,
+                              double confidence, uint64_t seed, b3d_ransac_result* result_h);
+
 /* ---- outlier filters -------------------------------------------------------------------------------------- */
 /* remove_statistical_outlier(nb_neighbors, std_ratio) -- pointcloud_processing.py:35-36, test/mini1.py:175.
  * keep: uint8 [n]; kept_idx: int64 [n] ascending indices (optional); n_kept_h: count. */

@@ -220,6 +220,26 @@ def orient_normals(points, normals, k=100):
     return out, flipped.astype(bool)
 
 
+def match_features(fa, fb):
+    """Nearest row of fb for every row of fa (float64 squared L2, ties to the smallest index)."""
+    fa, fb = _c(fa, np.float64), _c(fb, np.float64)
+    out = np.empty(len(fa), np.int32)
+    lib().orc_match_features(_p(fa), C.c_int64(len(fa)), _p(fb), C.c_int64(len(fb)), int(fa.shape[1]), _p(out))
+    return out
+
+
+def ransac(src, tgt, corres, dmax, ransac_n=3, edge_similarity=0.0, checker_distance=0.0, max_iteration=100000, confidence=0.999, seed=0):
+    """registration_ransac_based_on_correspondence, single-threaded bookkeeping, counter-based picks (test/mini1.py:269-281)."""
+    src, tgt = _c(src, np.float64), _c(tgt, np.float64)
+    corres = np.ascontiguousarray(np.asarray(corres).reshape(-1, 2), dtype=np.int32)
+    T = np.empty(16, np.float64)
+    st = np.zeros(5, np.float64)
+    lib().orc_ransac(_p(src), C.c_int64(len(src)), _p(tgt), C.c_int64(len(tgt)), _p(corres), C.c_int64(len(corres)), C.c_double(dmax), int(ransac_n),
+                     C.c_double(edge_similarity), C.c_double(checker_distance), C.c_int64(max_iteration), C.c_double(confidence),
+                     C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), _p(T), _p(st))
+    return dict(transformation=T.reshape(4, 4), fitness=st[0], inlier_rmse=st[1], n_corr=int(st[2]), iterations=int(st[3]), validated=int(st[4]))
+
+
 P2P, P2L, GICP = 0, 1, 2
 
 

@@ -1351,4 +1351,147 @@ int orc_orient_normals(const double* pts, double* nrm, int64_t n, int k, uint8_t
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// registration_ransac_based_on_feature_matching -- test/mini1.py:269-281, test/check2.py:132-144.  PARITY UNPINNED
+// (upstream draws from a std::mt19937 seeded by the system, one hypothesis per OpenMP thread at a time: no two runs of the
+// library agree). Restated as the library's loop run by ONE thread, with counter-based picks (splitmix64 of (seed, itr, j))
+// so that a hypothesis is a pure function of its index: feature nearest neighbours (brute force, the k-d tree metric's
+// accumulation order), Umeyama on the picks, edge-length and distance checkers, validation = 1-NN within d_max of every
+// transformed source point, IsBetterRANSACThan (fitness, then rmse), estimated iterations for the confidence.
+// The rmse tie-break uses the sum of squared distances in units of d_max^2 / 2^40, like the device path.
+// ---------------------------------------------------------------------------------------------
+namespace {
+inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+inline int64_t ransac_pick(uint64_t seed, int64_t itr, int j, int64_t nc) {
+    const uint64_t x = splitmix64(splitmix64(seed) ^ ((uint64_t)itr * 8ull + (uint64_t)j));
+    return (int64_t)(((unsigned __int128)x * (unsigned __int128)(uint64_t)nc) >> 64);
+}
+inline double feature_dist2(const double* a, const double* b, int dim) {
+    double r = 0.0;
+    int k = 0;
+    for (; k + 3 < dim; k += 4) {
+        const double d0 = a[k] - b[k], d1 = a[k + 1] - b[k + 1], d2 = a[k + 2] - b[k + 2], d3 = a[k + 3] - b[k + 3];
+        r += ((d0 * d0 + d1 * d1) + d2 * d2) + d3 * d3;
+    }
+    for (; k < dim; ++k) {
+        const double d = a[k] - b[k];
+        r += d * d;
+    }
+    return r;
+}
+}  // namespace
+
+void orc_match_features(const double* fa, int64_t na, const double* fb, int64_t nb, int dim, int32_t* nn) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < na; ++i) {
+        double best = 1.0e300;
+        int32_t bi = -1;
+        for (int64_t j = 0; j < nb; ++j) {
+            const double d = feature_dist2(fa + i * dim, fb + j * dim, dim);
+            if (d < best) { best = d; bi = (int32_t)j; }
+        }
+        nn[i] = bi;
+    }
+}
+
+// out: T[16], stats[5] = fitness, rmse (from the quantised sum), inliers, iterations, validated
+int orc_ransac(const double* src, int64_t ns, const double* tgt, int64_t nt, const int32_t* corres, int64_t nc, double dmax, int n, double edge_sim,
+               double check_dist, int64_t max_iteration, double confidence, uint64_t seed, double* T_out, double* stats) {
+    mat4_identity(T_out);
+    for (int i = 0; i < 5; ++i) stats[i] = 0.0;
+    if (n < 3 || n > 8 || dmax <= 0 || nc < n || ns == 0 || nt == 0) return 0;
+    KdTree<double> tree;
+    tree.build(tgt, nt);
+    const double r2 = dmax * dmax, q_scale = 1099511627776.0 / r2;
+    int64_t est_k = max_iteration, validated = 0, itr = 0;
+    bool have = false;
+    int64_t best_cnt = 0;
+    uint64_t best_sumq = 0;
+    std::vector<double> moved((size_t)ns * 3);
+    std::vector<int32_t> corr(ns);
+    for (; itr < max_iteration && itr < est_k; ++itr) {
+        double s[8][3], t[8][3], mu_s[3] = {0, 0, 0}, mu_d[3] = {0, 0, 0};
+        for (int j = 0; j < n; ++j) {
+            const int64_t c = ransac_pick(seed, itr, j, nc);
+            const int32_t si = corres[2 * c], ti = corres[2 * c + 1];
+            for (int a = 0; a < 3; ++a) {
+                s[j][a] = src[3 * (int64_t)si + a];
+                t[j][a] = tgt[3 * (int64_t)ti + a];
+                mu_s[a] += s[j][a];
+                mu_d[a] += t[j][a];
+            }
+        }
+        bool ok = true;
+        if (edge_sim > 0.0)
+            for (int i = 0; i < n && ok; ++i)
+                for (int j = i + 1; j < n; ++j) {
+                    const double a0 = s[i][0] - s[j][0], a1 = s[i][1] - s[j][1], a2 = s[i][2] - s[j][2];
+                    const double b0 = t[i][0] - t[j][0], b1 = t[i][1] - t[j][1], b2 = t[i][2] - t[j][2];
+                    const double ds = std::sqrt((a0 * a0 + a1 * a1) + a2 * a2), dt = std::sqrt((b0 * b0 + b1 * b1) + b2 * b2);
+                    if (ds < dt * edge_sim || dt < ds * edge_sim) { ok = false; break; }
+                }
+        if (!ok) continue;
+        const double inv_n = 1.0 / (double)n;
+        for (int a = 0; a < 3; ++a) { mu_s[a] *= inv_n; mu_d[a] *= inv_n; }
+        double Sigma[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < n; ++j)
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) Sigma[3 * r + c] += (t[j][r] - mu_d[r]) * (s[j][c] - mu_s[c]);
+        for (int k = 0; k < 9; ++k) Sigma[k] *= inv_n;
+        double T[16];
+        umeyama_from_moments(mu_s, mu_d, Sigma, T);
+        for (int k = 0; k < 12 && ok; ++k)
+            if (!std::isfinite(T[k])) ok = false;
+        if (ok && check_dist > 0.0)
+            for (int j = 0; j < n; ++j) {
+                const double x = T[0] * s[j][0] + T[1] * s[j][1] + T[2] * s[j][2] + T[3];
+                const double y = T[4] * s[j][0] + T[5] * s[j][1] + T[6] * s[j][2] + T[7];
+                const double z = T[8] * s[j][0] + T[9] * s[j][1] + T[10] * s[j][2] + T[11];
+                const double e0 = x - t[j][0], e1 = y - t[j][1], e2 = z - t[j][2];
+                if (std::sqrt((e0 * e0 + e1 * e1) + e2 * e2) > check_dist) { ok = false; break; }
+            }
+        if (!ok) continue;
+        ++validated;
+        // validation over the whole cloud (same arithmetic as the device path: no perspective division, rows of T)
+        int64_t cnt = 0;
+        uint64_t sumq = 0;
+#pragma omp parallel for schedule(static) reduction(+ : cnt, sumq)
+        for (int64_t i = 0; i < ns; ++i) {
+            const double* p = src + 3 * i;
+            const double q[3] = {T[0] * p[0] + T[1] * p[1] + T[2] * p[2] + T[3], T[4] * p[0] + T[5] * p[1] + T[6] * p[2] + T[7],
+                                 T[8] * p[0] + T[9] * p[1] + T[10] * p[2] + T[11]};
+            double d2 = 0.0;
+            if (tree.nn_within(q, r2, &d2) >= 0) {
+                ++cnt;
+                sumq += (uint64_t)(d2 * q_scale);
+            }
+        }
+        bool better;
+        if (!have) better = cnt > 0;
+        else if (cnt != best_cnt) better = cnt > best_cnt;
+        else better = cnt > 0 && sumq < best_sumq;
+        if (!better) continue;
+        have = true;
+        best_cnt = cnt;
+        best_sumq = sumq;
+        std::memcpy(T_out, T, 12 * sizeof(double));
+        const double ratio = (double)cnt / (double)nc;
+        const double est = std::log(1.0 - confidence) / std::log(1.0 - std::pow(ratio, n));
+        if (est < (double)est_k) est_k = (int64_t)std::ceil(est);
+    }
+    stats[3] = (double)std::min(itr, std::min(est_k, max_iteration));
+    stats[4] = (double)validated;
+    if (have) {
+        stats[0] = (double)best_cnt / (double)ns;
+        stats[1] = std::sqrt((double)best_sumq / q_scale / (double)best_cnt);
+        stats[2] = (double)best_cnt;
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -468,6 +468,47 @@ def test_orient_normals_consistent_tangent_plane(ops):
         ops.orient_normals_consistent_tangent_plane(pts, None, 100)
 
 
+def test_match_features_bit_exact(ops):
+    """The feature nearest-neighbour search of registration_ransac_based_on_feature_matching (test/mini1.py:269): FPFH of two
+    fixture clouds, indices identical to the oracle's brute force; odd sizes and a dimension that is not a multiple of 4."""
+    pa, na = golden_cloud("output_00094")
+    pb, nb_ = golden_cloud("output84_00060")
+    fa, fb = ops.compute_fpfh(pa, na, 100, 0.1), ops.compute_fpfh(pb, nb_, 100, 0.1)
+    assert np.array_equal(ops.match_features(fa, fb), oracle.match_features(fa, fb))
+    rng = np.random.default_rng(3)
+    for na_, nb2, dim in ((1, 1, 1), (130, 33, 5), (257, 1000, 33), (5, 0, 7)):
+        a, b = rng.normal(size=(na_, dim)), rng.normal(size=(nb2, dim))
+        if nb2 > 4:
+            b[3] = b[1]  # exact tie: the smaller index wins
+            a[0] = b[1]
+        assert np.array_equal(ops.match_features(a, b), oracle.match_features(a, b))
+
+
+def test_ransac_correspondence_vs_oracle(ops):
+    """registration_ransac_based_on_correspondence (test/mini1.py:269-281: ransac_n 4, edge-length 0.9 and distance checkers,
+    confidence 0.999): same picks on the device and in the oracle -> same winning hypothesis."""
+    tgt, _ = golden_cloud("output_00094")
+    T = small_rigid(0.3, -0.2, 0.5, (0.1, -0.05, 0.2))
+    rng = np.random.default_rng(11)
+    src = oracle.transform(np.linalg.inv(T), tgt)[0] + rng.normal(0, 2e-4, tgt.shape)
+    n = len(src)
+    corr = np.stack([np.arange(n), np.arange(n)], 1)
+    bad = rng.random(n) < 0.9
+    corr[bad, 1] = rng.integers(0, n, int(bad.sum()))
+    for seed, rn, edge, dist in ((1, 4, 0.9, 0.01), (2, 3, 0.0, 0.01), (3, 3, 0.9, 0.0)):
+        ref = oracle.ransac(src, tgt, corr, 0.01, rn, edge, dist, 20000, 0.999, seed=seed)
+        out = ops.ransac_correspondence(src, tgt, corr, 0.01, rn, edge, dist, 20000, 0.999, seed=seed)
+        assert out["n_corr"] == ref["n_corr"] and out["validated"] == ref["validated"] and out["iterations"] == ref["iterations"]
+        assert np.allclose(out["transformation"], ref["transformation"], atol=1e-9)
+        assert abs(out["inlier_rmse"] - ref["inlier_rmse"]) < 1e-12
+        assert out["fitness"] > 0.95 and rot_err(out["transformation"][:3, :3], T[:3, :3]) < 5e-3
+    # degenerate requests give the library's empty result
+    empty = ops.ransac_correspondence(src, tgt, corr, 0.01, 2, 0.9, 0.01, 1000, 0.999)
+    assert empty["fitness"] == 0.0 and np.array_equal(empty["transformation"], np.eye(4))
+    none = ops.ransac_correspondence(src, tgt, corr, 0.01, 3, 0.0, 0.0, 0, 0.999)  # no iterations allowed
+    assert none["n_corr"] == 0 and np.array_equal(none["transformation"], np.eye(4))
+
+
 def test_fpfh_features(ops):
     """compute_fpfh_feature(Hybrid(0.1, 100)) as in test/mini1.py:244-250 on a fixture cloud with its own normals."""
     pts, nrm = golden_cloud("output_00094")

@@ -119,6 +119,43 @@ def test_sticky_correspondences_change_nothing(b3):
     assert all(row[3] >= 3 for row in runs[0])
 
 
+def test_global_registration_recipe(b3):
+    """The reference's multiway-registration recipe on one pair (test/mini1.py:236-303): voxel grid, statistical outliers,
+    normals, FPFH(5 voxels, 100) -> RANSAC on feature matches (ransac_n 4, edge 0.9 + distance checkers) -> point-to-plane ICP
+    at 0.4 voxels from the RANSAC pose -> information matrix. The large motion (25 degrees, 30 cm) is out of plain ICP's reach."""
+    from b200recon import registration as reg
+    from b200recon.geometry import KDTreeSearchParamHybrid
+    pts, _ = golden_cloud("output_00094")
+    voxel = 0.01
+    T = small_rigid(0.35, -0.25, 0.4, (0.3, -0.1, 0.2))
+    rng = np.random.default_rng(5)
+    clouds, feats = [], []
+    for k, P in enumerate((oracle.transform(np.linalg.inv(T), pts)[0] + rng.normal(0, 1e-4, pts.shape), pts)):
+        pcd = b3.PointCloud(P).voxel_down_sample(voxel)
+        pcd, _ = pcd.remove_statistical_outlier(nb_neighbors=20, std_ratio=2.0)
+        pcd.estimate_normals(KDTreeSearchParamHybrid(radius=voxel * 2, max_nn=30))
+        clouds.append(pcd)
+        feats.append(reg.compute_fpfh_feature(pcd, KDTreeSearchParamHybrid(radius=voxel * 5, max_nn=100)))
+    src, tgt = clouds
+    ransac = reg.registration_ransac_based_on_feature_matching(
+        src, tgt, feats[0].data, feats[1].data, mutual_filter=False, max_correspondence_distance=voxel * 1.5,
+        estimation_method=reg.TransformationEstimationPointToPoint(False), ransac_n=4,
+        checkers=[reg.CorrespondenceCheckerBasedOnEdgeLength(0.9), reg.CorrespondenceCheckerBasedOnDistance(voxel * 1.5)],
+        criteria=reg.RANSACConvergenceCriteria(max_iteration=4000000, confidence=0.999))
+    assert ransac.transformation.any() and ransac.fitness > 0.5
+    assert len(ransac.correspondence_set) == round(ransac.fitness * len(src.points))
+    icp = reg.registration_icp(src, tgt, voxel * 0.4, ransac.transformation, reg.TransformationEstimationPointToPlane())
+    assert rot_err(icp.transformation[:3, :3], T[:3, :3]) < 2e-3 and np.linalg.norm(icp.transformation[:3, 3] - T[:3, 3]) < 2e-3
+    info = reg.get_information_matrix_from_point_clouds(src, tgt, voxel * 1.5, icp.transformation)
+    assert info.shape == (6, 6) and info[3, 3] == len(reg.evaluate_registration(src, tgt, voxel * 1.5, icp.transformation).correspondence_set)
+    # plain ICP from the identity does not get there
+    plain = reg.registration_icp(src, tgt, voxel * 1.5, np.eye(4), reg.TransformationEstimationPointToPlane())
+    assert rot_err(plain.transformation[:3, :3], T[:3, :3]) > 0.1
+    mutual = reg.registration_ransac_based_on_feature_matching(src, tgt, feats[0], feats[1], True, voxel * 1.5, ransac_n=3,
+                                                               criteria=reg.RANSACConvergenceCriteria(100000, 0.999))
+    assert mutual.fitness > 0.5
+
+
 def test_capture_and_alignment_classes(b3):
     """The reference's scan loop (main.py:34-49) over replayed fixture frames: capture -> align -> accumulate."""
     from b200recon import synth
