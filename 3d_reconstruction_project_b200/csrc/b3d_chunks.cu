@@ -130,7 +130,7 @@ static int cut_chunks(b3d_ctx* ctx, const uint64_t* keys, const double4* pts, in
     DevBuf<int64_t> n_heads;
     B3D_TRY(heads.alloc(ctx, (size_t)n));
     B3D_TRY(n_heads.alloc(ctx, 1));
-    double tau_cells = 2.0;
+    double tau_cells = 1.5;  // measured on config 2 (1.0 / 1.25 / 1.5 / 2.0 / 3.0 cells: 49.7 / 47.9 / 47.5 / 47.8 / 51.5 ms per step)
     if (const char* e = getenv("B3D_CHUNK_GAP")) tau_cells = atof(e);
     const double tau = tau_cells * cell;
     B3D_TRY(compact(ctx, GapPred{pts, keys, shift, tau * tau}, ChunkEmit{heads.p}, n, n_heads.p));

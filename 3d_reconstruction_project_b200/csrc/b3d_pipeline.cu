@@ -6,6 +6,7 @@
 // one hash grid, one normals launch, and P-wide ICP passes (grid.y = pair). Host synchronisations per batch: a handful
 // (bounds -> lattice, run count -> sizes, final results), independent of P.
 #include "b3d_common.cuh"
+#include <cstdlib>
 #include "b3d_icp.cuh"
 #include "b3d_search.cuh"
 
@@ -81,14 +82,17 @@ static int register_clouds_f32(b3d_ctx* ctx, DevBuf<float>& xyz, const std::vect
     B3D_TRY(upload_segments(ctx, toff, &toff_d, &tseg));
 
     // 4. ONE target grid for the normals and for the ICP correspondence search whenever their radii are comparable: cell =
-    // the larger radius (one ring covers both; the staged searches take any cell size). One sort instead of two.
+    // 1.3 x the larger radius (the staged searches take any cell size). One sort instead of two. Measured on config 2
+    // (ms per 64-pair step at cell = 0.75 / 1 / 1.2 / 1.35 / 1.5 / 2 radii: 59.8 / 50.8 / 48.1 / 48.0 / 50.0 / 58.7): larger
+    // cells mean fewer hash probes per staged box, until the boxes of the normals overflow their staging buffer.
     Grid<double> tgrid, icp_grid_own;
     const Grid<double>* icp_grid = &tgrid;
     int n_rmax = 1, icp_rmax = 1;
     const double r_n = pr->normals_radius, r_i = pr->icp_max_dist;
     const bool shared = r_n > 0 && std::max(r_n, r_i) <= 3.0 * std::min(r_n, r_i);
     if (shared) {
-        const double cell = std::max(r_n, r_i) * 1.001;
+        static const double cell_scale = getenv("B3D_PIPE_CELL_SCALE") ? atof(getenv("B3D_PIPE_CELL_SCALE")) : 1.3;
+        const double cell = std::max(r_n, r_i) * 1.001 * cell_scale;
         B3D_TRY(grid_build<double>(ctx, tgt_pts, tseg, cell, nullptr, &tgrid));
         n_rmax = rings_for_radius(r_n, cell);
         icp_rmax = rings_for_radius(r_i, cell);
