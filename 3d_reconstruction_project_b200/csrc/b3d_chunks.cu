@@ -39,7 +39,7 @@ __device__ __forceinline__ unsigned long long hilbert3(uint32_t x, uint32_t y, u
 // Morton key of the (transformed) query on a quarter-cell lattice of its cloud's search grid: consecutive keys are
 // spatially compact, so the 32 queries of a warp fit a small box (and stay compact under rigid updates).
 __global__ void __launch_bounds__(256) chunk_key_kernel(const double* __restrict__ pts, const int32_t* __restrict__ off, const double* __restrict__ transforms,
-                                                        int transform_stride, const Lattice* __restrict__ lat, int shift, int hilbert_bits,
+                                                        int transform_stride, const Lattice* __restrict__ lat, int shift, int hilbert_bits, int sub,
                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ order) {
     const int cloud = blockIdx.y;
     const Lattice L = lat[cloud];
@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256) chunk_key_kernel(const double* __restrict
     if (transforms != nullptr)
         for (int k = 0; k < 12; ++k) T[k] = transforms[(int64_t)cloud * transform_stride + k];
     const int32_t s0 = off[cloud], s1 = off[cloud + 1];
-    const double q = L.cell * 0.25;
+    const double q = L.cell / (double)sub;
+    const double margin = (double)sub;  // one cell below the lattice origin
     for (int32_t i = s0 + blockIdx.x * blockDim.x + threadIdx.x; i < s1; i += gridDim.x * blockDim.x) {
         const double x = pts[3 * (int64_t)i], y = pts[3 * (int64_t)i + 1], z = pts[3 * (int64_t)i + 2];
         const double px = T[0] * x + T[1] * y + T[2] * z + T[3];
@@ -55,8 +56,8 @@ __global__ void __launch_bounds__(256) chunk_key_kernel(const double* __restrict
         const double pz = T[8] * x + T[9] * y + T[10] * z + T[11];
         const double hi = 2097151.0;  // 2^21 - 1
         // one cell of margin below the lattice origin; everything farther out clamps to the border
-        const double ux = fmin(fmax(floor((px - L.ox) / q) + 4.0, 0.0), hi), uy = fmin(fmax(floor((py - L.oy) / q) + 4.0, 0.0), hi),
-                     uz = fmin(fmax(floor((pz - L.oz) / q) + 4.0, 0.0), hi);
+        const double ux = fmin(fmax(floor((px - L.ox) / q) + margin, 0.0), hi), uy = fmin(fmax(floor((py - L.oy) / q) + margin, 0.0), hi),
+                     uz = fmin(fmax(floor((pz - L.oz) / q) + margin, 0.0), hi);
         const unsigned long long cap = (1ull << (shift / 3)) - 1ull;  // coordinates beyond the keyed range clamp to the border
         const unsigned long long ix = min((unsigned long long)ux, cap), iy = min((unsigned long long)uy, cap), iz = min((unsigned long long)uz, cap);
         const unsigned long long m = hilbert_bits > 0 ? hilbert3((uint32_t)ix, (uint32_t)iy, (uint32_t)iz, hilbert_bits)
@@ -160,7 +161,8 @@ int build_query_chunks(b3d_ctx* ctx, const double* pts, const int32_t* off_d, co
         longest = std::max<int64_t>(longest, off_h[b + 1] - off_h[b]);
     }
     int axis_bits = 1;
-    while (axis_bits < 21 && (1ll << axis_bits) < 4 * max_axis + 8) ++axis_bits;
+    static const int sub = getenv("B3D_CHUNK_SUB") ? std::max(1, atoi(getenv("B3D_CHUNK_SUB"))) : 4;  // lattice steps per grid cell
+    while (axis_bits < 21 && (1ll << axis_bits) < (int64_t)sub * max_axis + 2 * sub) ++axis_bits;
     int bbits = 0;
     while ((1ll << bbits) < B) ++bbits;
     while (3 * axis_bits + bbits > 63) --axis_bits;
@@ -173,7 +175,7 @@ int build_query_chunks(b3d_ctx* ctx, const double* pts, const int32_t* off_d, co
     B3D_TRY(o_out.alloc(ctx, n));
     const int kb = (int)std::min<int64_t>((longest + 255) / 256, std::max(1, ctx->sm_count * 16 / B));
     B3D_LAUNCH(ctx, chunk_key_kernel, dim3(std::max(1, kb), B), 256, 0, pts, off_d, transforms, transform_stride, lattices.lat.p, shift,
-               getenv("B3D_CHUNK_MORTON") ? 0 : axis_bits, k_in.p, o_in.p);
+               getenv("B3D_CHUNK_MORTON") ? 0 : axis_bits, sub, k_in.p, o_in.p);
     bool in_a = true;
     B3D_TRY(radix_sort_pairs(ctx, k_in.p, o_in.p, k_out.p, o_out.p, n, shift + bbits, &in_a));
     if (in_a) {

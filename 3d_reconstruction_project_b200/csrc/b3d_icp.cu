@@ -865,6 +865,15 @@ static void empty_result(const double* init_h, b3d_icp_result* r) {
     r->n_correspondences = 0;
 }
 
+// Target grid of a stand-alone registration: cells somewhat larger than d_max (fewer hash probes per staged box, see the
+// sweep in b3d_pipeline.cu); rmax = rings a per-lane walk needs for d_max on that grid.
+static int build_icp_grid(b3d_ctx* ctx, const double* tgt, const Segments& seg, double max_dist, Grid<double>* grid, int* rmax) {
+    static const double scale = getenv("B3D_ICP_CELL_SCALE") ? atof(getenv("B3D_ICP_CELL_SCALE")) : 1.3;
+    B3D_TRY(build_search_grid<double>(ctx, tgt, seg, 8, max_dist * scale, grid, nullptr));
+    *rmax = rings_for_radius(max_dist, grid->cell);
+    return B3D_OK;
+}
+
 // builds the single-pair problem (target grid included) inside st
 static int setup_single(b3d_ctx* ctx, b3d_icp_state* st, int kind, const double* src, int64_t ns_local, const double* src_cov, const double* tgt,
                         int64_t nt, const double* tgt_normals, const double* tgt_cov, double max_dist, const double* init_h, double rel_fitness,
@@ -873,7 +882,7 @@ static int setup_single(b3d_ctx* ctx, b3d_icp_state* st, int kind, const double*
     Segments sseg;
     B3D_TRY(single_segment(ctx, ns_local, &st->src_off, &sseg));
     int rmax = 1;
-    B3D_TRY(build_search_grid<double>(ctx, tgt, st->tgt_seg, 8, max_dist, &st->grid, &rmax));
+    B3D_TRY(build_icp_grid(ctx, tgt, st->tgt_seg, max_dist, &st->grid, &rmax));
     IcpProblem& pb = st->pb;
     pb.kind = kind;
     pb.P = 1;
@@ -1011,7 +1020,7 @@ int b3d_icp_batch(b3d_ctx* ctx, int kind, int n_pairs, const double* src, const 
     B3D_TRY(upload_segments(ctx, to, &st.tgt_off, &st.tgt_seg));
     B3D_TRY(upload_segments(ctx, so, &st.src_off, &sseg));
     int rmax = 1;
-    B3D_TRY(build_search_grid<double>(ctx, tgt, st.tgt_seg, 8, max_dist, &st.grid, &rmax));
+    B3D_TRY(build_icp_grid(ctx, tgt, st.tgt_seg, max_dist, &st.grid, &rmax));
     IcpProblem& pb = st.pb;
     pb.kind = kind;
     pb.P = P;
