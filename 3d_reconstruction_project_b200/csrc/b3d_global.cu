@@ -199,12 +199,7 @@ extern "C" int b3d_match_features(b3d_ctx* ctx, const double* feat_a, int64_t na
     B3D_REQUIRE(feat_a != nullptr && nn_out != nullptr && (feat_b != nullptr || nb == 0), "b3d_match_features: NULL buffer");
     B3D_TRY(ctx->bind());
     const size_t smem = (size_t)(kFeatTileQ * (dim + 1) + kFeatTileT * dim) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        B3D_CUDA(cudaFuncSetAttribute(feature_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)((kFeatTileQ * (kFeatMaxDim + 1) + kFeatTileT * kFeatMaxDim) * sizeof(double))));
-        attr_set = true;
-    }
+    B3D_CUDA(cudaFuncSetAttribute(feature_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B3D_LAUNCH(ctx, feature_nn_kernel, (int)((na + kFeatTileQ - 1) / kFeatTileQ), kFeatTileQ, smem, feat_a, na, feat_b, nb, dim, nn_out);
     return B3D_OK;
 }
