@@ -26,7 +26,14 @@ namespace {
 #endif
 constexpr int kIcpBlock = B3D_ICP_BLOCK;  // threads per block of the pass kernel (a warp works alone; the block only shares the partial sum)
 constexpr int kIcpInformation = 3;  // internal kind: G^T G of get_information_matrix_from_point_clouds (rows from the target point)
-constexpr int kIcpMaxGroups = 1024 * (128 / kIcpBlock);  // partial-sum groups (blocks) per pair
+// Partial-sum groups (blocks) per pair, a function of the pair's own chunk count only (batch == single-pair results). Fewer,
+// longer-lived blocks amortise every warp's cold start (four dependent loads before its first chunk is under way); more
+// blocks fill the machine when a single pair runs alone. Measured on config 2, ICP ms per 64-pair step / per single pair:
+// 128: 20.3 / 1.70, 256: 20.6 / 1.15, 384: 21.1 / 0.97, 512: 21.5 / 0.89, 1024: 23.4 / 0.89.
+#ifndef B3D_ICP_GROUPS
+#define B3D_ICP_GROUPS 384
+#endif
+constexpr int kIcpMaxGroups = B3D_ICP_GROUPS * (128 / kIcpBlock);  // partial-sum groups (blocks) per pair
 constexpr double kIcpReach2 = 1.25;   // search radius of a lane that found nothing last time, in units of d_max (see the pass kernel)
 
 // ---- small dense helpers (device) ----------------------------------------------------------------------------------
@@ -258,7 +265,6 @@ template <int KIND>
 __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel(IcpKernelArgs A) {
     const int pair = blockIdx.y;
     IcpPairState* st = A.state + pair;
-    if (st->done) return;
     __shared__ double sT[16];
     __shared__ double sm[kIcpBlock / 32][32];
     __shared__ double srow[kIcpBlock / 32][32][kIcpRow];
@@ -266,10 +272,15 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
     __shared__ int s_cand_pos[kIcpBlock / 32][kStageCap];
     __shared__ StageScratch s_stage[kIcpBlock / 32];
     __shared__ int s_last;
+    // one round trip for everything the block needs to start: the loop state (done flag, transform) and the pair's ranges
+    // are all requested before the first wait
+    const int done = st->done;
     if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
-    __syncthreads();
     const int32_t s0 = A.src_off[pair], s1 = A.src_off[pair + 1];
     const int32_t t0 = A.tgt_off[pair];
+    const int32_t c0 = A.chunk_off[pair], c1 = A.chunk_off[pair + 1];
+    if (done) return;  // uniform over the block
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int op_p, op_q;
     icp_sum_operands(KIND, lane, op_p, op_q);
@@ -282,7 +293,6 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
     const bool affine = sT[12] == 0.0 && sT[13] == 0.0 && sT[14] == 0.0 && sT[15] == 1.0;
     // this pair's range of warp chunks (chunks never straddle pairs) and its number of partial-sum groups: a function of
     // the pair's own chunk count only, so a pair's result does not depend on what else is in the batch
-    const int32_t c0 = A.chunk_off[pair], c1 = A.chunk_off[pair + 1];
     const int groups = max(1, min((c1 - c0 + kIcpBlock / 32 - 1) / (kIcpBlock / 32), kIcpMaxGroups));
     if ((int)blockIdx.x >= groups) return;
     // the next chunk's query is fetched while the current one is processed (two dependent loads off the critical path)

@@ -161,7 +161,10 @@ __global__ void __launch_bounds__(128) normals_kernel(GridView<T> g, const uint6
 // per-lane kernel afterwards.
 constexpr int kNrmBlock = 128;
 constexpr int kNrmList = 32;   // neighbours per lane kept in shared memory (k <= 32 on this path)
-constexpr int kNrmCap = 192;   // staged candidates per warp
+#ifndef B3D_NRM_CAP
+#define B3D_NRM_CAP 192
+#endif
+constexpr int kNrmCap = B3D_NRM_CAP;   // staged candidates per warp
 
 struct NrmWarpSmem {
     float4 cand[kNrmCap];
