@@ -299,9 +299,9 @@ def main():
             b = kernel_bytes(top["name"], N_raw, Ms + Mt, Mt, Ms, n_corr, icp_bpl)
             ach = top["gbps"] if top["gbps"] is not None else 0.0
             # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture of this command
-            # (profiles/r01l_ncu_icp_pass_p64_step_digest.txt: dram__bytes_read.sum + dram__bytes_write.sum over the ten
-            # passes of one 64-pair step = 17.25 GB + 1.77 GB, divided by the ten launches -- per launch, like `achieved`)
-            traffic = {"icp_pass_kernel": 19.02256e9 / 10.0}.get(top["name"]) if P == 64 else None
+            # (profiles/r01n_ncu_icp_pass_p64_step_digest.txt: dram__bytes_read.sum + dram__bytes_write.sum over the ten
+            # passes of one 64-pair step = 15.94 GB + 1.69 GB, divided by the ten launches -- per launch, like `achieved`)
+            traffic = {"icp_pass_kernel": 17.628067e9 / 10.0}.get(top["name"]) if P == 64 else None
             roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                         "peak_source": peak_src, "algorithmic_bytes_per_launch": b, "avg_launch_us": top["avg_us"], "share_of_step": top["share"]}
         # whole-pipeline roofline: compulsory bytes of every stage (SURVEY 8d "pipeline per pair") over the device-timed step
