@@ -34,6 +34,12 @@ class RansacResult(C.Structure):
                 ("n_correspondences", C.c_int64), ("iterations", C.c_int64), ("validated", C.c_int64)]
 
 
+class FgrOption(C.Structure):
+    _fields_ = [("division_factor", C.c_double), ("use_absolute_scale", C.c_int), ("decrease_mu", C.c_int),
+                ("maximum_correspondence_distance", C.c_double), ("iteration_number", C.c_int), ("tuple_scale", C.c_double),
+                ("maximum_tuple_count", C.c_int), ("tuple_test", C.c_int)]
+
+
 class PairParams(C.Structure):
     _fields_ = [("w", C.c_int), ("h", C.c_int), ("fx", C.c_float), ("fy", C.c_float), ("ppx", C.c_float), ("ppy", C.c_float),
                 ("depth_scale", C.c_float), ("voxel_size", C.c_float), ("normals_max_nn", C.c_int), ("normals_radius", C.c_double),
@@ -81,6 +87,7 @@ SIGNATURES = {
     "b3d_compute_fpfh": (_i, [_vp, _vp, _vp, _i64, _i, _d, _vp]),
     "b3d_orient_normals_consistent_tangent_plane": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
     "b3d_match_features": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _vp]),
+    "b3d_fgr_feature_matching": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i, _vp, C.c_uint64, _vp, _vp]),
     "b3d_ransac_correspondence": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _d, _i, _d, _d, _i64, _d, C.c_uint64, _vp]),
     "b3d_statistical_outlier": (_i, [_vp, _vp, _i64, _i, _d, _vp, _vp, _pi64]),
     "b3d_radius_outlier": (_i, [_vp, _vp, _i64, _i, _d, _vp, _vp, _pi64]),

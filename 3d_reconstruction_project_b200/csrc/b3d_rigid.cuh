@@ -1,9 +1,61 @@
-// b3d_rigid.cuh -- small rigid-motion helpers shared by the ICP engine and the global registration: 4x4 identity, symmetric
-// 3x3 Jacobi eigen-decomposition, Eigen::umeyama (no scaling) from means and cross-covariance.
+// b3d_rigid.cuh -- small rigid-motion helpers shared by the ICP engine and the global registration: 4x4 product / identity,
+// TransformVector6dToMatrix4d, 6x6 LDL^T solve, symmetric 3x3 Jacobi eigen-decomposition, Eigen::umeyama (no scaling).
 #pragma once
 
 namespace b3d {
 
+__device__ inline void mat4_mul(const double* A, const double* B, double* C) {
+    double R[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0;
+            for (int k = 0; k < 4; ++k) s += A[4 * i + k] * B[4 * k + j];
+            R[4 * i + j] = s;
+        }
+    for (int i = 0; i < 16; ++i) C[i] = R[i];
+}
+// TransformVector6dToMatrix4d: R = Rz(x2) Ry(x1) Rx(x0), t = x[3..5]
+__device__ inline void vec6_to_mat4(const double* x, double* T) {
+    const double ca = cos(x[0]), sa = sin(x[0]);
+    const double cb = cos(x[1]), sb = sin(x[1]);
+    const double cg = cos(x[2]), sg = sin(x[2]);
+    T[0] = cg * cb; T[1] = cg * sb * sa - sg * ca; T[2] = cg * sb * ca + sg * sa; T[3] = x[3];
+    T[4] = sg * cb; T[5] = sg * sb * sa + cg * ca; T[6] = sg * sb * ca - cg * sa; T[7] = x[4];
+    T[8] = -sb;     T[9] = cb * sa;                T[10] = cb * ca;               T[11] = x[5];
+    T[12] = 0; T[13] = 0; T[14] = 0; T[15] = 1;
+}
+// 6x6 symmetric solve by LDL^T without pivoting; false if a pivot is not positive / finite (identity update)
+__device__ inline bool solve6(const double* A, const double* b, double* x) {
+    double L[36], D[6];
+    for (int i = 0; i < 36; ++i) L[i] = 0;
+    for (int j = 0; j < 6; ++j) {
+        double d = A[6 * j + j];
+        for (int k = 0; k < j; ++k) d -= L[6 * j + k] * L[6 * j + k] * D[k];
+        if (!(d > 0) || !isfinite(d)) return false;
+        D[j] = d;
+        L[6 * j + j] = 1;
+        for (int i = j + 1; i < 6; ++i) {
+            double s = A[6 * i + j];
+            for (int k = 0; k < j; ++k) s -= L[6 * i + k] * L[6 * j + k] * D[k];
+            L[6 * i + j] = s / d;
+        }
+    }
+    double y[6];
+    for (int i = 0; i < 6; ++i) {
+        double s = b[i];
+        for (int k = 0; k < i; ++k) s -= L[6 * i + k] * y[k];
+        y[i] = s;
+    }
+    for (int i = 0; i < 6; ++i) y[i] /= D[i];
+    for (int i = 5; i >= 0; --i) {
+        double s = y[i];
+        for (int k = i + 1; k < 6; ++k) s -= L[6 * k + i] * x[k];
+        x[i] = s;
+    }
+    for (int i = 0; i < 6; ++i)
+        if (!isfinite(x[i])) return false;
+    return true;
+}
 __device__ inline void mat4_identity(double* T) {
     for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.0 : 0.0;
 }

@@ -229,6 +229,26 @@ def ransac_correspondence(src, tgt, corres, max_dist, ransac_n=3, edge_similarit
                 n_corr=int(r.n_correspondences), iterations=int(r.iterations), validated=int(r.validated))
 
 
+def fgr_feature_matching(src, tgt, feat_src, feat_tgt, division_factor=1.4, use_absolute_scale=False, decrease_mu=True,
+                         maximum_correspondence_distance=0.025, iteration_number=64, tuple_scale=0.95, maximum_tuple_count=1000, tuple_test=True,
+                         seed=0, device=0):
+    """registration_fgr_based_on_feature_matching -- test/check6.py:236-240. Features [n, dim]. -> (T source->target, matches used)"""
+    ctx = get_context(device)
+    s, t = ctx.to_device(src, torch.float64), ctx.to_device(tgt, torch.float64)
+    _check_n3(s, "source points")
+    _check_n3(t, "target points")
+    fs, ft = ctx.to_device(feat_src, torch.float64), ctx.to_device(feat_tgt, torch.float64)
+    if fs.dim() != 2 or ft.dim() != 2 or fs.shape[1] != ft.shape[1] or fs.shape[0] != s.shape[0] or ft.shape[0] != t.shape[0]:
+        raise ValueError("features must be [n_points, dim] arrays of the same dimension")
+    opt = N.FgrOption(float(division_factor), int(bool(use_absolute_scale)), int(bool(decrease_mu)), float(maximum_correspondence_distance),
+                      int(iteration_number), float(tuple_scale), int(maximum_tuple_count), int(bool(tuple_test)))
+    T = (C.c_double * 16)()
+    n = C.c_int64(0)
+    N.check(N.lib().b3d_fgr_feature_matching(ctx.handle, ptr(s), s.shape[0], ptr(t), t.shape[0], ptr(fs), ptr(ft), int(fs.shape[1]), C.byref(opt),
+                                             C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), T, C.byref(n)))
+    return np.array(T[:], dtype=np.float64).reshape(4, 4), int(n.value)
+
+
 def _outlier(fn, points, a, b, device, as_tensor):
     ctx = get_context(device)
     p = ctx.to_device(points, torch.float64)

@@ -207,3 +207,26 @@ def registration_ransac_based_on_feature_matching(source, target, source_feature
             corres = corres[keep]
     return registration_ransac_based_on_correspondence(source, target, corres, max_correspondence_distance, estimation_method, ransac_n,
                                                        checkers, criteria, seed)
+
+
+class FastGlobalRegistrationOption:
+    """o3d.pipelines.registration.FastGlobalRegistrationOption (test/check6.py:238-239 sets maximum_correspondence_distance)."""
+
+    def __init__(self, division_factor=1.4, use_absolute_scale=False, decrease_mu=True, maximum_correspondence_distance=0.025,
+                 iteration_number=64, tuple_scale=0.95, maximum_tuple_count=1000, tuple_test=True, seed=None):
+        self.division_factor, self.use_absolute_scale, self.decrease_mu = float(division_factor), bool(use_absolute_scale), bool(decrease_mu)
+        self.maximum_correspondence_distance, self.iteration_number = float(maximum_correspondence_distance), int(iteration_number)
+        self.tuple_scale, self.maximum_tuple_count, self.tuple_test, self.seed = float(tuple_scale), int(maximum_tuple_count), bool(tuple_test), seed
+
+
+def registration_fgr_based_on_feature_matching(source, target, source_feature, target_feature, option=None):
+    """test/check6.py:236-240, check7.py:245, check8.py:244, check81.py:242: Fast Global Registration from FPFH matches."""
+    source, target = as_cloud(source), as_cloud(target)
+    option = option or FastGlobalRegistrationOption()
+    if not source.has_points() or not target.has_points():
+        raise RuntimeError("FastGlobalRegistration: source or target point cloud is empty.")
+    fs, ft = _feature_rows(source_feature), _feature_rows(target_feature)
+    T, _ = ops.fgr_feature_matching(np.asarray(source.points), np.asarray(target.points), fs, ft, option.division_factor, option.use_absolute_scale,
+                                    option.decrease_mu, option.maximum_correspondence_distance, option.iteration_number, option.tuple_scale,
+                                    option.maximum_tuple_count, option.tuple_test, seed=(option.seed or 0), device=source.device)
+    return evaluate_registration(source, target, option.maximum_correspondence_distance, T)

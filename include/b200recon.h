@@ -152,6 +152,23 @@ int b3d_ransac_correspondence(b3d_ctx* ctx, const double* src, int64_t ns, const
                               double max_dist, int ransac_n, double edge_similarity, double checker_distance, int64_t max_iteration,
                               double confidence, uint64_t seed, b3d_ransac_result* result_h);
 
+/* registration_fgr_based_on_feature_matching(source, target, source_fpfh, target_fpfh, FastGlobalRegistrationOption(...)) --
+ * test/check6.py:236-240, check7.py:245-249, check8.py:244-248, check81.py:242-246. Field names and defaults are the library's. */
+typedef struct b3d_fgr_option {
+    double division_factor;                 /* 1.4 */
+    int use_absolute_scale;                 /* 0 */
+    int decrease_mu;                        /* 1 */
+    double maximum_correspondence_distance; /* 0.025 */
+    int iteration_number;                   /* 64 */
+    double tuple_scale;                     /* 0.95 */
+    int maximum_tuple_count;                /* 1000 */
+    int tuple_test;                         /* 1 */
+} b3d_fgr_option;
+/* Features row-major [n, dim]. T_h: host double[16], source -> target (identity when fewer than 10 matches survive);
+ * n_corres_h (optional): matches the optimisation ran on. The tuple test's random triples are a pure function of (seed, trial). */
+int b3d_fgr_feature_matching(b3d_ctx* ctx, const double* src, int64_t ns, const double* tgt, int64_t nt, const double* feat_src,
+                             const double* feat_tgt, int dim, const b3d_fgr_option* opt, uint64_t seed, double* T_h, int64_t* n_corres_h);
+
 /* ---- outlier filters -------------------------------------------------------------------------------------- */
 /* remove_statistical_outlier(nb_neighbors, std_ratio) -- pointcloud_processing.py:35-36, test/mini1.py:175.
  * keep: uint8 [n]; kept_idx: int64 [n] ascending indices (optional); n_kept_h: count. */

@@ -240,6 +240,19 @@ def ransac(src, tgt, corres, dmax, ransac_n=3, edge_similarity=0.0, checker_dist
     return dict(transformation=T.reshape(4, 4), fitness=st[0], inlier_rmse=st[1], n_corr=int(st[2]), iterations=int(st[3]), validated=int(st[4]))
 
 
+def fgr(src, tgt, feat_src, feat_tgt, division_factor=1.4, use_absolute_scale=False, decrease_mu=True, maximum_correspondence_distance=0.025,
+        iteration_number=64, tuple_scale=0.95, maximum_tuple_count=1000, tuple_test=True, seed=0):
+    """registration_fgr_based_on_feature_matching (test/check6.py:236-240). Features [n, dim]. -> (T source->target, matches used)"""
+    src, tgt, fs, ft = _c(src, np.float64), _c(tgt, np.float64), _c(feat_src, np.float64), _c(feat_tgt, np.float64)
+    opt = np.array([division_factor, float(use_absolute_scale), float(decrease_mu), maximum_correspondence_distance, iteration_number, tuple_scale,
+                    maximum_tuple_count, float(tuple_test)], np.float64)
+    T = np.empty(16, np.float64)
+    lib().orc_fgr.restype = C.c_int64
+    n = lib().orc_fgr(_p(src), C.c_int64(len(src)), _p(tgt), C.c_int64(len(tgt)), _p(fs), _p(ft), int(fs.shape[1]), _p(opt),
+                      C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), _p(T))
+    return T.reshape(4, 4), int(n)
+
+
 P2P, P2L, GICP = 0, 1, 2
 
 

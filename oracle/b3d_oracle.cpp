@@ -1494,4 +1494,117 @@ int orc_ransac(const double* src, int64_t ns, const double* tgt, int64_t nt, con
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// registration_fgr_based_on_feature_matching -- test/check6.py:236-240, check7.py:245, check8.py:244.  PARITY UNPINNED
+// (restated from the published algorithm and the upstream routine's structure; the tuple test draws random triples, here
+// counter-based like the RANSAC above). Clouds centred and scaled by the largest centred norm; mutual nearest features;
+// tuple test; 64 Gauss-Newton steps with the scaled Geman-McClure weight and graduated non-convexity; the transform is
+// returned source -> target in original coordinates.
+// opt: division_factor, use_absolute_scale, decrease_mu, max_corr_dist, iterations, tuple_scale, max_tuple_count, tuple_test
+// ---------------------------------------------------------------------------------------------
+int64_t orc_fgr(const double* src, int64_t ns, const double* tgt, int64_t nt, const double* fs, const double* ft, int dim, const double* opt,
+                uint64_t seed, double* T_out) {
+    mat4_identity(T_out);
+    if (ns == 0 || nt == 0) return 0;
+    const double division = opt[0], max_dist = opt[3], tuple_scale = opt[5];
+    const bool absolute = opt[1] != 0, decrease = opt[2] != 0, tuple_test = opt[7] != 0;
+    const int iterations = (int)opt[4];
+    const int64_t max_tuples = (int64_t)opt[6];
+    auto centre = [](const double* x, int64_t n, double* mean) {
+        for (int k = 0; k < 3; ++k) mean[k] = 0;
+        for (int64_t i = 0; i < n; ++i)
+            for (int k = 0; k < 3; ++k) mean[k] += x[3 * i + k];
+        for (int k = 0; k < 3; ++k) mean[k] /= (double)n;
+    };
+    double mean_s[3], mean_t[3], scale = 0.0;
+    centre(src, ns, mean_s);
+    centre(tgt, nt, mean_t);
+    std::vector<double> p((size_t)ns * 3), q((size_t)nt * 3);
+    for (int64_t i = 0; i < ns; ++i) {
+        const double x = src[3 * i] - mean_s[0], y = src[3 * i + 1] - mean_s[1], z = src[3 * i + 2] - mean_s[2];
+        scale = std::max(scale, std::sqrt((x * x + y * y) + z * z));
+    }
+    for (int64_t i = 0; i < nt; ++i) {
+        const double x = tgt[3 * i] - mean_t[0], y = tgt[3 * i + 1] - mean_t[1], z = tgt[3 * i + 2] - mean_t[2];
+        scale = std::max(scale, std::sqrt((x * x + y * y) + z * z));
+    }
+    const double sg = absolute ? 1.0 : scale;
+    for (int64_t i = 0; i < ns; ++i)
+        for (int k = 0; k < 3; ++k) p[3 * i + k] = (src[3 * i + k] - mean_s[k]) / sg;
+    for (int64_t i = 0; i < nt; ++i)
+        for (int k = 0; k < 3; ++k) q[3 * i + k] = (tgt[3 * i + k] - mean_t[k]) / sg;
+    std::vector<int32_t> ij(ns), ji(nt);
+    orc_match_features(fs, ns, ft, nt, dim, ij.data());
+    orc_match_features(ft, nt, fs, ns, dim, ji.data());
+    std::vector<int32_t> corres;
+    for (int64_t i = 0; i < ns; ++i)
+        if (ij[i] >= 0 && ji[ij[i]] == i) { corres.push_back((int32_t)i); corres.push_back(ij[i]); }
+    int64_t nc = (int64_t)corres.size() / 2;
+    if (tuple_test && nc >= 3) {
+        std::vector<int32_t> tup;
+        const int64_t trials = nc * 100;
+        int64_t got = 0;
+        for (int64_t t = 0; t < trials && got < max_tuples; ++t) {
+            int a[3];
+            for (int k = 0; k < 3; ++k) a[k] = (int)ransac_pick(seed ^ 0x5851F42D4C957F2Dull, t, k, nc);
+            double li[3], lj[3];
+            for (int k = 0; k < 3; ++k) {
+                const int u = a[k], v = a[(k + 1) % 3];
+                const int iu = corres[2 * u], iv = corres[2 * v], ju = corres[2 * u + 1], jv = corres[2 * v + 1];
+                const double a0 = p[3 * iu] - p[3 * iv], a1 = p[3 * iu + 1] - p[3 * iv + 1], a2 = p[3 * iu + 2] - p[3 * iv + 2];
+                const double b0 = q[3 * ju] - q[3 * jv], b1 = q[3 * ju + 1] - q[3 * jv + 1], b2 = q[3 * ju + 2] - q[3 * jv + 2];
+                li[k] = std::sqrt((a0 * a0 + a1 * a1) + a2 * a2);
+                lj[k] = std::sqrt((b0 * b0 + b1 * b1) + b2 * b2);
+            }
+            bool ok = true;
+            for (int k = 0; k < 3; ++k)
+                if (!(li[k] * tuple_scale < lj[k] && lj[k] < li[k] / tuple_scale)) ok = false;
+            if (!ok) continue;
+            for (int k = 0; k < 3; ++k) { tup.push_back(corres[2 * a[k]]); tup.push_back(corres[2 * a[k] + 1]); }
+            ++got;
+        }
+        corres.swap(tup);
+        nc = (int64_t)corres.size() / 2;
+    }
+    if (nc < 10) return nc;
+    double par = absolute ? scale : 1.0;
+    double trans[16];
+    mat4_identity(trans);
+    for (int itr = 0; itr < iterations; ++itr) {
+        double a[27] = {0};
+        for (int64_t c = 0; c < nc; ++c) {
+            const int ii = corres[2 * c], jj = corres[2 * c + 1];
+            const double qx = q[3 * jj], qy = q[3 * jj + 1], qz = q[3 * jj + 2];
+            const double r[3] = {p[3 * ii] - qx, p[3 * ii + 1] - qy, p[3 * ii + 2] - qz};
+            const double temp = par / (((r[0] * r[0] + r[1] * r[1]) + r[2] * r[2]) + par);
+            const double w = temp * temp;
+            const double J[3][6] = {{0.0, -qz, qy, -1.0, 0.0, 0.0}, {qz, 0.0, -qx, 0.0, -1.0, 0.0}, {-qy, qx, 0.0, 0.0, 0.0, -1.0}};
+            for (int row = 0; row < 3; ++row) {
+                int t = 0;
+                for (int u = 0; u < 6; ++u)
+                    for (int v = u; v < 6; ++v) a[t++] += J[row][u] * J[row][v] * w;
+                for (int u = 0; u < 6; ++u) a[21 + u] += J[row][u] * r[row] * w;
+            }
+        }
+        double M[36], b[6], x[6], D[16];
+        int t = 0;
+        for (int u = 0; u < 6; ++u)
+            for (int v = u; v < 6; ++v) { M[6 * u + v] = a[t]; M[6 * v + u] = a[t]; ++t; }
+        for (int u = 0; u < 6; ++u) b[u] = -a[21 + u];
+        mat4_identity(D);
+        if (solve6(M, b, x)) vec6_to_mat4(x, D);
+        mat4_mul(D, trans, trans);
+        transform_cloud(D, q.data(), nt, nullptr, nullptr);
+        if (decrease && itr % 4 == 0 && par > max_dist) par /= division;
+    }
+    double t[3];
+    for (int r = 0; r < 3; ++r)
+        t[r] = -(trans[4 * r] * mean_t[0] + trans[4 * r + 1] * mean_t[1] + trans[4 * r + 2] * mean_t[2]) + trans[4 * r + 3] * sg + mean_s[r];
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) T_out[4 * r + c] = trans[4 * c + r];
+        T_out[4 * r + 3] = -(trans[r] * t[0] + trans[4 + r] * t[1] + trans[8 + r] * t[2]);
+    }
+    return nc;
+}
+
 }  // extern "C"

@@ -509,6 +509,28 @@ def test_ransac_correspondence_vs_oracle(ops):
     assert none["n_corr"] == 0 and np.array_equal(none["transformation"], np.eye(4))
 
 
+def test_fgr_feature_matching_vs_oracle(ops):
+    """registration_fgr_based_on_feature_matching (test/check6.py:236-240): the same FPFH features into the CUDA path and the
+    oracle -> same number of tuple matches, transforms equal to rounding; the large known motion is recovered."""
+    tgt, nrm = golden_cloud("output_00094")
+    T = small_rigid(0.35, -0.25, 0.4, (0.3, -0.1, 0.2))
+    rng = np.random.default_rng(9)
+    src, snrm = oracle.transform(np.linalg.inv(T), tgt, normals=nrm)[:2]
+    src = src + rng.normal(0, 1e-4, src.shape)
+    fs, ft = ops.compute_fpfh(src, snrm, 100, 0.05), ops.compute_fpfh(tgt, nrm, 100, 0.05)
+    for kw in (dict(maximum_correspondence_distance=0.015), dict(maximum_correspondence_distance=0.015, tuple_test=False),
+               dict(maximum_correspondence_distance=0.015, use_absolute_scale=True, maximum_tuple_count=300, seed=5)):
+        ref_T, ref_n = oracle.fgr(src, tgt, fs, ft, **kw)
+        out_T, out_n = ops.fgr_feature_matching(src, tgt, fs, ft, **kw)
+        assert out_n == ref_n and out_n >= 10
+        assert np.allclose(out_T, ref_T, atol=1e-8), np.abs(out_T - ref_T).max()
+        assert rot_err(out_T[:3, :3], T[:3, :3]) < 1e-3 and np.linalg.norm(out_T[:3, 3] - T[:3, 3]) < 1e-3
+    # features that match nothing consistently: fewer than 10 tuple matches -> identity, like the library
+    junk_T, junk_n = ops.fgr_feature_matching(src[:200], tgt[:200], rng.normal(size=(200, 33)), rng.normal(size=(200, 33)),
+                                              maximum_correspondence_distance=0.015)
+    assert junk_n < 10 and np.array_equal(junk_T, np.eye(4))
+
+
 def test_fpfh_features(ops):
     """compute_fpfh_feature(Hybrid(0.1, 100)) as in test/mini1.py:244-250 on a fixture cloud with its own normals."""
     pts, nrm = golden_cloud("output_00094")

@@ -154,6 +154,12 @@ def test_global_registration_recipe(b3):
     mutual = reg.registration_ransac_based_on_feature_matching(src, tgt, feats[0], feats[1], True, voxel * 1.5, ransac_n=3,
                                                                criteria=reg.RANSACConvergenceCriteria(100000, 0.999))
     assert mutual.fitness > 0.5
+    # the other initialisation the reference uses (test/check6.py:236-240): Fast Global Registration, then the same refinement
+    fgr = reg.registration_fgr_based_on_feature_matching(src, tgt, feats[0], feats[1],
+                                                         reg.FastGlobalRegistrationOption(maximum_correspondence_distance=voxel * 1.5))
+    assert fgr.fitness > 0.5 and rot_err(fgr.transformation[:3, :3], T[:3, :3]) < 2e-2
+    icp2 = reg.registration_icp(src, tgt, voxel * 0.4, fgr.transformation, reg.TransformationEstimationPointToPlane())
+    assert rot_err(icp2.transformation[:3, :3], T[:3, :3]) < 2e-3 and np.linalg.norm(icp2.transformation[:3, 3] - T[:3, 3]) < 2e-3
 
 
 def test_capture_and_alignment_classes(b3):
