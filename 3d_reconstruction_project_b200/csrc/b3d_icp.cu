@@ -33,7 +33,19 @@ constexpr int kIcpInformation = 3;  // internal kind: G^T G of get_information_m
 #ifndef B3D_ICP_GROUPS
 #define B3D_ICP_GROUPS 384
 #endif
-constexpr int kIcpMaxGroups = B3D_ICP_GROUPS * (128 / kIcpBlock);  // partial-sum groups (blocks) per pair
+constexpr int kIcpMinGroups = B3D_ICP_GROUPS * (128 / kIcpBlock);  // partial-sum groups (blocks) of an ordinary pair
+constexpr int kIcpMaxGroups = 4096 * (128 / kIcpBlock);            // ... of a very large one
+// Groups of a pair with `chunks` warp chunks: one chunk per warp while the pair is tiny, kIcpMinGroups blocks for ordinary
+// frame pairs, about eight chunks per warp beyond that (a 1e8-point cloud must still fill the machine on its own).
+__host__ __device__ inline int icp_groups(int chunks) {
+    const int wpb = kIcpBlock / 32;
+    const int one_each = (chunks + wpb - 1) / wpb;
+    int g = (chunks + 8 * wpb - 1) / (8 * wpb);
+    const int floor_g = one_each < kIcpMinGroups ? one_each : kIcpMinGroups;
+    g = g < floor_g ? floor_g : g;
+    g = g > kIcpMaxGroups ? kIcpMaxGroups : g;
+    return g < 1 ? 1 : g;
+}
 constexpr double kIcpReach2 = 1.25;   // search radius of a lane that found nothing last time, in units of d_max (see the pass kernel)
 
 // ---- small dense helpers (device) ----------------------------------------------------------------------------------
@@ -241,7 +253,7 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
     const bool affine = sT[12] == 0.0 && sT[13] == 0.0 && sT[14] == 0.0 && sT[15] == 1.0;
     // this pair's range of warp chunks (chunks never straddle pairs) and its number of partial-sum groups: a function of
     // the pair's own chunk count only, so a pair's result does not depend on what else is in the batch
-    const int groups = max(1, min((c1 - c0 + kIcpBlock / 32 - 1) / (kIcpBlock / 32), kIcpMaxGroups));
+    const int groups = icp_groups(c1 - c0);
     if ((int)blockIdx.x >= groups) return;
     // the next chunk's query is fetched while the current one is processed (two dependent loads off the critical path)
     const int32_t c_step = groups * (kIcpBlock / 32);
@@ -675,7 +687,7 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
         }
     }
     // partial-sum groups per pair depend only on that pair's own chunk count (results do not depend on the batch)
-    w->blocks = std::max(1, std::min((w->chunks.most + kIcpBlock / 32 - 1) / (kIcpBlock / 32), kIcpMaxGroups));
+    w->blocks = icp_groups(w->chunks.most);
     B3D_TRY(w->partial.alloc(ctx, (size_t)P * w->blocks * kIcpSums));
     if (pb.kind == B3D_ICP_POINT_TO_PLANE) {
         B3D_TRY(w->tgt_nrm_sorted.alloc(ctx, (size_t)nt * 3));
