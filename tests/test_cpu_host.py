@@ -131,6 +131,42 @@ def test_replay_pipeline_and_realsense_wrapper(built):
         b3.RealSensePipeline().start_pipeline()
 
 
+def test_registration_option_classes(built):
+    """Host mirror of o3d.pipelines.registration's option objects on the global-registration row (test/mini1.py:269-281,
+    test/check6.py:236-240): names, defaults, layout conversion, argument screening -- no device needed."""
+    import b200recon
+    from b200recon import registration as reg
+    o = reg.FastGlobalRegistrationOption()
+    assert (o.division_factor, o.use_absolute_scale, o.decrease_mu, o.maximum_correspondence_distance, o.iteration_number, o.tuple_scale,
+            o.maximum_tuple_count, o.tuple_test) == (1.4, False, True, 0.025, 64, 0.95, 1000, True)
+    c = reg.RANSACConvergenceCriteria()
+    assert (c.max_iteration, c.confidence) == (100000, 0.999)
+    assert reg._checker_params([reg.CorrespondenceCheckerBasedOnEdgeLength(0.9), reg.CorrespondenceCheckerBasedOnDistance(0.015)]) == (0.9, 0.015)
+    assert reg._checker_params(None) == (0.0, 0.0)
+    with pytest.raises(RuntimeError, match="only CorrespondenceChecker"):
+        reg._checker_params([object()])
+    f = reg.Feature(np.arange(66, dtype=np.float64).reshape(33, 2))  # Open3D layout: [dimension, N]
+    rows = reg._feature_rows(f)
+    assert f.dimension() == 33 and f.num() == 2 and rows.shape == (2, 33) and rows.flags["C_CONTIGUOUS"] and rows[1, 0] == 1.0
+    # degenerate requests return the library's empty result before anything touches the device
+    pc = b200recon.PointCloud(np.zeros((5, 3)))
+    r = reg.registration_ransac_based_on_feature_matching(pc, pc, f, f, False, 0.01, ransac_n=2)
+    assert r.fitness == 0.0 and np.array_equal(r.transformation, np.eye(4)) and len(r.correspondence_set) == 0
+    # the open3d stand-in exposes the same names under pipelines.registration
+    import importlib, sys
+    shim_dir = os.path.join(os.path.dirname(b200recon.__file__), "shims")
+    sys.path.insert(0, shim_dir)
+    try:
+        o3d = importlib.import_module("open3d")
+        for name in ("registration_icp", "registration_generalized_icp", "registration_ransac_based_on_feature_matching",
+                     "registration_fgr_based_on_feature_matching", "FastGlobalRegistrationOption", "compute_fpfh_feature",
+                     "get_information_matrix_from_point_clouds", "CorrespondenceCheckerBasedOnEdgeLength", "RANSACConvergenceCriteria"):
+            assert hasattr(o3d.pipelines.registration, name), name
+    finally:
+        sys.path.remove(shim_dir)
+        sys.modules.pop("open3d", None)
+
+
 def test_partitioning(built):
     from b200recon import distributed as dist
     for n, w in ((512, 8), (10, 4), (3, 8), (0, 2)):
