@@ -440,7 +440,8 @@ extern "C" int b3d_ransac_correspondence(b3d_ctx* ctx, const double* src, int64_
     int rmax = 1;
     B3D_TRY(build_search_grid<double>(ctx, tgt, tseg, 8, max_dist, &tgrid, &rmax));
     B3D_TRY(build_search_grid<double>(ctx, src, sseg, 8, max_dist, &sgrid, nullptr));
-    const int64_t R = std::max<int64_t>(256, std::min<int64_t>(65536, ((int64_t)1 << 26) / std::max<int64_t>(ns, 1)));
+    // hypotheses per round: bounded by the validation work (survivors x source points) and by gridDim.y of the validation launch
+    const int64_t R = std::max<int64_t>(256, std::min<int64_t>(32768, ((int64_t)1 << 26) / std::max<int64_t>(ns, 1)));
     DevBuf<int> n_pass;
     DevBuf<long long> pass_itr;
     DevBuf<double> pass_T;
