@@ -531,6 +531,38 @@ def test_fgr_feature_matching_vs_oracle(ops):
     assert junk_n < 10 and np.array_equal(junk_T, np.eye(4))
 
 
+def test_orient_normals_fuzz(ops):
+    """Small adversarial clouds for the spanning-tree machinery of orient_normals_consistent_tangent_plane: several far-apart
+    clusters (the Euclidean tree has to bridge more than one gap, components of equal size), duplicated points (zero-length
+    edges, ties broken by the end points' indices), a lattice (exact distance ties everywhere), tiny clouds (k > n)."""
+    rng = np.random.default_rng(77)
+    for case in range(24):
+        kind = case % 4
+        n = int(rng.choice([4, 5, 9, 33, 100, 257, 600]))
+        if kind == 0:  # clusters far apart, two of them of equal size
+            m = max(n // 4, 1)
+            pts = np.concatenate([rng.normal(c, 0.02, (m, 3)) for c in ((0, 0, 0), (1.0, 0.2, 0.1), (-0.7, 0.9, 0.3), (0.1, -1.2, 2.0))])
+        elif kind == 1:  # duplicates
+            pts = rng.normal(0, 0.1, (n, 3))
+            pts[rng.random(n) < 0.3] = pts[0]
+        elif kind == 2:  # lattice
+            s = int(np.ceil(n ** (1 / 3)))
+            pts = (np.stack(np.meshgrid(np.arange(s), np.arange(s), np.arange(s), indexing="ij"), -1).reshape(-1, 3)[:max(n, 4)] * 0.01).astype(np.float64)
+        else:  # a noisy sphere
+            pts = rng.normal(size=(n, 3))
+            pts = pts / np.linalg.norm(pts, axis=1, keepdims=True) * (1 + rng.normal(0, 0.01, (n, 1)))
+        pts = np.ascontiguousarray(pts + rng.choice([0.0, 5.0]))
+        nrm = rng.normal(size=pts.shape)
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        if kind == 3:
+            nrm = pts / np.linalg.norm(pts, axis=1, keepdims=True) * np.where(rng.random(len(pts)) < 0.5, -1.0, 1.0)[:, None]
+        k = int(rng.choice([10, 16, 100]))
+        ref, ref_flip = oracle.orient_normals(pts, nrm, k)
+        out, flip = ops.orient_normals_consistent_tangent_plane(pts, nrm, k)
+        assert np.array_equal(flip, ref_flip), (case, kind, len(pts), k, int((flip != ref_flip).sum()))
+        assert np.array_equal(out, ref)
+
+
 def test_fpfh_features(ops):
     """compute_fpfh_feature(Hybrid(0.1, 100)) as in test/mini1.py:244-250 on a fixture cloud with its own normals."""
     pts, nrm = golden_cloud("output_00094")
