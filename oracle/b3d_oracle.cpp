@@ -21,6 +21,13 @@
 //   z16 (librealsense) deprojection, tensor voxel, tensor normals, radius outlier, ICP/GICP:
 //                                                PARITY UNPINNED (nothing in the reference stores their
 //                                                outputs); known-answer tests only.
+//   information matrix, FPFH, normal orientation (consistent tangent plane), feature matching,
+//   RANSAC on correspondences, Fast Global Registration ("next" rows):
+//                                                PARITY UNPINNED; held against independent references
+//                                                in tests/test_oracle_next_rows.py (analytic orientations,
+//                                                numpy brute force, known rigid motions). The randomised
+//                                                routines use counter-based picks instead of upstream's
+//                                                system-seeded generator (no two upstream runs agree).
 //
 // Build: g++ -O2 -std=c++17 -fopenmp -ffp-contract=off -shared -fPIC (see oracle/Makefile).
 // -ffp-contract=off matters: voxel keys, squared distances and sums are compared bit-exactly.
