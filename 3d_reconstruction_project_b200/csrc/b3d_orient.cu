@@ -142,21 +142,29 @@ __device__ __forceinline__ unsigned long long edge_id(int a, int b) {
 
 // Sweep 1 / 2 over a list with `deg` entries per row (row r = vertex row_vertex[r] or r itself): per component, the
 // smallest crossing weight (sweep 1), then the smallest edge id among the entries of that weight (sweep 2).
+// Components only ever merge, so an entry whose two ends share a component is dead for good: sweep 1 overwrites it with -1
+// (no component lookup for it in later rounds) and marks rows without a live entry, which later sweeps skip altogether.
 template <int SWEEP>
-__global__ void boruvka_sweep_kernel(const int32_t* __restrict__ row_vertex, const int32_t* __restrict__ nbr, const double* __restrict__ w, int64_t rows,
+__global__ void boruvka_sweep_kernel(const int32_t* __restrict__ row_vertex, int32_t* __restrict__ nbr, const double* __restrict__ w, int64_t rows,
                                      int deg, const int32_t* __restrict__ comp, unsigned long long* __restrict__ best_w,
-                                     unsigned long long* __restrict__ best_e) {
+                                     unsigned long long* __restrict__ best_e, uint8_t* __restrict__ row_alive) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
+    if (row_alive != nullptr && !row_alive[r]) return;
     const int v = row_vertex ? row_vertex[r] : (int)r;
     const int cv = comp[v];
     unsigned long long my_w = kNoEdge, my_e = kNoEdge;
     const unsigned long long cur_v = SWEEP == 2 ? best_w[cv] : 0ull;
+    bool any = false;
     for (int j = 0; j < deg; ++j) {
         const int u = nbr[r * deg + j];
         if (u < 0) continue;
         const int cu = comp[u];
-        if (cu == cv) continue;
+        if (cu == cv) {
+            if (SWEEP == 1) nbr[r * deg + j] = -1;
+            continue;
+        }
+        any = true;
         const unsigned long long wb = weight_bits(w[r * deg + j]);
         if (SWEEP == 1) {
             my_w = wb < my_w ? wb : my_w;
@@ -168,6 +176,7 @@ __global__ void boruvka_sweep_kernel(const int32_t* __restrict__ row_vertex, con
         }
     }
     if (SWEEP == 1) {
+        if (row_alive != nullptr && !any) row_alive[r] = 0;
         if (my_w != kNoEdge && my_w < best_w[cv]) atomicMin(&best_w[cv], my_w);
     } else {
         if (my_e != kNoEdge && my_e < best_e[cv]) atomicMin(&best_e[cv], my_e);
@@ -474,10 +483,11 @@ int forest_init(b3d_ctx* ctx, Forest* f, int64_t n, bool signs) {
 
 struct EdgeList {  // rows x deg neighbour entries with weights; row r belongs to vertex r (row_vertex == NULL) or row_vertex[r]
     const int32_t* row_vertex;
-    const int32_t* nbr;
+    int32_t* nbr;  // entries inside one component are overwritten with -1 as the rounds go
     const double* w;
     int64_t rows;
     int deg;
+    uint8_t* row_alive;  // optional [rows], 1 = the row still has a live entry
 };
 
 // One Boruvka round over the given lists. hooks_out: number of components that merged into another one.
@@ -487,12 +497,12 @@ int boruvka_round(b3d_ctx* ctx, Forest* f, const EdgeList* lists, int n_lists, c
     for (int l = 0; l < n_lists; ++l) {
         const EdgeList& L = lists[l];
         if (L.rows == 0) continue;
-        B3D_LAUNCH(ctx, boruvka_sweep_kernel<1>, (int)((L.rows + 127) / 128), 128, 0, L.row_vertex, L.nbr, L.w, L.rows, L.deg, f->comp.p, f->best_w.p, f->best_e.p);
+        B3D_LAUNCH(ctx, boruvka_sweep_kernel<1>, (int)((L.rows + 127) / 128), 128, 0, L.row_vertex, L.nbr, L.w, L.rows, L.deg, f->comp.p, f->best_w.p, f->best_e.p, L.row_alive);
     }
     for (int l = 0; l < n_lists; ++l) {
         const EdgeList& L = lists[l];
         if (L.rows == 0) continue;
-        B3D_LAUNCH(ctx, boruvka_sweep_kernel<2>, (int)((L.rows + 127) / 128), 128, 0, L.row_vertex, L.nbr, L.w, L.rows, L.deg, f->comp.p, f->best_w.p, f->best_e.p);
+        B3D_LAUNCH(ctx, boruvka_sweep_kernel<2>, (int)((L.rows + 127) / 128), 128, 0, L.row_vertex, L.nbr, L.w, L.rows, L.deg, f->comp.p, f->best_w.p, f->best_e.p, L.row_alive);
     }
     B3D_LAUNCH(ctx, boruvka_hook_kernel, vb, 256, 0, n, f->comp.p, f->best_e.p, nrm, f->sgn.p, f->parent.p, f->psign.p);
     B3D_CUDA(cudaMemsetAsync(f->counters.p + 1, 0, sizeof(int), ctx->stream));
@@ -540,7 +550,14 @@ extern "C" int b3d_orient_normals_consistent_tangent_plane(b3d_ctx* ctx, const d
     {
         Forest f;
         B3D_TRY(forest_init(ctx, &f, n, false));
-        EdgeList knn{nullptr, nb.p, nw.p, n, kk};
+        // the Euclidean rounds kill entries of a private copy of the lists; the Riemannian stage below needs them all again
+        DevBuf<int32_t> nb1;
+        DevBuf<uint8_t> alive1;
+        B3D_TRY(nb1.alloc(ctx, (size_t)n * kk));
+        B3D_TRY(alive1.alloc(ctx, (size_t)n));
+        B3D_CUDA(cudaMemcpyAsync(nb1.p, nb.p, (size_t)n * kk * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        B3D_CUDA(cudaMemsetAsync(alive1.p, 1, (size_t)n, ctx->stream));
+        EdgeList knn{nullptr, nb1.p, nw.p, n, kk, alive1.p};
         int hooks = 1;
         while (f.edges < n - 1 && hooks > 0) B3D_TRY(boruvka_round(ctx, &f, &knn, 1, nullptr, tree_a.p, tree_b.p, &hooks));
         if (f.edges < n - 1) {
@@ -570,7 +587,7 @@ extern "C" int b3d_orient_normals_consistent_tangent_plane(b3d_ctx* ctx, const d
                 B3D_LAUNCH(ctx, foreign_bound_kernel, (int)((n + 127) / 128), 128, 0, grid.view(), stride, f.comp.p, largest.p, ub.p);
                 B3D_LAUNCH(ctx, tile_info_kernel, n_tiles, kTile, 0, grid.view(), f.comp.p, tile_box.p, tile_comp.p);
                 B3D_LAUNCH(ctx, foreign_nearest_kernel, n_tiles, kTile, 0, grid.view(), f.comp.p, largest.p, ub.p, tile_box.p, tile_comp.p, n_tiles, fnb.p, fd.p);
-                EdgeList bridge{nullptr, fnb.p, fd.p, n, 1};
+                EdgeList bridge{nullptr, fnb.p, fd.p, n, 1, nullptr};
                 B3D_TRY(boruvka_round(ctx, &f, &bridge, 1, nullptr, tree_a.p, tree_b.p, &hooks));
             }
         }
@@ -584,7 +601,10 @@ extern "C" int b3d_orient_normals_consistent_tangent_plane(b3d_ctx* ctx, const d
     Forest f;
     B3D_TRY(forest_init(ctx, &f, n, true));
     {
-        EdgeList lists[2] = {{nullptr, nb.p, nw.p, n, kk}, {tree_a.p, tree_b.p, tw.p, n - 1, 1}};
+        DevBuf<uint8_t> alive2;
+        B3D_TRY(alive2.alloc(ctx, (size_t)n));
+        B3D_CUDA(cudaMemsetAsync(alive2.p, 1, (size_t)n, ctx->stream));
+        EdgeList lists[2] = {{nullptr, nb.p, nw.p, n, kk, alive2.p}, {tree_a.p, tree_b.p, tw.p, n - 1, 1, nullptr}};
         int hooks = 1;
         while (f.edges < n - 1 && hooks > 0) B3D_TRY(boruvka_round(ctx, &f, lists, 2, normals, nullptr, nullptr, &hooks));
     }
