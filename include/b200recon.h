@@ -120,7 +120,8 @@ int b3d_estimate_normals_tensor(b3d_ctx* ctx, const float* xyz, int64_t n, int m
 /* GICP covariances from normals, C = R diag(eps,1,1) R^T -- inside registration_generalized_icp, test/GICP1.py:99-102 */
 int b3d_covariances_from_normals(b3d_ctx* ctx, const double* normals, int64_t n, double eps, double* cov);
 
-/* PointCloud.orient_normals_consistent_tangent_plane(k) -- normal_estimation.py:21 (k = 100): Riemannian graph (Euclidean
+/* PointCloud.orient_normals_consistent_tangent_plane(k) -- normal_estimation.py:21, visualizer.py:68, test/check2.py:253,
+ * test/GICP1.py:200 (always k = 100): Riemannian graph (Euclidean
  * minimum spanning tree + k nearest neighbours, weight 1 - |n_i . n_j|), its minimum spanning tree, signs propagated from the
  * first point of largest z (turned towards +z). normals are flipped IN PLACE; flipped (optional, uint8 [n]) gets 1 where a
  * normal was negated (so a float32 copy of the normals can follow). k <= 128; fewer than 4 points is an error like upstream. */
