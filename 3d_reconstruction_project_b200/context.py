@@ -46,7 +46,7 @@ class Context:
         N.check(N.lib().b3d_ctx_profile(self.handle, int(bool(enable))))
 
     def profile_report(self):
-        """{kernel name: (launches, total_ms)} since profiling was enabled; clears the records."""
+        """{kernel name: (launches, total_ms, declared bytes)} since profiling was enabled; clears the records."""
         need = N.lib().b3d_ctx_profile_report(self.handle, None, 0)
         if need < 0:
             raise RuntimeError("profile report failed")
@@ -54,8 +54,8 @@ class Context:
         N.lib().b3d_ctx_profile_report(self.handle, buf, len(buf))
         out = {}
         for line in buf.value.decode().splitlines():
-            name, n, ms = line.split("\t")
-            out[name] = (int(n), float(ms))
+            f = line.split("\t")
+            out[f[0]] = (int(f[1]), float(f[2]), int(f[3]) if len(f) > 3 else 0)
         return out
 
     # ---- torch-backed buffers ----------------------------------------------------------------------------------
@@ -89,9 +89,12 @@ def get_context(device=0):
     pool = getattr(_tls, "pool", None)
     if pool is None:
         pool = _tls.pool = {}
-    ctx = pool.get(d)
+    # one context per (device, current torch stream): a caller inside `with torch.cuda.stream(s)` gets a context whose
+    # kernels run on s, like the torch allocations and copies around the call
+    key = (d, int(torch.cuda.current_stream(d).cuda_stream))
+    ctx = pool.get(key)
     if ctx is None or ctx.handle is None:
-        ctx = pool[d] = Context(d)
+        ctx = pool[key] = Context(d)
     return ctx
 
 

@@ -40,7 +40,7 @@ __device__ __forceinline__ unsigned long long hilbert3(uint32_t x, uint32_t y, u
 // spatially compact, so the 32 queries of a warp fit a small box (and stay compact under rigid updates).
 __global__ void __launch_bounds__(256) chunk_key_kernel(const double* __restrict__ pts, const int32_t* __restrict__ off, const double* __restrict__ transforms,
                                                         int transform_stride, const Lattice* __restrict__ lat, int shift, int hilbert_bits, int sub,
-                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ order) {
+                                                        uint64_t* __restrict__ keys) {
     const int cloud = blockIdx.y;
     const Lattice L = lat[cloud];
     double T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
@@ -63,7 +63,6 @@ __global__ void __launch_bounds__(256) chunk_key_kernel(const double* __restrict
         const unsigned long long m = hilbert_bits > 0 ? hilbert3((uint32_t)ix, (uint32_t)iy, (uint32_t)iz, hilbert_bits)
                                                       : (morton_spread3(ix) << 2) | (morton_spread3(iy) << 1) | morton_spread3(iz);
         keys[i] = ((unsigned long long)cloud << shift) | (m & ((1ull << shift) - 1ull));
-        order[i] = (uint32_t)i;
     }
 }
 
@@ -168,20 +167,16 @@ int build_query_chunks(b3d_ctx* ctx, const double* pts, const int32_t* off_d, co
     while (3 * axis_bits + bbits > 63) --axis_bits;
     const int shift = 3 * axis_bits;
     DevBuf<uint64_t> k_in, k_out;
-    DevBuf<uint32_t> o_in, o_out;
+    DevBuf<uint32_t> o_out;
     B3D_TRY(k_in.alloc(ctx, n));
     B3D_TRY(k_out.alloc(ctx, n));
-    B3D_TRY(o_in.alloc(ctx, n));
     B3D_TRY(o_out.alloc(ctx, n));
     const int kb = (int)std::min<int64_t>((longest + 255) / 256, std::max(1, ctx->sm_count * 16 / B));
     B3D_LAUNCH(ctx, chunk_key_kernel, dim3(std::max(1, kb), B), 256, 0, pts, off_d, transforms, transform_stride, lattices.lat.p, shift,
-               getenv("B3D_CHUNK_MORTON") ? 0 : axis_bits, sub, k_in.p, o_in.p);
-    bool in_a = true;
-    B3D_TRY(radix_sort_pairs(ctx, k_in.p, o_in.p, k_out.p, o_out.p, n, shift + bbits, &in_a));
-    if (in_a) {
-        std::swap(k_in, k_out);
-        std::swap(o_in, o_out);
-    }
+               getenv("B3D_CHUNK_MORTON") ? 0 : axis_bits, sub, k_in.p);
+    (void)bbits;
+    B3D_TRY(radix_sort_keys(ctx, k_in.p, n, shift, off_h, off_d, k_out.p, o_out.p));
+    k_in.release();
     B3D_LAUNCH(ctx, chunk_gather_kernel, ctx->grid_for(n, 256, 1, 8), 256, 0, pts, o_out.p, n, out->pts.p);
     DevBuf<int64_t> n_chunks_d;
     B3D_TRY(n_chunks_d.alloc(ctx, 1));

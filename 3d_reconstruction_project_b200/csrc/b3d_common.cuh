@@ -67,11 +67,16 @@ struct b3d_ctx {
     struct ProfRec {
         const char* name;
         cudaEvent_t e0, e1;
+        int64_t bytes;  // memory traffic the launch site declared for this launch (0: none declared)
     };
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> prof_pool;
     void prof_begin(const char* name);
     void prof_end();
+    // declares the bytes the most recent launch reads + writes (profile report column 4); no-op unless profiling
+    void prof_bytes(int64_t bytes) {
+        if (profiling && !prof.empty()) prof.back().bytes = bytes;
+    }
 
     // Scratch memory: a per-context caching allocator over cudaMalloc. The pipelines allocate the same sequence of sizes
     // every step; cudaMallocAsync's pool occasionally re-maps physical memory for large blocks (measured: 20-480 ms stalls,
@@ -313,6 +318,23 @@ __host__ __device__ __forceinline__ unsigned long long morton_spread3(unsigned l
     return v;
 }
 
+__host__ __device__ __forceinline__ unsigned long long morton_compact3(unsigned long long v) {  // every third bit -> 21 bits
+    v &= 0x1249249249249249ull;
+    v = (v | (v >> 2)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v >> 4)) & 0x100f00f00f00f00full;
+    v = (v | (v >> 8)) & 0x1f0000ff0000ffull;
+    v = (v | (v >> 16)) & 0x1f00000000ffffull;
+    v = (v | (v >> 32)) & 0x1fffffull;
+    return v;
+}
+
+// Key of a cell in the hashed cell table of a search grid: cloud and cell coordinates packed side by side (shift / 3 bits
+// per axis -- search grids sort by Morton keys of exactly that width). Cheaper to form per probe than the Morton key.
+__host__ __device__ __forceinline__ unsigned long long grid_slot_key(int shift, int cloud, long long x, long long y, long long z) {
+    const int ab = shift / 3;
+    return ((unsigned long long)cloud << shift) | ((unsigned long long)x << (2 * ab)) | ((unsigned long long)y << ab) | (unsigned long long)z;
+}
+
 // key of the cell (x, y, z) (coordinates already biased into [0, n)) inside its cloud
 __host__ __device__ __forceinline__ unsigned long long lattice_key(const Lattice& L, long long x, long long y, long long z) {
     if (L.morton) return (morton_spread3((unsigned long long)x) << 2) | (morton_spread3((unsigned long long)y) << 1) | morton_spread3((unsigned long long)z);
@@ -359,6 +381,11 @@ struct SpatialSort {
 
 // hand-written stable LSD radix sort of (key, value) pairs by key bits [0, end_bit) (b3d_radix.cu); ping-pong buffers
 int radix_sort_pairs(b3d_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, int64_t n, int end_bit, bool* result_in_a);
+// Segmented stable sort of composite keys (segment << low_bits | low key) by their low bits, one segment per cloud
+// (packed key + position words, one look-back scatter kernel per 8-bit pass; b3d_radix.cu). order_out[j] = input position
+// of the j-th sorted key (ascending among equal keys).
+int radix_sort_keys(b3d_ctx* ctx, const uint64_t* keys_in, int64_t n, int low_bits, const std::vector<int32_t>& seg_off_h, const int32_t* seg_off_d,
+                    uint64_t* keys_out, uint32_t* order_out);
 
 // bounds_h: [B][6] (min xyz, max xyz) per cloud; clouds with no points get +-DBL_MAX
 template <typename T>
@@ -400,16 +427,18 @@ struct GridView {
     const Lattice* lat;  // per cloud
     int shift;
     int32_t n;
+    const int4* rec;     // float64 grids: sorted like pts, fixed-point coordinates in units of cell / 2^s + sorted position (b3d_stage2.cuh)
 };
 
 template <typename T>
 struct Grid {
     DevBuf<typename PointT<T>::vec4> pts;
+    DevBuf<int4> rec;    // float64 grids only
     DevBuf<HashSlot> slots;
     uint32_t mask = 0;
     SpatialSort sort;
     double cell = 0;
-    GridView<T> view() const { return GridView<T>{pts.p, slots.p, mask, sort.lat.p, sort.shift, (int32_t)sort.n}; }
+    GridView<T> view() const { return GridView<T>{pts.p, slots.p, mask, sort.lat.p, sort.shift, (int32_t)sort.n, rec.p}; }
 };
 
 template <typename T>

@@ -147,7 +147,7 @@ int b3d_ctx::upload(void* dst_d, const void* src_h, size_t bytes) {
 }
 
 void b3d_ctx::prof_begin(const char* name) {
-    ProfRec r{name, nullptr, nullptr};
+    ProfRec r{name, nullptr, nullptr, 0};
     for (cudaEvent_t* e : {&r.e0, &r.e1}) {
         if (!prof_pool.empty()) {
             *e = prof_pool.back();
@@ -189,6 +189,7 @@ int64_t b3d_ctx_profile_report(b3d_ctx* ctx, char* buf, int64_t cap) {
         std::string name;
         int64_t n;
         double ms;
+        int64_t bytes;
     };
     std::vector<Agg> agg;
     for (auto& r : ctx->prof) {
@@ -204,10 +205,11 @@ int64_t b3d_ctx_profile_report(b3d_ctx* ctx, char* buf, int64_t cap) {
             if (a.name == nm) {
                 a.n += 1;
                 a.ms += ms;
+                a.bytes += r.bytes;
                 found = true;
                 break;
             }
-        if (!found) agg.push_back({nm, 1, (double)ms});
+        if (!found) agg.push_back({nm, 1, (double)ms, r.bytes});
     }
     for (size_t i = 0; i < agg.size(); ++i)
         for (size_t j = i + 1; j < agg.size(); ++j)
@@ -215,7 +217,7 @@ int64_t b3d_ctx_profile_report(b3d_ctx* ctx, char* buf, int64_t cap) {
     std::string out;
     char line[256];
     for (auto& a : agg) {
-        snprintf(line, sizeof(line), "%s\t%lld\t%.6f\n", a.name.c_str(), (long long)a.n, a.ms);
+        snprintf(line, sizeof(line), "%s\t%lld\t%.6f\t%lld\n", a.name.c_str(), (long long)a.n, a.ms, (long long)a.bytes);
         out += line;
     }
     if (buf && cap > 0) {

@@ -9,6 +9,7 @@
 #include "b3d_search.cuh"
 #include "b3d_scan.cuh"
 #include "b3d_stage.cuh"
+#include "b3d_stage2.cuh"
 
 #include <cmath>
 #include <cstdlib>
@@ -582,6 +583,469 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
     }
 }
 
+// ======================================================================================================================
+// Round-2 pass kernel. Same algorithm and the same results as icp_pass_kernel above (the float scan is a pre-filter; winners
+// and near-ties are decided in float64 with the library's (d2, index) rule), different machinery:
+//  * staging through b3d_stage2.cuh: integer fixed-point geometry (boxes, cells and the box filter are shifts, subtractions and
+//    compares; the box of a chunk is six REDUX instructions), cp.async.bulk copies of whole grid cells into shared memory, one
+//    mbarrier wait per batch, filter and in-place compaction out of shared memory;
+//  * the scan takes four candidates per step and keeps (best, runner-up, winning group) with 3 ALU operations per
+//    candidate instead of 5; the winner inside the group is resolved once after the loop;
+//  * a box that does not fit the buffer is scanned in several batches instead of falling back to the per-lane walk;
+//  * warps are independent to the end: every warp hands its 29 sums to the block through shared memory and leaves; the last
+//    warp of a block to arrive adds the block's rows, the last block of a pair adds the pair's rows (fixed orders, no atomics
+//    on the data path, no block barrier after the start-up);
+//  * everything that runs rarely (per-lane walk, float64 tie resolution, the final reduction, the peer exchange, the solve) is
+//    out of line: the round-2 kernel first measured at 187 KB of code and spent a third of its issue slots waiting for
+//    instructions (profiles/r02a_ncu_icp_pass2_p16_digest.txt).
+#ifndef B3D_ICP2_CAP
+#define B3D_ICP2_CAP 380
+#endif
+#ifndef B3D_ICP2_MIN_BLOCKS
+#define B3D_ICP2_MIN_BLOCKS 6
+#endif
+constexpr int kIcp2Cap = B3D_ICP2_CAP;  // raw cell records per batch (+4 scan padding = 384 x 16 bytes)
+using Icp2Smem = StageSmem<kIcp2Cap>;
+static_assert(sizeof(float4) * (kIcp2Cap + 4) >= sizeof(double) * 32 * kIcpRow, "the row buffer of the reduction aliases the candidate buffer");
+
+__device__ __forceinline__ float dot_t(const float4& c, float fx, float fy, float fz) { return fmaf(fx, c.x, fmaf(fy, c.y, fmaf(fz, c.z, c.w))); }
+
+// cold: exact per-lane walk of the grid (box too large to stage, or a near-tie in a box that took several batches)
+__device__ __noinline__ int icp2_walk(const GridView<double>& g, int pair, double px, double py, double pz, double r2, int rmax, double* d2, int* idx,
+                                      double4* q) {
+    const int pos = nn_within_query<double>(g, pair, px, py, pz, r2, rmax, d2, idx);
+    if (pos >= 0) *q = ld_point(g.pts + pos);
+    return pos;
+}
+
+// cold: more than one staged candidate inside the rounding band of the best -- decide in float64 with the (d2, index) rule
+__device__ __noinline__ int icp2_resolve_ties(const double4* __restrict__ pts, const float4* __restrict__ buf, const int* __restrict__ posb, int kept,
+                                              float fx, float fy, float fz, float lim_t, double px, double py, double pz, int wpos, double* d2, int* idx,
+                                              double4* q) {
+    int pos = wpos;
+    for (int i = 0; i < kept; ++i) {
+        if (dot_t(buf[i], fx, fy, fz) <= lim_t) {
+            const int p2 = posb[i];
+            if (p2 == wpos) continue;
+            const double4 q2 = ld_point(pts + p2);
+            const double e2 = dist2<double>(px - q2.x, py - q2.y, pz - q2.z);
+            const int i2 = point_index(q2);
+            if (e2 < *d2 || (e2 == *d2 && i2 < *idx)) { *d2 = e2; *idx = i2; pos = p2; *q = q2; }
+        }
+    }
+    return pos;
+}
+
+// cold: the last warp of the last block of a pair -- the pair's rows in a fixed order (lane j sums column j), the optional
+// all-reduce over peer memory, and the solve / update of the loop state
+__device__ __noinline__ void icp2_finish_pair(const IcpKernelArgs& A, int pair, int groups, int ns_local) {
+    const int lane = threadIdx.x & 31;
+    IcpPairState* st = A.state + pair;
+    const double* base = A.partial + (int64_t)pair * gridDim.x * kIcpSums;
+    double total = 0.0;
+    if (lane < kIcpSums) {
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        int b = 0;
+        for (; b + 16 <= groups; b += 16) {
+            double t[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) t[k] = __ldcg(base + (int64_t)(b + k) * kIcpSums + lane);
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) { v0 += t[k]; v1 += t[k + 1]; v2 += t[k + 2]; v3 += t[k + 3]; }
+        }
+        for (; b < groups; ++b) {
+            const double t = __ldcg(base + (int64_t)b * kIcpSums + lane);
+            const int r = b & 3;
+            if (r == 0) v0 += t; else if (r == 1) v1 += t; else if (r == 2) v2 += t; else v3 += t;
+        }
+        total = (v0 + v1) + (v2 + v3);
+        A.sums[(int64_t)pair * kIcpSums + lane] = total;
+    }
+    __syncwarp();
+    if (A.peer_world > 1) {
+        // ---- all-reduce over peer memory. Buffer of a rank: slots [2 parities][world][32] doubles, then flags [2][world]
+        // (pass number + 1 as a double). Two parities: a rank can be at most one pass ahead of the slowest reader.
+        // Stores of the sums (relaxed, system scope), then the flag with release semantics; the reader acquires the flag.
+        const int W = A.peer_world;
+        const unsigned int pass = st->pass_id;
+        const int par = (int)(pass & 1u);
+        const double stamp = (double)(pass + 1u);
+        if (lane < kIcpSums) {
+            for (int r = 0; r < W; ++r) {
+                double* slot = A.peer_buf[r] + ((int64_t)par * W + A.peer_rank) * 32 + lane;
+                asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(slot), "d"(total) : "memory");
+            }
+        }
+        __threadfence_system();
+        __syncwarp();
+        if (lane < W) {
+            double* flag = A.peer_buf[lane] + (int64_t)2 * W * 32 + (int64_t)par * W + A.peer_rank;
+            asm volatile("st.release.sys.global.f64 [%0], %1;" ::"l"(flag), "d"(stamp) : "memory");
+        }
+        int timeout = 0;
+        if (lane < W) {
+            const double* flag = A.peer_buf[A.peer_rank] + (int64_t)2 * W * 32 + (int64_t)par * W + lane;
+            const long long t0c = clock64();
+            while (true) {
+                double v;
+                asm volatile("ld.acquire.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(flag) : "memory");
+                if (v == stamp) break;
+                if (clock64() - t0c > 4000000000ll) {  // ~2 s: a peer never arrived
+                    timeout = 1;
+                    break;
+                }
+            }
+        }
+        timeout = __any_sync(0xffffffffu, timeout) ? 1 : 0;
+        if (lane < kIcpSums) {
+            double t = 0.0;
+            for (int r = 0; r < W; ++r) {
+                const double* slot = A.peer_buf[A.peer_rank] + ((int64_t)par * W + r) * 32 + lane;
+                double v;
+                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(slot) : "memory");
+                t += v;
+            }
+            total = t;
+            A.sums[(int64_t)pair * kIcpSums + lane] = t;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            st->pass_id = pass + 1u;
+            if (timeout) {
+                st->done = 1;
+                st->converged = -1;  // exchange timed out
+            }
+        }
+        if (timeout) {
+            if (lane == 0) st->ticket = 0;
+            return;
+        }
+    }
+    // every lane gathers the 29 totals (lane 0 solves)
+    double a[kIcpSums];
+#pragma unroll
+    for (int j = 0; j < kIcpSums; ++j) a[j] = __shfl_sync(0xffffffffu, total, j);
+    if (lane == 0) {
+        st->ticket = 0;
+#ifndef B3D_TEST_NO_FINALIZE
+        if (A.fused) {
+            const double ns = A.ns_global ? (double)A.ns_global[pair] : (double)ns_local;
+            icp_finalize_pair(A.kind, a, ns, A.rel_fitness, A.rel_rmse, A.max_iter, st);
+        }
+#endif
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kernel(const __grid_constant__ IcpKernelArgs A) {
+    extern __shared__ __align__(16) unsigned char icp2_smem[];
+    const int pair = blockIdx.y;
+    IcpPairState* st = A.state + pair;
+    __shared__ double sT[16];
+    __shared__ double sm[kIcpBlock / 32][32];
+    __shared__ unsigned int s_arrived;
+    const int done = st->done;
+    if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
+    if (threadIdx.x == 0) s_arrived = 0u;
+    const int32_t s0 = A.src_off[pair], s1 = A.src_off[pair + 1];
+    const int32_t t0 = A.tgt_off[pair];
+    const int32_t c0 = A.chunk_off[pair], c1 = A.chunk_off[pair + 1];
+    if (done) return;  // uniform over the block
+    const int groups = icp_groups(c1 - c0);
+    if ((int)blockIdx.x >= groups) return;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Icp2Smem& S = reinterpret_cast<Icp2Smem*>(icp2_smem)[warp];
+    stage2_init_barrier(&S.mbar);
+    uint32_t parity = 0;
+    const UnitFrame F = unit_frame(A.grid.lat[pair], A.grid.shift);
+    const double inv_pm2 = (1.0 / F.per_m) * (1.0 / F.per_m);  // metres^2 per unit^2
+    int op_p, op_q;
+    icp_sum_operands(KIND, lane, op_p, op_q);
+    double (*rows)[kIcpRow] = reinterpret_cast<double (*)[kIcpRow]>(S.buf);
+    double acc = 0.0;  // lane j: running total of sum j
+    const double dmax = sqrt(A.r2);
+    const bool affine = sT[12] == 0.0 && sT[13] == 0.0 && sT[14] == 0.0 && sT[15] == 1.0;
+    const int32_t c_step = groups * (kIcpBlock / 32);
+    int32_t c = c0 + blockIdx.x * (kIcpBlock / 32) + warp;
+    // the next chunk's query is fetched while the current one is processed
+    double4 nsp = make_double4(0.0, 0.0, 0.0, 0.0);
+    float4 nkr = make_float4(0.f, 0.f, 0.f, 0.f);
+    int nkp = -1;
+    int32_t ni = 0;
+    bool nvalid = false;
+    if (c < c1) {
+        ni = A.chunk_start[c] + lane;
+        nvalid = ni < A.chunk_start[c + 1];
+        if (nvalid) {
+            nsp = ld_point(A.src_sorted + ni);
+            if (A.keep_ref != nullptr) {
+                nkr = A.keep_ref[ni];
+                nkp = A.keep_pos[ni];
+            }
+        }
+    }
+    for (; c < c1; c += c_step) {
+        const double4 sp = nsp;
+        const float4 kr = nkr;
+        const int kp = nkp;
+        const int32_t si = ni;
+        const bool valid = nvalid;
+        nvalid = false;
+        if (c + c_step < c1) {
+            ni = A.chunk_start[c + c_step] + lane;
+            nvalid = ni < A.chunk_start[c + c_step + 1];
+            if (nvalid) {
+                nsp = ld_point(A.src_sorted + ni);
+                if (A.keep_ref != nullptr) {
+                    nkr = A.keep_ref[ni];
+                    nkp = A.keep_pos[ni];
+                }
+            }
+        }
+        double px = 0, py = 0, pz = 0;
+        int oi = 0;
+        if (valid) {
+            oi = point_index(sp);  // original (batch-global) source index
+            const double x = sp.x, y = sp.y, z = sp.z;
+            // PointCloud::Transform: (T [p,1]).xyz / w
+            px = sT[0] * x + sT[1] * y + sT[2] * z + sT[3];
+            py = sT[4] * x + sT[5] * y + sT[6] * z + sT[7];
+            pz = sT[8] * x + sT[9] * y + sT[10] * z + sT[11];
+            if (!affine) {
+                const double w = sT[12] * x + sT[13] * y + sT[14] * z + sT[15];
+                px /= w; py /= w; pz /= w;
+            }
+        }
+        // ---- correspondence: sticky check, then one staged search bounded by the distance to the previous partner ---------
+        double d2 = 0.0;
+        int idx = 0, pos = -1;
+        double4 q = make_double4(0.0, 0.0, 0.0, 0.0);  // the partner's point record
+        bool need = valid;
+        double reach = dmax;  // this lane's search radius
+        if (valid && A.keep_ref != nullptr) {
+            const double mx = px - (double)kr.x, my = py - (double)kr.y, mz = pz - (double)kr.z;
+            // movement since the last search (+ the float rounding of the stored position)
+            const double moved = sqrt(mx * mx + my * my + mz * mz) + 2.0e-7 * (fabs(px) + fabs(py) + fabs(pz));
+            const double lim = (double)kr.w;  // every other target point was at least this far from the stored position (0: unknown)
+            if (kp >= 0) {
+                q = ld_point(A.grid.pts + kp);
+                const double dk = dist2<double>(px - q.x, py - q.y, pz - q.z);
+                const double u = sqrt(dk);
+                if (u * (1.0 + 1e-12) + moved < lim) {  // still strictly nearer than anything else can be
+                    need = false;
+                    pos = kp;
+                    d2 = dk;
+                    idx = point_index(q);
+                } else {
+                    const double slack = fmin(fmax(0.5 * moved, 0.01 * dmax), 0.1 * dmax);
+                    reach = fmin(u * (1.0 + 1e-9) + slack, dmax);  // nothing beyond d_max counts anyway
+                }
+            } else if (lim > 0.0) {
+                if (dmax * (1.0 + 1e-12) + moved < lim) need = false;  // nothing was within lim, nothing can be within d_max now
+                else if (moved < 0.5 * (kIcpReach2 - 1.0) * dmax) reach = dmax * kIcpReach2;
+            }
+        }
+        const unsigned int need_mask = __ballot_sync(0xffffffffu, need);
+        if (A.stats && lane == 0) {
+            if (need_mask == 0u) atomicAdd(&g_icp_stats[6], 1ull);
+            atomicAdd(&g_icp_stats[7], (unsigned long long)__popc(need_mask));
+        }
+        if (need_mask != 0u) {
+            // the chunk's box in fixed-point units of the target grid: every searching lane's ball, one unit of margin for the
+            // floor() of the records and one for the roundings here
+            const double ux = unit_coord_of_query(px, F.ox, F.per_m), uy = unit_coord_of_query(py, F.oy, F.per_m), uz = unit_coord_of_query(pz, F.oz, F.per_m);
+            const double ru = reach * F.per_m * (1.0 + 1e-12) + 2.0;
+            int lox = need ? unit_floor_clamped(ux - ru) : 0x7fffffff, loy = need ? unit_floor_clamped(uy - ru) : 0x7fffffff,
+                loz = need ? unit_floor_clamped(uz - ru) : 0x7fffffff;
+            int hix = need ? unit_ceil_clamped(ux + ru) : (int)0x80000000, hiy = need ? unit_ceil_clamped(uy + ru) : (int)0x80000000,
+                hiz = need ? unit_ceil_clamped(uz + ru) : (int)0x80000000;
+            lox = max(__reduce_min_sync(0xffffffffu, lox), 0); loy = max(__reduce_min_sync(0xffffffffu, loy), 0); loz = max(__reduce_min_sync(0xffffffffu, loz), 0);
+            hix = __reduce_max_sync(0xffffffffu, hix); hiy = __reduce_max_sync(0xffffffffu, hiy); hiz = __reduce_max_sync(0xffffffffu, hiz);
+            // this lane's query as an offset from the box centre (the centre stage2_run uses)
+            const int ccx = (int)(((long long)lox + hix) >> 1), ccy = (int)(((long long)loy + hiy) >> 1), ccz = (int)(((long long)loz + hiz) >> 1);
+            const double qdx = ux - (double)ccx, qdy = uy - (double)ccy, qdz = uz - (double)ccz;
+            const float qfx = (float)qdx, qfy = (float)qdy, qfz = (float)qdz;
+            const float fx = -2.0f * qfx, fy = -2.0f * qfy, fz = -2.0f * qfz;
+            // largest offset component of a candidate or of this query
+            const float H = fmaxf(fmaxf(fmaxf((float)(hix - ccx), (float)(hiy - ccy)), (float)(hiz - ccz)) + 1.0f, fmaxf(fmaxf(fabsf(qfx), fabsf(qfy)), fabsf(qfz)));
+            const float band_w = stage2_band(H);
+            float best = 3.0e38f, second = 3.0e38f;
+            int wpos = -1;      // sorted position of the float winner
+            int last_kept = 0;  // candidates of the last batch (still in shared memory after the call)
+            auto scan = [&](int kept) {
+                last_kept = kept;
+                if (!need) return;
+                float b = best, s2 = second;
+                int grp = -1;
+                for (int gi = 0; gi < kept; gi += 4) {
+                    const float ta = dot_t(S.buf[gi], fx, fy, fz), tb = dot_t(S.buf[gi + 1], fx, fy, fz);
+                    const float tc = dot_t(S.buf[gi + 2], fx, fy, fz), td = dot_t(S.buf[gi + 3], fx, fy, fz);
+                    const float m01 = fminf(ta, tb), M01 = fmaxf(ta, tb), m23 = fminf(tc, td), M23 = fmaxf(tc, td);
+                    const float m = fminf(m01, m23), Mm = fmaxf(m01, m23);
+                    const float sg = fminf(fminf(M01, M23), Mm);  // second smallest of the four
+                    s2 = fminf(s2, fminf(sg, fmaxf(m, b)));
+                    grp = m < b ? gi : grp;
+                    b = fminf(b, m);
+                }
+                if (grp >= 0) {
+                    // the new best sits in group grp: the first of the four that reproduces it (ties end up in the float64 path)
+                    int w = grp + 3;
+                    if (dot_t(S.buf[grp + 2], fx, fy, fz) == b) w = grp + 2;
+                    if (dot_t(S.buf[grp + 1], fx, fy, fz) == b) w = grp + 1;
+                    if (dot_t(S.buf[grp], fx, fy, fz) == b) w = grp;
+                    wpos = S.pos[w];
+                }
+                best = b;
+                second = s2;
+            };
+            const int nb = stage2_run<kIcp2Cap>(A.grid, F, pair, lox, loy, loz, hix, hiy, hiz, S, parity, scan);
+            if (A.stats && lane == 0) {
+                atomicAdd(&g_icp_stats[0], 1ull);
+                if (nb < 0) atomicAdd(&g_icp_stats[2], 1ull);
+                else atomicAdd(&g_icp_stats[3], (unsigned long long)last_kept);
+                if (nb > 1) atomicAdd(&g_icp_stats[1], 1ull);
+            }
+            double others2 = 3.0e38;  // lower bound of the squared distance (metres) of every target point but the winner
+            bool bounded = nb >= 0;   // every target point within `reach` of the query was looked at
+            if (need) {
+                if (nb < 0) {
+                    pos = icp2_walk(A.grid, pair, px, py, pz, A.r2, A.rmax, &d2, &idx, &q);
+                } else if (wpos >= 0) {
+                    const bool ambiguous = second <= best + band_w;
+                    if (ambiguous && nb > 1) {
+                        // near-tie in a box that took several batches (the earlier candidates are gone)
+                        pos = icp2_walk(A.grid, pair, px, py, pz, A.r2, A.rmax, &d2, &idx, &q);
+                        bounded = false;
+                    } else {
+                        pos = wpos;
+                        q = ld_point(A.grid.pts + pos);
+                        d2 = dist2<double>(px - q.x, py - q.y, pz - q.z);
+                        idx = point_index(q);
+                        if (ambiguous) {
+                            pos = icp2_resolve_ties(A.grid.pts, S.buf, S.pos, last_kept, fx, fy, fz, best + band_w, px, py, pz, wpos, &d2, &idx, &q);
+                            others2 = d2;
+                        } else {
+                            others2 = fmax(d2, ((qdx * qdx + qdy * qdy + qdz * qdz) + (double)second - (double)band_w) * inv_pm2);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (need && A.keep_ref != nullptr) {
+                // what this search proved: the nearest point (if any within reach) and that every other point is at least
+                // min(runner-up, reach) away; stored rounded down
+                float lbf = 0.f;
+                if (bounded) lbf = (float)(fmin(sqrt(others2), reach) * (1.0 - 1.0e-6));
+                A.keep_ref[si] = make_float4((float)px, (float)py, (float)pz, lbf);
+                A.keep_pos[si] = pos;
+            }
+        }
+        if (pos >= 0 && !(d2 < A.r2)) pos = -1;
+        double e[kIcpRow];
+#pragma unroll
+        for (int j = 0; j < kIcpRow; ++j) e[j] = 0.0;
+        double W[9], gd[3], gp[3];  // generalized ICP / information matrix only
+        bool matched = false;
+        if (valid) {
+            if (A.corr != nullptr) A.corr[oi] = pos >= 0 ? idx - t0 : -1;
+            if (pos >= 0) {
+                matched = true;
+                e[7] = 1.0;
+                e[8] = d2;
+                if (KIND == kIcpInformation) {
+                    gp[0] = q.x; gp[1] = q.y; gp[2] = q.z;
+                } else if (KIND == B3D_ICP_POINT_TO_POINT) {
+                    e[0] = px; e[1] = py; e[2] = pz;
+                    e[3] = q.x; e[4] = q.y; e[5] = q.z;
+                } else if (KIND == B3D_ICP_POINT_TO_PLANE) {
+                    const double* nq = A.tgt_nrm_sorted + 3 * (int64_t)pos;
+                    const double n0 = __ldg(nq), n1 = __ldg(nq + 1), n2 = __ldg(nq + 2);
+                    e[0] = py * n2 - pz * n1; e[1] = pz * n0 - px * n2; e[2] = px * n1 - py * n0;
+                    e[3] = n0; e[4] = n1; e[5] = n2;
+                    e[6] = (px - q.x) * n0 + (py - q.y) * n1 + (pz - q.z) * n2;
+                } else {
+                    // generalized ICP: M = C_t + R C_s R^T, W = (M^-1)^(1/2), rows r_k = W_k (p - q), J = W [ -[p]x | I ]
+                    const double* Ct = A.tgt_cov_sorted + 9 * (int64_t)pos;
+                    const double* Cs = A.src_cov + 9 * (int64_t)oi;
+                    double RC[9], M[9];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) RC[3 * r + cc] = sT[4 * r] * Cs[cc] + sT[4 * r + 1] * Cs[3 + cc] + sT[4 * r + 2] * Cs[6 + cc];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc)
+                            M[3 * r + cc] = __ldg(Ct + 3 * r + cc) + (RC[3 * r] * sT[4 * cc] + RC[3 * r + 1] * sT[4 * cc + 1] + RC[3 * r + 2] * sT[4 * cc + 2]);
+                    inv_sqrt_sym3(M, W);
+                    gd[0] = px - q.x; gd[1] = py - q.y; gd[2] = pz - q.z;
+                    gp[0] = px; gp[1] = py; gp[2] = pz;
+                }
+            }
+        }
+        const int n_rows = (KIND == B3D_ICP_GENERALIZED || KIND == kIcpInformation) ? 3 : 1;
+        for (int row = 0; row < n_rows; ++row) {
+            if (KIND == kIcpInformation) {
+                if (matched) {
+                    // G = [ -[t]x | I ] for the target point t (kept in gp)
+                    e[0] = row == 0 ? 0.0 : (row == 1 ? -gp[2] : gp[1]);
+                    e[1] = row == 0 ? gp[2] : (row == 1 ? 0.0 : -gp[0]);
+                    e[2] = row == 0 ? -gp[1] : (row == 1 ? gp[0] : 0.0);
+                    e[3] = row == 0 ? 1.0 : 0.0; e[4] = row == 1 ? 1.0 : 0.0; e[5] = row == 2 ? 1.0 : 0.0;
+                    e[6] = 0.0;
+                    if (row > 0) { e[7] = 0.0; e[8] = 0.0; }
+                }
+            }
+            if (KIND == B3D_ICP_GENERALIZED) {
+                if (matched) {
+                    const double w0 = W[3 * row], w1 = W[3 * row + 1], w2 = W[3 * row + 2];
+                    // J = W_row [ -[p]x | I ],  -[p]x = [0 pz -py; -pz 0 px; py -px 0]
+                    e[0] = w1 * (-gp[2]) + w2 * gp[1];
+                    e[1] = w0 * gp[2] + w2 * (-gp[0]);
+                    e[2] = w0 * (-gp[1]) + w1 * gp[0];
+                    e[3] = w0; e[4] = w1; e[5] = w2;
+                    e[6] = w0 * gd[0] + w1 * gd[1] + w2 * gd[2];
+                    if (row > 0) { e[7] = 0.0; e[8] = 0.0; }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kIcpRow; ++j) rows[lane][j] = e[j];
+            __syncwarp();
+            if ((KIND == B3D_ICP_GENERALIZED || KIND == kIcpInformation) && row > 0 && lane >= 27) {
+                // count and sum d2 are taken once per correspondence (row 0)
+            } else {
+#pragma unroll 8
+                for (int l = 0; l < 32; ++l) acc += rows[l][op_p] * rows[l][op_q];
+            }
+            __syncwarp();
+        }
+    }
+    // ---- the warp's 29 sums -> the block's row (the last warp of the block to arrive adds the four rows in warp order) ----
+    sm[warp][lane] = acc;
+    __threadfence_block();
+    __syncwarp();  // every lane's row entry is out before lane 0 announces the warp
+    unsigned int arrived = 0;
+    if (lane == 0) arrived = atomicAdd(&s_arrived, 1u);
+    arrived = __shfl_sync(0xffffffffu, arrived, 0);
+    if (arrived != (unsigned int)(kIcpBlock / 32 - 1)) return;
+    __threadfence_block();
+    {
+        double v = sm[0][lane];
+#pragma unroll
+        for (int w = 1; w < kIcpBlock / 32; ++w) v += sm[w][lane];
+        if (lane < kIcpSums) A.partial[((int64_t)pair * gridDim.x + blockIdx.x) * kIcpSums + lane] = v;
+    }
+    __threadfence();
+    __syncwarp();
+    unsigned int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&st->ticket, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket != (unsigned int)groups - 1u) return;
+    __threadfence();
+    icp2_finish_pair(A, pair, groups, s1 - s0);
+}
+
 __global__ void icp_finalize_kernel(int kind, const double* __restrict__ sums, const int32_t* __restrict__ src_off, const int64_t* __restrict__ ns_global,
                                     double rel_fitness, double rel_rmse, int max_iter, IcpPairState* state, int P) {
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
@@ -737,9 +1201,24 @@ static IcpKernelArgs make_args(const IcpProblem& pb, IcpWork* w, int32_t* corr, 
     return A;
 }
 
+template <int KIND>
+static int launch_pass2(b3d_ctx* ctx, const IcpKernelArgs& A, dim3 grid) {
+    const size_t smem = sizeof(Icp2Smem) * (kIcpBlock / 32);
+    B3D_CUDA(cudaFuncSetAttribute(icp_pass2_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device; cheap
+    B3D_LAUNCH(ctx, icp_pass2_kernel<KIND>, grid, kIcpBlock, smem, A);
+    return B3D_OK;
+}
+
 int icp_pass(b3d_ctx* ctx, const IcpProblem& pb, IcpWork* w, int32_t* corr, bool fused) {
     IcpKernelArgs A = make_args(pb, w, corr, fused);
     const dim3 grid(w->blocks, pb.P);
+    static const bool v1 = getenv("B3D_ICP_V1") != nullptr;  // the round-1 kernel (kept for A/B runs and as the reference of the equality test)
+    if (!v1 && A.grid.rec != nullptr) {
+        if (pb.kind == B3D_ICP_POINT_TO_POINT) return launch_pass2<B3D_ICP_POINT_TO_POINT>(ctx, A, grid);
+        if (pb.kind == kIcpInformation) return launch_pass2<kIcpInformation>(ctx, A, grid);
+        if (pb.kind == B3D_ICP_POINT_TO_PLANE) return launch_pass2<B3D_ICP_POINT_TO_PLANE>(ctx, A, grid);
+        return launch_pass2<B3D_ICP_GENERALIZED>(ctx, A, grid);
+    }
     if (pb.kind == B3D_ICP_POINT_TO_POINT) {
         B3D_LAUNCH(ctx, icp_pass_kernel<B3D_ICP_POINT_TO_POINT>, grid, kIcpBlock, 0, A);
     } else if (pb.kind == kIcpInformation) {

@@ -4,6 +4,8 @@
 #include "b3d_scan.cuh"
 #include "b3d_search.cuh"
 #include "b3d_stage.cuh"
+#include "b3d_stage2.cuh"
+#include "b3d_sortnet.cuh"
 
 #include <cmath>
 #include <cstdlib>
@@ -307,6 +309,206 @@ __global__ void __launch_bounds__(kNrmBlock) normals_staged_kernel(GridView<doub
     }
 }
 
+// ---- staged legacy normals, round 2 ------------------------------------------------------------------------------------
+// Two kernels instead of one (profiles/r01n_ncu_normals_staged_p64_digest.txt: 4.7 G warp instructions at 19 active lanes,
+// instruction-cache misses, a per-thread insertion sort on 10 of 32 lanes):
+//  normals_cov2_kernel: one warp per chunk. Staging through b3d_stage2.cuh (bulk copies of whole cells, float32 filter out of
+//    shared memory); every lane collects the candidates inside its radius (exact: borderline ones are confirmed in float64),
+//    the short lists are ordered by distance with a SORTING NETWORK HELD IN REGISTERS (uniform control flow, sized by the
+//    longest list of the warp), the nine raw moments are summed in that order from the float64 points (re-gathered, L1) and
+//    the covariance goes to global memory (48 bytes per point). No float64 copy of the candidates in shared memory.
+//  normals_eig2_kernel: one thread per point, closed-form eigenvector + orientation against the prior, every lane busy.
+// Points that need the k-nearest cut (more than k in-radius neighbours, or more than 32), or whose box takes more than one
+// staging batch, are queued for the per-lane kernel exactly as before (their covariance slot is marked).
+#ifndef B3D_NRM2_CAP
+#define B3D_NRM2_CAP 380
+#endif
+constexpr int kNrm2Cap = B3D_NRM2_CAP;
+constexpr int kNrm2List = 32;
+struct alignas(16) Nrm2Smem {
+    StageSmem<kNrm2Cap> stage;
+    unsigned char list[32][kNrm2List + 4];  // per lane: candidate slots inside the radius, scan order (row stride 36 bytes)
+};
+
+#define B3D_CE(a, b)                          \
+    {                                         \
+        const unsigned int lo_ = min(k[a], k[b]); \
+        k[b] = max(k[a], k[b]);               \
+        k[a] = lo_;                           \
+    }
+
+__global__ void __launch_bounds__(kNrmBlock, 5) normals_cov2_kernel(GridView<double> g, const int32_t* __restrict__ chunk_start,
+                                                                   const int32_t* __restrict__ chunk_off, int B, int n_chunks, int k_nn, double radius,
+                                                                   double r2, double* __restrict__ cov6, int* __restrict__ todo,
+                                                                   int* __restrict__ todo_count, int stats) {
+    extern __shared__ __align__(16) unsigned char nrm2_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Nrm2Smem& W = reinterpret_cast<Nrm2Smem*>(nrm2_smem)[warp];
+    auto& S = W.stage;
+    stage2_init_barrier(&S.mbar);
+    uint32_t parity = 0;
+    unsigned char* list = W.list[lane];
+    int cur_cloud = -1;
+    UnitFrame F = {};
+    float r2u = 0.f;   // radius^2 in units^2
+    double ru = 0.0;   // radius in units (+ margins)
+    for (int c = blockIdx.x * (kNrmBlock / 32) + warp; c < n_chunks; c += gridDim.x * (kNrmBlock / 32)) {
+        // cloud of this chunk: last b with chunk_off[b] <= c
+        int lo_b = 0, hi_b = B;
+        while (hi_b - lo_b > 1) {
+            const int m = (lo_b + hi_b) >> 1;
+            if (chunk_off[m] <= c) lo_b = m; else hi_b = m;
+        }
+        const int cloud = lo_b;
+        if (cloud != cur_cloud) {
+            F = unit_frame(g.lat[cloud], g.shift);
+            r2u = (float)(r2 * F.per_m * F.per_m);
+            ru = radius * F.per_m * (1.0 + 1e-12) + 2.0;
+            cur_cloud = cloud;
+        }
+        const int32_t i = chunk_start[c] + lane;
+        const bool valid = i < chunk_start[c + 1];
+        double qx = 0, qy = 0, qz = 0;
+        int oi = 0;
+        if (valid) {
+            const double4 q = ld_point(g.pts + i);
+            qx = q.x; qy = q.y; qz = q.z;
+            oi = point_index(q);
+        }
+        // the chunk's box in fixed-point units: every query's ball, margins for the floor() of the records and the roundings here
+        const double ux = unit_coord_of_query(qx, F.ox, F.per_m), uy = unit_coord_of_query(qy, F.oy, F.per_m), uz = unit_coord_of_query(qz, F.oz, F.per_m);
+        int lox = valid ? unit_floor_clamped(ux - ru) : 0x7fffffff, loy = valid ? unit_floor_clamped(uy - ru) : 0x7fffffff,
+            loz = valid ? unit_floor_clamped(uz - ru) : 0x7fffffff;
+        int hix = valid ? unit_ceil_clamped(ux + ru) : (int)0x80000000, hiy = valid ? unit_ceil_clamped(uy + ru) : (int)0x80000000,
+            hiz = valid ? unit_ceil_clamped(uz + ru) : (int)0x80000000;
+        lox = max(__reduce_min_sync(0xffffffffu, lox), 0); loy = max(__reduce_min_sync(0xffffffffu, loy), 0); loz = max(__reduce_min_sync(0xffffffffu, loz), 0);
+        hix = __reduce_max_sync(0xffffffffu, hix); hiy = __reduce_max_sync(0xffffffffu, hiy); hiz = __reduce_max_sync(0xffffffffu, hiz);
+        const int ccx = (int)(((long long)lox + hix) >> 1), ccy = (int)(((long long)loy + hiy) >> 1), ccz = (int)(((long long)loz + hiz) >> 1);
+        const float qox = (float)(ux - (double)ccx), qoy = (float)(uy - (double)ccy), qoz = (float)(uz - (double)ccz);
+        const float fx = -2.0f * qox, fy = -2.0f * qoy, fz = -2.0f * qoz;
+        const float qq = fmaf(qoz, qoz, fmaf(qoy, qoy, qox * qox));
+        const float H = fmaxf(fmaxf((float)(hix - ccx), (float)(hiy - ccy)), (float)(hiz - ccz)) + 1.0f;
+        // |d2f - d2| <= rounding of the scanned t (half of stage2_band would do) + of |q|^2 + of the add + of r2u itself
+        const float band = stage2_band(H) + 4.0e-7f * r2u;
+        int n = 0;
+        int kept_all = 0;
+        auto scan = [&](int kept) {
+            kept_all = kept;
+            if (!valid) return;
+            for (int j = 0; j < kept; ++j) {
+                const float4 cj = S.buf[j];
+                const float d2f = fmaf(fx, cj.x, fmaf(fy, cj.y, fmaf(fz, cj.z, cj.w))) + qq;
+                if (d2f <= r2u + band) {
+                    bool acc = d2f < r2u - band;
+                    if (!acc) {
+                        const double4 pj = ld_point(g.pts + S.pos[j]);
+                        acc = dist2<double>(qx - pj.x, qy - pj.y, qz - pj.z) < r2;
+                    }
+                    if (acc) {
+                        if (n < kNrm2List) list[n] = (unsigned char)j;
+                        ++n;
+                    }
+                }
+            }
+        };
+        const int nb = stage2_run<kNrm2Cap>(g, F, cloud, lox, loy, loz, hix, hiy, hiz, S, parity, scan);
+        const unsigned int valid_mask = __ballot_sync(0xffffffffu, valid);
+        if (stats && lane == 0) {
+            atomicAdd(&g_nrm_stats[0], 1ull);
+            if (nb != 1) atomicAdd(&g_nrm_stats[1], 1ull); else atomicAdd(&g_nrm_stats[3], (unsigned long long)kept_all);
+            atomicAdd(&g_nrm_stats[4], (unsigned long long)__popc(valid_mask));
+        }
+        // one batch holds every candidate (slots fit a byte); anything else goes to the per-lane kernel
+        const bool chunk_ok = nb == 1 && kept_all <= 256;
+        const bool punt = valid && (!chunk_ok || n > k_nn || n > kNrm2List);
+        if (punt) {
+            if (stats && chunk_ok) atomicAdd(&g_nrm_stats[2], 1ull);
+            todo[atomicAdd(todo_count, 1)] = i;
+            cov6[6 * (int64_t)oi] = __longlong_as_double(0x7ff8000000000b3dll);  // marked: the eigen kernel skips it
+        }
+        const bool work = valid && !punt;
+        if (!work) n = 0;
+        const int nmax = __reduce_max_sync(0xffffffffu, n);
+        if (nmax == 0) {
+            __syncwarp();
+            continue;
+        }
+        // ---- keys into registers: (float bits of d2 with the low 8 bits replaced by the candidate slot), ascending = (d2, scan order)
+        unsigned int k[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            k[j] = 0xffffffffu;
+            if (j < nmax && j < n) {
+                const int slot = list[j];
+                const float4 cj = S.buf[slot];
+                const float d2f = fmaf(fx, cj.x, fmaf(fy, cj.y, fmaf(fz, cj.z, cj.w))) + qq;
+                k[j] = (__float_as_uint(fmaxf(d2f, 0.0f)) & ~255u) | (unsigned int)slot;
+            }
+        }
+        if (nmax <= 8) {
+            B3D_SORTNET_8(B3D_CE)
+        } else if (nmax <= 16) {
+            B3D_SORTNET_16(B3D_CE)
+        } else {
+            B3D_SORTNET_32(B3D_CE)
+        }
+        // ---- raw-moment covariance over the neighbour set in distance order (float64 points re-gathered) ------------------
+        double cu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (j < nmax && j < n) {
+                const double4 pj = ld_point(g.pts + S.pos[k[j] & 255u]);
+                const double x = pj.x, y = pj.y, z = pj.z;
+                cu[0] += x; cu[1] += y; cu[2] += z;
+                cu[3] += x * x; cu[4] += x * y; cu[5] += x * z;
+                cu[6] += y * y; cu[7] += y * z; cu[8] += z * z;
+            }
+        }
+        if (work) {
+            double C[6] = {1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
+            if (n >= 3) {
+                const double cn = (double)n;
+#pragma unroll
+                for (int j = 0; j < 9; ++j) cu[j] /= cn;
+                C[0] = cu[3] - cu[0] * cu[0];
+                C[1] = cu[4] - cu[0] * cu[1];
+                C[2] = cu[5] - cu[0] * cu[2];
+                C[3] = cu[6] - cu[1] * cu[1];
+                C[4] = cu[7] - cu[1] * cu[2];
+                C[5] = cu[8] - cu[2] * cu[2];
+            }
+            double* out = cov6 + 6 * (int64_t)oi;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) out[j] = C[j];
+        }
+        __syncwarp();
+    }
+}
+#undef B3D_CE
+
+// cov6[i] = {a00 a01 a02 a11 a12 a22} of point i (original index) -> unit normal, oriented against the prior
+__global__ void __launch_bounds__(256) normals_eig2_kernel(const double* __restrict__ cov6, int64_t n, const double* __restrict__ prior,
+                                                           double* __restrict__ normals) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double* c = cov6 + 6 * i;
+        const double a00 = c[0];
+        if (__double_as_longlong(a00) == 0x7ff8000000000b3dll) continue;  // queued for the per-lane kernel
+        Sym3<double> C{a00, c[1], c[2], c[3], c[4], c[5]};
+        Vec3<double> nrm = sym3_smallest_eigvec<double>(C);
+        const double len = sqrt(nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z);
+        if (prior != nullptr) {
+            const double ox = prior[3 * i], oy = prior[3 * i + 1], oz = prior[3 * i + 2];
+            if (len == 0.0) nrm = {ox, oy, oz};
+            else if (nrm.x * ox + nrm.y * oy + nrm.z * oz < 0.0) nrm = {-nrm.x, -nrm.y, -nrm.z};
+        } else if (len == 0.0) {
+            nrm = {0.0, 0.0, 1.0};
+        }
+        normals[3 * i] = nrm.x;
+        normals[3 * i + 1] = nrm.y;
+        normals[3 * i + 2] = nrm.z;
+    }
+}
+
 // ---- k nearest export (b3d_knn_hybrid): arbitrary queries against a grid -------------------------------------------
 template <typename T, int KMAX>
 __global__ void __launch_bounds__(128) knn_export_kernel(GridView<T> g, const int32_t* __restrict__ off, const T* __restrict__ queries, int64_t nq,
@@ -491,11 +693,23 @@ int estimate_normals_batch(b3d_ctx* ctx, const T* xyz, const Segments& seg, int 
             B3D_TRY(todo_buf.alloc(ctx, (size_t)n));
             B3D_TRY(todo_count_buf.alloc(ctx, 1));
             B3D_CUDA(cudaMemsetAsync(todo_count_buf.p, 0, sizeof(int), ctx->stream));
-            const int sblocks = std::max(1, std::min((qc.n_chunks + kNrmBlock / 32 - 1) / (kNrmBlock / 32), ctx->sm_count * 32));
-            const size_t smem = sizeof(NrmWarpSmem) * (kNrmBlock / 32);
-            B3D_CUDA(cudaFuncSetAttribute(normals_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            B3D_LAUNCH(ctx, normals_staged_kernel, sblocks, kNrmBlock, smem, grid->view(), qc.q, qc.chunk_start.p, qc.chunk_off.p, seg.B, qc.n_chunks, max_nn,
-                       radius, r2, prior, normals, todo_buf.p, todo_count_buf.p, getenv("B3D_ICP_STATS") ? 1 : 0);
+            static const bool v1 = getenv("B3D_NRM_V1") != nullptr;  // the round-1 kernel, kept for A/B runs
+            if (!v1 && grid->rec.p != nullptr) {
+                DevBuf<double> cov6;
+                B3D_TRY(cov6.alloc(ctx, (size_t)n * 6));
+                const int sblocks = std::max(1, std::min((qc.n_chunks + kNrmBlock / 32 - 1) / (kNrmBlock / 32), ctx->sm_count * 20));
+                const size_t smem = sizeof(Nrm2Smem) * (kNrmBlock / 32);
+                B3D_CUDA(cudaFuncSetAttribute(normals_cov2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                B3D_LAUNCH(ctx, normals_cov2_kernel, sblocks, kNrmBlock, smem, grid->view(), qc.chunk_start.p, qc.chunk_off.p, seg.B, qc.n_chunks, max_nn,
+                           radius, r2, cov6.p, todo_buf.p, todo_count_buf.p, getenv("B3D_ICP_STATS") ? 1 : 0);
+                B3D_LAUNCH(ctx, normals_eig2_kernel, ctx->grid_for(n, 256, 1, 8), 256, 0, cov6.p, (int64_t)n, prior, normals);
+            } else {
+                const int sblocks = std::max(1, std::min((qc.n_chunks + kNrmBlock / 32 - 1) / (kNrmBlock / 32), ctx->sm_count * 32));
+                const size_t smem = sizeof(NrmWarpSmem) * (kNrmBlock / 32);
+                B3D_CUDA(cudaFuncSetAttribute(normals_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                B3D_LAUNCH(ctx, normals_staged_kernel, sblocks, kNrmBlock, smem, grid->view(), qc.q, qc.chunk_start.p, qc.chunk_off.p, seg.B, qc.n_chunks,
+                           max_nn, radius, r2, prior, normals, todo_buf.p, todo_count_buf.p, getenv("B3D_ICP_STATS") ? 1 : 0);
+            }
             todo = todo_buf.p;
             todo_count = todo_count_buf.p;
             blocks = std::min(blocks, ctx->sm_count * 4);  // the queue is short; the kernel strides over it

@@ -16,13 +16,13 @@ constexpr unsigned long long kEmptyKey = ~0ull;
 // beyond this ring a k-nearest query stops walking shells and scans its whole cloud instead (isolated points)
 constexpr int kMaxRing = 6;
 
-__host__ __device__ __forceinline__ unsigned long long hash_key(unsigned long long k) {
-    k ^= k >> 33;
-    k *= 0xff51afd7ed558ccdULL;
-    k ^= k >> 33;
-    k *= 0xc4ceb9fe1a85ec53ULL;
-    k ^= k >> 33;
-    return k;
+// 32-bit mix of a slot key (two multiplies and two xor-shifts; the keys are small packed integers)
+__host__ __device__ __forceinline__ uint32_t hash_key(unsigned long long k) {
+    uint32_t h = (uint32_t)k * 0x9E3779B1u ^ (uint32_t)(k >> 32) * 0x85EBCA6Bu;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 13;
+    return h;
 }
 
 __device__ __forceinline__ float4 ld_point(const float4* p) { return __ldg(p); }
@@ -38,7 +38,7 @@ __device__ __forceinline__ double index_as_w(double, int i) { return __longlong_
 
 template <typename T>
 __device__ __forceinline__ bool grid_lookup(const GridView<T>& g, unsigned long long key, int& start, int& end) {
-    uint32_t s = (uint32_t)hash_key(key) & g.mask;
+    uint32_t s = hash_key(key) & g.mask;
     while (true) {
         uint4 raw = __ldg(reinterpret_cast<const uint4*>(g.slots + s));
         unsigned long long k = ((unsigned long long)raw.y << 32) | raw.x;
@@ -84,7 +84,6 @@ __device__ __forceinline__ int grid_walk(const GridView<T>& g, int cloud, T qx, 
     const double slack = 1.0 - SearchSlack<T>::rel;
     const double h2 = h * h * slack;
     double face = fmin(fmin(fmin(fx, 1.0 - fx), fmin(fy, 1.0 - fy)), fmin(fz, 1.0 - fz));
-    const unsigned long long cloud_bits = (unsigned long long)cloud << g.shift;
     // rings entirely outside the lattice cannot hold points: the farthest useful ring
     long long far = 0;
     {
@@ -115,7 +114,7 @@ __device__ __forceinline__ int grid_walk(const GridView<T>& g, int cloud, T qx, 
                     const double gz = dz > 0 ? (double)dz - fz : (dz < 0 ? fz - (double)dz - 1.0 : 0.0);
                     const double box2 = (gxy2 + gz * gz) * h2;
                     if (box2 > thr()) continue;
-                    const unsigned long long key = cloud_bits | lattice_key(L, x, y, z);
+                    const unsigned long long key = grid_slot_key(g.shift, cloud, x, y, z);
                     int s, e;
                     if (!grid_lookup(g, key, s, e)) continue;
                     for (int p = s; p < e; ++p) visit(p, ld_point(g.pts + p));
@@ -224,9 +223,8 @@ __device__ __forceinline__ int nn_within_query(const GridView<T>& g, int cloud, 
     const double slack = 1.0 - SearchSlack<T>::rel;
     const double h2 = h * h * slack;
     const double face = fmin(fmin(fmin(fx, 1.0 - fx), fmin(fy, 1.0 - fy)), fmin(fz, 1.0 - fz));
-    const unsigned long long cloud_bits = (unsigned long long)cloud << g.shift;
     auto scan_cell = [&](long long x, long long y, long long z) {
-        const unsigned long long key = cloud_bits | lattice_key(L, x, y, z);
+        const unsigned long long key = grid_slot_key(g.shift, cloud, x, y, z);
         int s, e;
         if (!grid_lookup(g, key, s, e)) return;
         for (int p = s; p < e; ++p) {

@@ -4,6 +4,7 @@
 #include "b3d_common.cuh"
 #include "b3d_scan.cuh"
 #include "b3d_search.cuh"
+#include "b3d_stage2.cuh"
 
 #include <cfloat>
 #include <climits>
@@ -71,8 +72,7 @@ __global__ void bounds_final_kernel(const double* __restrict__ partial, int nblo
 // grid = (blocks per cloud, B)
 template <typename T>
 __global__ void __launch_bounds__(256) cell_key_kernel(const T* __restrict__ xyz, const int32_t* __restrict__ off,
-                                                       const Lattice* __restrict__ lat, int shift, uint64_t* __restrict__ keys,
-                                                       uint32_t* __restrict__ order) {
+                                                       const Lattice* __restrict__ lat, int shift, uint64_t* __restrict__ keys) {
     const int b = blockIdx.y;
     const Lattice L = lat[b];
     const int64_t s = off[b], e = off[b + 1];
@@ -82,7 +82,6 @@ __global__ void __launch_bounds__(256) cell_key_kernel(const T* __restrict__ xyz
         lattice_coord<T>(L, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], cx, cy, cz);
         cx -= L.kx0; cy -= L.ky0; cz -= L.kz0;
         keys[i] = cloud_bits | lattice_key(L, cx, cy, cz);
-        order[i] = (uint32_t)i;
     }
 }
 
@@ -107,9 +106,13 @@ __global__ void run_offsets_kernel(const uint64_t* __restrict__ keys, int32_t* r
     }
 }
 
+// rec (float64 grids): the staged searches' 16-byte record of the point -- fixed-point coordinates in units of cell / 2^s
+// relative to the lattice origin (b3d_stage2.cuh: unit_coord_of_point; record >> s == cell index), .w = sorted position
 template <typename T>
 __global__ void __launch_bounds__(256) gather_sorted_kernel(const T* __restrict__ xyz, const uint32_t* __restrict__ order, int32_t n,
-                                                            typename PointT<T>::vec4* __restrict__ out) {
+                                                            typename PointT<T>::vec4* __restrict__ out, const uint64_t* __restrict__ keys,
+                                                            const Lattice* __restrict__ lat, int shift, int4* __restrict__ rec) {
+    const int us = grid_unit_shift(shift);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t p = order[i];
         typename PointT<T>::vec4 v;
@@ -118,6 +121,11 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(const T* __restrict_
         v.z = xyz[3 * (int64_t)p + 2];
         v.w = index_as_w(T(0), (int)p);
         out[i] = v;
+        if (rec != nullptr) {
+            const Lattice L = lat[(int)(keys[i] >> shift)];
+            rec[i] = make_int4(unit_coord_of_point((double)v.x, L.ox, L.cell, us), unit_coord_of_point((double)v.y, L.oy, L.cell, us),
+                               unit_coord_of_point((double)v.z, L.oz, L.cell, us), (int)i);
+        }
     }
 }
 
@@ -129,12 +137,16 @@ __global__ void __launch_bounds__(256) hash_clear_kernel(HashSlot* __restrict__ 
     }
 }
 
+// keys: sorted composite Morton keys of a search grid; the table is keyed by grid_slot_key (cloud | x | y | z)
 __global__ void __launch_bounds__(256) hash_insert_kernel(const uint64_t* __restrict__ keys, const int32_t* __restrict__ run_start, int64_t n_runs,
-                                                          HashSlot* __restrict__ slots, uint32_t mask) {
+                                                          int shift, HashSlot* __restrict__ slots, uint32_t mask) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_runs; r += (int64_t)gridDim.x * blockDim.x) {
         const int32_t s = run_start[r], e = run_start[r + 1];
-        const unsigned long long key = keys[s];
-        uint32_t h = (uint32_t)hash_key(key) & mask;
+        const unsigned long long mk = keys[s];
+        const unsigned long long m = mk & ((1ull << shift) - 1ull);
+        const unsigned long long key = grid_slot_key(shift, (int)(mk >> shift), (long long)morton_compact3(m >> 2), (long long)morton_compact3(m >> 1),
+                                                     (long long)morton_compact3(m));
+        uint32_t h = hash_key(key) & mask;
         while (true) {
             unsigned long long prev = atomicCAS(&slots[h].key, kEmptyKey, key);
             if (prev == kEmptyKey) {
@@ -268,26 +280,21 @@ int spatial_sort(b3d_ctx* ctx, const T* xyz, const Segments& seg, double cell, i
     B3D_TRY(ctx->upload(out->lat.p, lat.data(), (size_t)B * sizeof(Lattice)));
 
     DevBuf<uint64_t> keys_in(ctx), keys_out(ctx);
-    DevBuf<uint32_t> ord_in(ctx), ord_out(ctx);
+    DevBuf<uint32_t> ord_out(ctx);
     B3D_TRY(keys_in.alloc(ctx, n));
     B3D_TRY(keys_out.alloc(ctx, n));
-    B3D_TRY(ord_in.alloc(ctx, n));
     B3D_TRY(ord_out.alloc(ctx, n));
     {
         int64_t longest = 0;
         for (int b = 0; b < B; ++b) longest = std::max<int64_t>(longest, seg.off_h[b + 1] - seg.off_h[b]);
         int blocks = (int)std::min<int64_t>((longest + 255) / 256, std::max(1, ctx->sm_count * 16 / B));
         blocks = std::max(1, blocks);
-        B3D_LAUNCH(ctx, cell_key_kernel<T>, dim3(blocks, B), 256, 0, xyz, seg.off, out->lat.p, shift, keys_in.p, ord_in.p);
+        B3D_LAUNCH(ctx, cell_key_kernel<T>, dim3(blocks, B), 256, 0, xyz, seg.off, out->lat.p, shift, keys_in.p);
     }
-    bool in_a = true;
-    B3D_TRY(radix_sort_pairs(ctx, keys_in.p, ord_in.p, keys_out.p, ord_out.p, n, end_bit, &in_a));
-    if (in_a) {
-        std::swap(keys_in, keys_out);
-        std::swap(ord_in, ord_out);
-    }
+    // the cloud id in the top bits is already in order (clouds lie back to back): every cloud is sorted on its cell bits
+    (void)end_bit;
+    B3D_TRY(radix_sort_keys(ctx, keys_in.p, n, shift, seg.off_h, seg.off, keys_out.p, ord_out.p));
     keys_in.release();
-    ord_in.release();
     // run heads -> run_start[], count -> host
     DevBuf<int32_t> run_start(ctx);
     DevBuf<int64_t> n_runs_d(ctx);
@@ -324,7 +331,9 @@ int grid_build(b3d_ctx* ctx, const T* xyz, const Segments& seg, double cell, con
     B3D_TRY(spatial_sort<T>(ctx, xyz, seg, cell, kLatSearch, *bounds, &out->sort));
     const int64_t n = out->sort.n;
     B3D_TRY(out->pts.alloc(ctx, n));
-    B3D_LAUNCH(ctx, gather_sorted_kernel<T>, ctx->grid_for(n, 256, 1, 16), 256, 0, xyz, out->sort.order.p, (int32_t)n, out->pts.p);
+    if (sizeof(T) == 8) B3D_TRY(out->rec.alloc(ctx, n));
+    B3D_LAUNCH(ctx, gather_sorted_kernel<T>, ctx->grid_for(n, 256, 1, 16), 256, 0, xyz, out->sort.order.p, (int32_t)n, out->pts.p, out->sort.keys.p,
+               out->sort.lat.p, out->sort.shift, sizeof(T) == 8 ? out->rec.p : (int4*)nullptr);
     uint32_t n_slots = 1024;
     while ((int64_t)n_slots < 2 * out->sort.n_runs) n_slots <<= 1;
     out->mask = n_slots - 1;
@@ -332,7 +341,7 @@ int grid_build(b3d_ctx* ctx, const T* xyz, const Segments& seg, double cell, con
     B3D_TRY(out->slots.alloc(ctx, n_slots));
     B3D_LAUNCH(ctx, hash_clear_kernel, ctx->grid_for(n_slots, 256, 1, 16), 256, 0, out->slots.p, n_slots);
     B3D_LAUNCH(ctx, hash_insert_kernel, ctx->grid_for(out->sort.n_runs, 256, 1, 16), 256, 0, out->sort.keys.p, out->sort.run_start.p,
-               out->sort.n_runs, out->slots.p, out->mask);
+               out->sort.n_runs, out->sort.shift, out->slots.p, out->mask);
     return B3D_OK;
 }
 template int grid_build<float>(b3d_ctx*, const float*, const Segments&, double, const std::vector<double>*, Grid<float>*);

@@ -67,7 +67,6 @@ __device__ __forceinline__ int warp_stage_box(const GridView<double>& g, int clo
     if (cn[0] > kStageMaxCells || cn[1] > kStageMaxCells || cn[2] > kStageMaxCells) return -1;
     const int ncell = (int)(cn[0] * cn[1] * cn[2]);
     if (ncell > kStageMaxCells) return -1;
-    const unsigned long long cloud_bits = (unsigned long long)cloud << g.shift;
     int total = 0;
     for (int base = 0; base < ncell; base += 32) {
         const int ci = base + lane;
@@ -77,7 +76,7 @@ __device__ __forceinline__ int warp_stage_box(const GridView<double>& g, int clo
             const int t = ci / (int)cn[2];
             const int yc = t % (int)cn[1], xc = t / (int)cn[1];
             const long long x = c0[0] + xc, y = c0[1] + yc, z = c0[2] + zc;
-            const unsigned long long key = cloud_bits | lattice_key(L, x, y, z);
+            const unsigned long long key = grid_slot_key(g.shift, cloud, x, y, z);
             int e;
             if (grid_lookup(g, key, s, e)) cnt = e - s;
         }

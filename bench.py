@@ -28,8 +28,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture of
+# this command at 64 pairs (profiles/, see profiles/README.md for the file the figure comes from)
+NCU_TRAFFIC_PER_LAUNCH = {"icp_pass_kernel": 17.628067e9 / 10.0}
+
 WORKLOAD = "config2: D435 848x480 depth pairs -> deproject + tensor voxel 5mm + hybrid normals(0.01,30) + point-to-plane ICP(0.02, 30 it)"
 PIPE = dict(voxel_size=0.005, normals_max_nn=30, normals_radius=0.01, icp_kind=1, icp_max_dist=0.02, icp_max_iter=30)
+
+
+def bench_config(world):
+    """The workload description both arms print under "config" (identical dictionaries; per-run details go under "run")."""
+    return {"workload": WORKLOAD, "unit_of_work": "one frame pair (two 848x480 depth frames)",
+            "parallelism": f"dp{world} (independent pairs per GPU, no data-path collective)",
+            "l2": "per-step working set (raw points of the batch) >> 126 MB L2: inputs larger than L2, no flush"}
 
 
 def parse():
@@ -41,6 +52,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--unique", type=int, default=8, help="distinct synthetic pairs rendered per rank (tiled up to --pairs with fresh hole masks)")
     ap.add_argument("--cpu-sample", type=int, default=6, help="pairs in the cpu_baseline sample")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (config 1, config 3, micro, config 5)")
+    ap.add_argument("--c5-points", type=int, default=10_000_000, help="config-5 leg: source points per rank")
     return ap.parse_args()
 
 
@@ -107,7 +120,8 @@ def run_reference(args):
         "impl": "reference", "metric": "icp_pairs_per_sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "mpoints_per_sec": v * 2 * n_px / 1e6,
-        "config": {"workload": WORKLOAD, "pairs_per_step": per_step},
+        "config": bench_config(args.gpus),
+        "run": {"pairs_per_step": per_step, "note": "bounded sample of the workload; the per-pair CPU cost does not depend on the batch size"},
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -164,19 +178,29 @@ class ClockSampler(threading.Thread):
 
 # ---- algorithmic bytes per launch (DESIGN.md "roofline") ---------------------------------------------------
 def kernel_bytes(name, N_raw, M_total, Mt, Ms, n_corr, icp_bytes_per_launch=None):
-    """Compulsory HBM traffic of one launch of `name` for a batch with N_raw raw points, M_total voxels (Ms sources, Mt targets)."""
+    """Compulsory (algorithmic) HBM traffic of one launch of `name` for a batch with N_raw raw points, M_total voxels (Ms sources,
+    Mt targets) -- SURVEY.md 8d. Sort passes and other temporaries are implementation traffic: they carry the bytes their launch
+    site declares (profile column 4) under "traffic_gbps" instead."""
+    icp = icp_bytes_per_launch if icp_bytes_per_launch is not None else 12 * Ms + 24 * n_corr
     table = {
         "deproject_z16_vec4_kernel": 14 * N_raw / 2,  # two launches per batch (sources, targets)
         "bounds_partial_kernel": 12 * N_raw,
-        "cell_key_kernel": 12 * N_raw + 12 * N_raw,  # points in, (key, index) out
+        "cell_key_kernel": (12 * N_raw + 8 * N_raw + 12 * Mt + 8 * Mt) / 2,  # points in, keys out; two launches (voxel lattice, target grid)
+        "chunk_key_kernel": 24 * Ms + 8 * Ms,
         "compact_kernel": 8 * N_raw + 4 * M_total,
         "voxel_reduce_short_kernel": 12 * N_raw + 12 * M_total,
         "voxel_reduce_long_kernel": 12 * N_raw * 0.05,
         "widen_kernel": 12 * M_total + 24 * M_total,
-        "gather_sorted_kernel": 24 * Mt + 32 * Mt,
+        "gather_sorted_kernel": 24 * Mt + 32 * Mt + 16 * Mt,
+        "gather_by_sorted_kernel": 24 * Mt + 24 * Mt,
+        "chunk_gather_kernel": 24 * Ms + 32 * Ms,
         "normals_kernel": 24 * Mt,  # SURVEY 8d: 12 M in + 12 M out (float32 units); neighbour gathers are cache traffic
+        "normals_staged_kernel": 24 * Mt,
+        "normals_cov2_kernel": 24 * Mt,   # the stage's compulsory bytes; its 48 M covariance hand-over to the eigen kernel is extra
+        "normals_eig2_kernel": 48 * Mt + 24 * Mt,
         # SURVEY 8d: 12 Ns + 24 nC per EXECUTED pass of a pair (finished pairs return at once); averaged over all launches
-        "icp_pass_kernel": icp_bytes_per_launch if icp_bytes_per_launch is not None else 12 * Ms + 24 * n_corr,
+        "icp_pass_kernel": icp,
+        "icp_pass2_kernel": icp,
     }
     return table.get(name)
 
@@ -273,26 +297,29 @@ def main():
     value = total_pairs / (ms_dev / 1e3)
     e2e_value = total_pairs / (ms_e2e / 1e3)
 
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    out = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         Ms = sum(r["m_source"] for r in res)
         Mt = sum(r["m_target"] for r in res)
         n_corr = sum(r["n_corr"] for r in res)
         N_raw = 2 * n_px * P
         kern_ms = sum(v[1] for v in report.values())
-        icp_launches = max(1, report.get("icp_pass_kernel", (PIPE["icp_max_iter"] + 1, 0.0))[0] // args.steps)
+        icp_name = "icp_pass2_kernel" if "icp_pass2_kernel" in report else "icp_pass_kernel"
+        icp_launches = max(1, report.get(icp_name, (PIPE["icp_max_iter"] + 1, 0.0, 0))[0] // args.steps)
         icp_bpl = sum((r["iterations"] + 1) * (12 * r["m_source"] + 24 * r["n_corr"]) for r in res) / icp_launches
         kernels = []
-        for name, (cnt, ms) in report.items():
+        for name, (cnt, ms, declared) in report.items():
             b = kernel_bytes(name, N_raw, Ms + Mt, Mt, Ms, n_corr, icp_bpl)
             kernels.append({"name": name, "launches_per_step": cnt / args.steps, "ms_per_step": ms / args.steps, "share": ms / kern_ms if kern_ms else 0.0,
-                            "avg_us": 1e3 * ms / cnt, "gbps": (b / (ms / cnt * 1e-3) / 1e9) if b else None})
+                            "avg_us": 1e3 * ms / cnt, "gbps": (b / (ms / cnt * 1e-3) / 1e9) if b else None,
+                            "traffic_gbps": (declared / (ms * 1e-3) / 1e9) if declared else None})
         top = kernels[0] if kernels else None
         roofline = None
         if top:
@@ -301,7 +328,7 @@ def main():
             # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture of this command
             # (profiles/r01n_ncu_icp_pass_p64_step_digest.txt: dram__bytes_read.sum + dram__bytes_write.sum over the ten
             # passes of one 64-pair step = 15.94 GB + 1.69 GB, divided by the ten launches -- per launch, like `achieved`)
-            traffic = {"icp_pass_kernel": 17.628067e9 / 10.0}.get(top["name"]) if P == 64 else None
+            traffic = NCU_TRAFFIC_PER_LAUNCH.get(top["name"]) if P == 64 else None
             roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                         "peak_source": peak_src, "algorithmic_bytes_per_launch": b, "avg_launch_us": top["avg_us"], "share_of_step": top["share"]}
         # whole-pipeline roofline: compulsory bytes of every stage (SURVEY 8d "pipeline per pair") over the device-timed step
@@ -319,9 +346,9 @@ def main():
             "metric": "icp_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "mpoints_per_sec": value * 2 * n_px / 1e6,
-            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": P, "global_pairs_per_step": P * world, "parallelism": f"dp{world} (independent pairs per GPU, no collective)",
-                       "l2": f"per-step working set {N_raw * 12 / 1e6:.0f} MB of raw points >> 126 MB L2 (inputs larger than L2, no flush)",
-                       "avg_icp_iterations": float(np.mean(iters)), "voxels_per_frame": (Ms + Mt) / (2 * P)},
+            "config": bench_config(world),
+            "run": {"pairs_per_gpu_per_step": P, "global_pairs_per_step": P * world, "raw_points_mb_per_step": N_raw * 12 / 1e6,
+                    "avg_icp_iterations": float(np.mean(iters)), "voxels_per_frame": (Ms + Mt) / (2 * P)},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * P * n_px * 2), "d2h_bytes_per_step": int(P * 176),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
@@ -329,9 +356,31 @@ def main():
             "roofline": roofline,
             "pipeline_roofline": {"achieved": pipe_gbps, "peak": peak, "unit": "GB/s", "frac": pipe_gbps / peak, "algorithmic_bytes_per_step": pipe_bytes},
             "cpu_baseline": cpu_base,
-            "kernels": kernels[:12],
+            "kernels": kernels[:16],
             "profiled_ms_per_step": ms_prof / args.steps,
         }
+    # ---- extra legs, outside the headline's timed region: the other BASELINE configurations ----------------------------------
+    extra = {}
+    if not args.no_extra:
+        from b200recon import benchmarks as B
+        src_d = tgt_d = src_h = tgt_h = None  # release the headline batch before the large extra legs
+        torch.cuda.empty_cache()
+        peak_x = peak if rank == 0 else None
+        if world == 1:
+            for name, fn in (("config1", lambda: B.config1_leg(local_rank, peak_gbs=peak_x)), ("config3", lambda: B.config3_leg(local_rank, peak_gbs=peak_x)),
+                             ("micro_voxel_10m", lambda: B.micro_voxel_leg(local_rank, peak_gbs=peak_x))):
+                try:
+                    extra[name] = fn()
+                except Exception as e:  # a failing extra leg must not take the headline line with it
+                    extra[name] = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            c5 = B.config5_leg(world, rank, local_rank, points_per_rank=args.c5_points, peak_gbs=peak_x)
+        except Exception as e:
+            c5 = {"error": f"{type(e).__name__}: {e}"}
+        if rank == 0:
+            extra["config5"] = c5
+    if rank == 0:
+        out["extra"] = extra
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -56,7 +56,7 @@ int b3d_ctx_synchronize(b3d_ctx* ctx);
 int64_t b3d_ctx_launch_count(b3d_ctx* ctx);
 /* Per-kernel device timing for bench.py's roofline: with profiling enabled every launch is bracketed by CUDA events on the
  * context's stream. b3d_ctx_profile_report writes "<kernel>\t<launches>\t<total_ms>\n" lines (descending total time) into
- * buf and clears the records; it returns the bytes needed (call with cap 0 to size the buffer). */
+ * buf (a fourth column carries the bytes the launch sites declared, 0 if none) and clears the records; it returns the bytes needed (call with cap 0 to size the buffer). */
 int b3d_ctx_profile(b3d_ctx* ctx, int enable);
 int64_t b3d_ctx_profile_report(b3d_ctx* ctx, char* buf, int64_t cap);
 
