@@ -89,6 +89,8 @@ def get_context(device=0):
     pool = getattr(_tls, "pool", None)
     if pool is None:
         pool = _tls.pool = {}
+    if not torch.cuda.is_available():
+        raise RuntimeError("b200recon needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     # one context per (device, current torch stream): a caller inside `with torch.cuda.stream(s)` gets a context whose
     # kernels run on s, like the torch allocations and copies around the call
     key = (d, int(torch.cuda.current_stream(d).cuda_stream))

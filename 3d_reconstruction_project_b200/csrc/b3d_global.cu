@@ -189,6 +189,29 @@ __global__ void __launch_bounds__(128) ransac_validate_kernel(GridView<double> s
 }
 
 
+// Inliers of the CORRESPONDENCE SET under every surviving hypothesis (EvaluateInlierCorrespondenceRatio of the library: the
+// exit condition of the RANSAC loop uses this share, not the fitness over the whole source). blockIdx.y = survivor.
+__global__ void __launch_bounds__(128) ransac_corres_inliers_kernel(const double* __restrict__ src, const double* __restrict__ tgt,
+                                                                    const int32_t* __restrict__ corres, long long nc, double r2,
+                                                                    const double* __restrict__ pass_T, unsigned int* __restrict__ inl) {
+    const int h = blockIdx.y;
+    __shared__ double sT[12];
+    if (threadIdx.x < 12) sT[threadIdx.x] = pass_T[12 * (int64_t)h + threadIdx.x];
+    __syncthreads();
+    unsigned int c = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += (long long)gridDim.x * blockDim.x) {
+        const double* p = src + 3 * (int64_t)corres[2 * i];
+        const double* g = tgt + 3 * (int64_t)corres[2 * i + 1];
+        const double e0 = (sT[0] * p[0] + sT[1] * p[1] + sT[2] * p[2] + sT[3]) - g[0];
+        const double e1 = (sT[4] * p[0] + sT[5] * p[1] + sT[6] * p[2] + sT[7]) - g[1];
+        const double e2 = (sT[8] * p[0] + sT[9] * p[1] + sT[10] * p[2] + sT[11]) - g[2];
+        if ((e0 * e0 + e1 * e1) + e2 * e2 < r2) ++c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c > 0) atomicAdd(&inl[h], c);
+}
+
 // ---- Fast Global Registration (registration_fgr_based_on_feature_matching -- test/check6.py:236-240, check7.py:245, check8.py:244) ----
 // Zhou, Park, Koltun 2016 as the library runs it: both clouds centred and scaled by the largest centred norm, mutual nearest
 // features, tuple test (three random matches must keep their edge lengths within tuple_scale on both clouds), then 64
@@ -445,16 +468,17 @@ extern "C" int b3d_ransac_correspondence(b3d_ctx* ctx, const double* src, int64_
     DevBuf<int> n_pass;
     DevBuf<long long> pass_itr;
     DevBuf<double> pass_T;
-    DevBuf<unsigned int> cnt;
+    DevBuf<unsigned int> cnt, inl;
     DevBuf<unsigned long long> sumq;
     B3D_TRY(n_pass.alloc(ctx, 1));
+    B3D_TRY(inl.alloc(ctx, R));
     B3D_TRY(pass_itr.alloc(ctx, R));
     B3D_TRY(pass_T.alloc(ctx, (size_t)R * 12));
     B3D_TRY(cnt.alloc(ctx, R));
     B3D_TRY(sumq.alloc(ctx, R));
     std::vector<long long> itr_h(R);
     std::vector<double> T_h((size_t)R * 12);
-    std::vector<unsigned int> cnt_h(R);
+    std::vector<unsigned int> cnt_h(R), inl_h(R);
     std::vector<unsigned long long> sumq_h(R);
     std::vector<int> order(R);
     const double r2 = max_dist * max_dist;
@@ -476,6 +500,10 @@ extern "C" int b3d_ransac_correspondence(b3d_ctx* ctx, const double* src, int64_
         B3D_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)S * sizeof(unsigned int), ctx->stream));
         B3D_CUDA(cudaMemsetAsync(sumq.p, 0, (size_t)S * sizeof(unsigned long long), ctx->stream));
         B3D_LAUNCH(ctx, ransac_validate_kernel, dim3(vblocks, S), 128, 0, sgrid.view(), tgrid.view(), rmax, r2, q_scale, pass_T.p, cnt.p, sumq.p);
+        B3D_CUDA(cudaMemsetAsync(inl.p, 0, (size_t)S * sizeof(unsigned int), ctx->stream));
+        B3D_LAUNCH(ctx, ransac_corres_inliers_kernel, dim3((unsigned int)std::min<int64_t>((nc + 127) / 128, 148 * 4), S), 128, 0, src, tgt, corres,
+                   (long long)nc, r2, pass_T.p, inl.p);
+        B3D_TRY(ctx->download(inl_h.data(), inl.p, (size_t)S * sizeof(unsigned int)));
         B3D_TRY(ctx->download(itr_h.data(), pass_itr.p, (size_t)S * sizeof(long long)));
         B3D_TRY(ctx->download(T_h.data(), pass_T.p, (size_t)S * 12 * sizeof(double)));
         B3D_TRY(ctx->download(cnt_h.data(), cnt.p, (size_t)S * sizeof(unsigned int)));
@@ -498,9 +526,12 @@ extern "C" int b3d_ransac_correspondence(b3d_ctx* ctx, const double* src, int64_
             best_cnt = c;
             best_sumq = sumq_h[h];
             for (int k = 0; k < 12; ++k) result_h->transformation[k] = T_h[(size_t)h * 12 + k];
-            const double ratio = (double)c / (double)nc;
-            const double est = std::log(1.0 - confidence) / std::log(1.0 - std::pow(ratio, ransac_n));
-            if (est < (double)est_k) est_k = (int64_t)std::ceil(est);
+            // exit condition: the inlier share of the correspondence set under this hypothesis (Open3D >= 0.13)
+            const double ratio = std::min(1.0, (double)inl_h[h] / (double)nc);
+            if (ratio > 0.0) {
+                const double est = ratio >= 1.0 ? 0.0 : std::log(1.0 - confidence) / std::log(1.0 - std::pow(ratio, ransac_n));
+                if (est < (double)est_k) est_k = (int64_t)std::ceil(est);
+            }
         }
     }
     result_h->iterations = std::min<int64_t>(r0, std::min(est_k, max_iteration));

@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
 #define B3D_ICP2_CAP 380
 #endif
 #ifndef B3D_ICP2_MIN_BLOCKS
-#define B3D_ICP2_MIN_BLOCKS 6
+#define B3D_ICP2_MIN_BLOCKS 4
 #endif
 constexpr int kIcp2Cap = B3D_ICP2_CAP;  // raw cell records per batch (+4 scan padding = 384 x 16 bytes)
 using Icp2Smem = StageSmem<kIcp2Cap>;
@@ -768,6 +768,7 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
     const bool affine = sT[12] == 0.0 && sT[13] == 0.0 && sT[14] == 0.0 && sT[15] == 1.0;
     const int32_t c_step = groups * (kIcpBlock / 32);
     int32_t c = c0 + blockIdx.x * (kIcpBlock / 32) + warp;
+#ifdef B3D_ICP2_PREFETCH
     // the next chunk's query is fetched while the current one is processed
     double4 nsp = make_double4(0.0, 0.0, 0.0, 0.0);
     float4 nkr = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -785,7 +786,9 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
             }
         }
     }
+#endif
     for (; c < c1; c += c_step) {
+#ifdef B3D_ICP2_PREFETCH
         const double4 sp = nsp;
         const float4 kr = nkr;
         const int kp = nkp;
@@ -803,6 +806,21 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                 }
             }
         }
+#else
+        // no software prefetch of the next chunk: the registers it would hold across the search are worth more (spills)
+        const int32_t si = A.chunk_start[c] + lane;
+        const bool valid = si < A.chunk_start[c + 1];
+        double4 sp = make_double4(0.0, 0.0, 0.0, 0.0);
+        float4 kr = make_float4(0.f, 0.f, 0.f, 0.f);
+        int kp = -1;
+        if (valid) {
+            sp = ld_point(A.src_sorted + si);
+            if (A.keep_ref != nullptr) {
+                kr = A.keep_ref[si];
+                kp = A.keep_pos[si];
+            }
+        }
+#endif
         double px = 0, py = 0, pz = 0;
         int oi = 0;
         if (valid) {

@@ -323,6 +323,9 @@ __global__ void __launch_bounds__(kNrmBlock) normals_staged_kernel(GridView<doub
 #ifndef B3D_NRM2_CAP
 #define B3D_NRM2_CAP 380
 #endif
+#ifndef B3D_NRM2_MIN_BLOCKS
+#define B3D_NRM2_MIN_BLOCKS 5
+#endif
 constexpr int kNrm2Cap = B3D_NRM2_CAP;
 constexpr int kNrm2List = 32;
 struct alignas(16) Nrm2Smem {
@@ -337,7 +340,7 @@ struct alignas(16) Nrm2Smem {
         k[a] = lo_;                           \
     }
 
-__global__ void __launch_bounds__(kNrmBlock, 5) normals_cov2_kernel(GridView<double> g, const int32_t* __restrict__ chunk_start,
+__global__ void __launch_bounds__(kNrmBlock, B3D_NRM2_MIN_BLOCKS) normals_cov2_kernel(GridView<double> g, const int32_t* __restrict__ chunk_start,
                                                                    const int32_t* __restrict__ chunk_off, int B, int n_chunks, int k_nn, double radius,
                                                                    double r2, double* __restrict__ cov6, int* __restrict__ todo,
                                                                    int* __restrict__ todo_count, int stats) {

@@ -103,11 +103,12 @@ class RealSensePipeline:
         try:
             self.pipeline.start(config)
         except RuntimeError as e:
+            # The reference prints the error, asks the pipeline that just failed to start for its active profile (which raises
+            # again), and exit(1)s the whole process from inside this class (realsense_pipeline.py:24-31). Same message, but the
+            # caller gets an exception it can handle and no call is made on a pipeline that never started.
             print(f"Failed to start pipeline: {e}")
-            device = self.pipeline.get_active_profile().get_device()
-            device.hardware_reset()
-            self.pipeline.stop()
-            exit(1)
+            self.pipeline = None
+            raise RuntimeError(f"Failed to start pipeline: {e}") from e
 
     def stop_pipeline(self):
         self.pipeline.stop()

@@ -5,7 +5,7 @@ import types
 
 import numpy as np
 
-from b200recon.realsense_pipeline import Intrinsics, ReplayPipeline
+from b200recon.realsense_pipeline import Intrinsics, ReplayPipeline, _ReplayFrame, _ReplayFrameset
 
 stream = types.SimpleNamespace(depth="depth", color="color")
 format = types.SimpleNamespace(z16="z16", bgr8="bgr8")
@@ -17,12 +17,13 @@ class config:
 
 
 class _EndlessReplay(ReplayPipeline):
-    """After the recorded frames: empty framesets (the reference's loop prints "No valid point cloud captured")."""
+    """After the recorded frames: empty framesets (the reference's loop prints "No valid point cloud captured"), one every
+    50 ms, for as long as the caller keeps polling -- nothing is stored per poll."""
 
     def wait_for_frames(self, timeout_ms=5000):
         if self._i >= len(self._frames):
             time.sleep(0.05)
-            self._frames.append((None, None))
+            return _ReplayFrameset(_ReplayFrame(None, self.intrinsics, self.depth_scale), _ReplayFrame(None))
         return super().wait_for_frames(timeout_ms)
 
 

@@ -1487,9 +1487,21 @@ int orc_ransac(const double* src, int64_t ns, const double* tgt, int64_t nt, con
         best_cnt = cnt;
         best_sumq = sumq;
         std::memcpy(T_out, T, 12 * sizeof(double));
-        const double ratio = (double)cnt / (double)nc;
-        const double est = std::log(1.0 - confidence) / std::log(1.0 - std::pow(ratio, n));
-        if (est < (double)est_k) est_k = (int64_t)std::ceil(est);
+        // exit condition (Open3D >= 0.13, EvaluateInlierCorrespondenceRatio): the share of the CORRESPONDENCE SET that the
+        // hypothesis maps within dmax -- not the fitness over the whole source
+        int64_t inl = 0;
+        for (int64_t c = 0; c < nc; ++c) {
+            const double* p = src + 3 * (int64_t)corres[2 * c];
+            const double* g = tgt + 3 * (int64_t)corres[2 * c + 1];
+            const double e0 = (T[0] * p[0] + T[1] * p[1] + T[2] * p[2] + T[3]) - g[0], e1 = (T[4] * p[0] + T[5] * p[1] + T[6] * p[2] + T[7]) - g[1],
+                         e2 = (T[8] * p[0] + T[9] * p[1] + T[10] * p[2] + T[11]) - g[2];
+            if ((e0 * e0 + e1 * e1) + e2 * e2 < r2) ++inl;
+        }
+        const double ratio = std::min(1.0, (double)inl / (double)nc);
+        if (ratio > 0.0) {
+            const double est = ratio >= 1.0 ? 0.0 : std::log(1.0 - confidence) / std::log(1.0 - std::pow(ratio, n));
+            if (est < (double)est_k) est_k = (int64_t)std::ceil(est);
+        }
     }
     stats[3] = (double)std::min(itr, std::min(est_k, max_iteration));
     stats[4] = (double)validated;

@@ -262,6 +262,40 @@ def test_stepwise_icp_two_shards_equal_single(b3):
     assert np.array_equal(corr, single["corr"])
 
 
+def test_sharded_icp_million_points_equals_single(b3):
+    """BASELINE config 5 at 1.2 M points on one GPU: the height-field cloud cut into three unequal shards, the 29 sums added in
+    rank order (what the all-reduce does), every shard applying the same update -> the unsharded registration's correspondence
+    set bit for bit and its transform to summation-order rounding; the known motion is recovered."""
+    from b200recon import distributed as dist, ops, synth
+    src, nrm = synth.height_field_cloud(1100, seed=4001)
+    T = synth.rigid(0.0003, -0.0002, 0.0004, (0.0008, -0.0006, 0.001))
+    tgt, tn = src @ T[:3, :3].T + T[:3, 3], nrm @ T[:3, :3].T
+    n = len(src)
+    assert n >= 1_000_000
+    kw = dict(tgt_normals=tn, rel_fitness=0.0, rel_rmse=0.0, max_iter=6)
+    single = ops.icp(1, src, tgt, 0.005, **kw)
+    cuts = [0, n // 5, n // 5 + n // 2, n]
+    shards = [dist.ShardedICP(1, src[a:b], n, tgt, 0.005, **kw) for a, b in zip(cuts[:-1], cuts[1:])]
+    for _ in range(10):
+        sums = [s.accumulate() for s in shards]
+        total = (sums[0] + sums[1]) + sums[2]
+        for t in sums:
+            t.copy_(total)
+        done = [s.update() for s in shards]
+        assert len(set(done)) == 1
+        if done[0]:
+            break
+    res = [s.finish() for s in shards]
+    for r in res[1:]:
+        assert np.array_equal(r["transformation"], res[0]["transformation"]) and r["fitness"] == res[0]["fitness"]
+    assert res[0]["iterations"] == single["iterations"] == 6
+    assert np.array_equal(np.concatenate([r["corr"] for r in res]), single["corr"])
+    assert rot_err(res[0]["transformation"][:3, :3], single["transformation"][:3, :3]) < 1e-10
+    assert np.linalg.norm(res[0]["transformation"][:3, 3] - single["transformation"][:3, 3]) < 1e-10
+    assert abs(res[0]["fitness"] - single["fitness"]) < 1e-12 and abs(res[0]["inlier_rmse"] - single["inlier_rmse"]) < 1e-12
+    assert rot_err(single["transformation"][:3, :3], T[:3, :3]) < 1e-5 and np.linalg.norm(single["transformation"][:3, 3] - T[:3, 3]) < 1e-5
+
+
 def test_fused_pass_single_rank_equals_icp(b3):
     """b3d_icp_pass_peers with a world of one: the pass kernel runs the update itself (one launch per pass, no exchange)
     and must land on exactly the single-call result."""
@@ -345,6 +379,26 @@ def test_disparity_pair_pipeline_vs_oracle(b3, kind):
         assert abs(r["fitness"] - ref["fitness"]) < 1e-4 and abs(r["inlier_rmse"] - ref["inlier_rmse"]) < 1e-4
 
 
+def test_config3_full_size_vs_oracle(b3):
+    """BASELINE config 3 at FULL size -- one 3264x2448 disparity pair (8 MP, Q of jetson_stereo_8MP x3.4) -> clouds -> tensor voxel
+    5 mm -> hybrid normals on both clouds -> covariances -> generalized ICP -- through b3d_register_disparity_pairs with HOST
+    rasters, against the oracle chain on the same rasters (~30 s of host time: the ray-cast and the CPU chain)."""
+    from b200recon import ops, synth
+    ds, dt, Q, T = synth.disparity_pair(2000, 2001)
+    assert ds.shape == (2448, 3264)
+    params = ops.make_disparity_params(3264, 2448, Q, 16, icp_kind=2)
+    got = ops.register_disparity_pairs(ds, dt, params)[0]
+    ref = oracle_disparity_pair(ds, dt, Q, 0.005, 30, 0.01, 2, 0.02, 30)
+    assert (got["m_source"], got["m_target"], got["n_raw"]) == (ref["m_source"], ref["m_target"], ref["n_raw"])  # voxel sets: same sizes
+    # stated tolerances (DESIGN.md): 1e-5 rad / 1e-5 m on the transform, 1e-4 on fitness and rmse
+    assert rot_err(got["transformation"][:3, :3], ref["transformation"][:3, :3]) < 1e-5
+    assert np.linalg.norm(got["transformation"][:3, 3] - ref["transformation"][:3, 3]) < 1e-5
+    assert abs(got["fitness"] - ref["fitness"]) < 1e-4 and abs(got["inlier_rmse"] - ref["inlier_rmse"]) < 1e-4
+    assert abs(got["iterations"] - ref["iterations"]) <= 1
+    # and the registration is right: the synthetic motion is recovered to the sensor's quantisation
+    assert rot_err(got["transformation"][:3, :3], T[:3, :3]) < 2e-3 and np.linalg.norm(got["transformation"][:3, 3] - T[:3, 3]) < 5e-3
+
+
 def test_replay_scan_example(b3, tmp_path):
     """The reference's whole flow (main.py:14-86) on replayed synthetic frames through the reference-facing classes."""
     import importlib.util
@@ -369,6 +423,25 @@ def test_replay_scan_example(b3, tmp_path):
     assert ne.has_normals() and np.allclose(np.linalg.norm(np.asarray(ne.normals), axis=1), 1.0, atol=1e-5)
     if len(processed.points):
         assert with_normals.has_normals()
+
+
+def test_reference_main_runs_unchanged(b3):
+    """the reference's own main.py, byte for byte, runs main.main() to its last line on b200recon (shims first on
+    sys.path, replayed camera, Enter fed once the frames are consumed): capture + P2P alignment in the scan thread, the saved PLY,
+    the post-processing chain and the normal estimation."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("run_reference_main", os.path.join(root, "tools", "run_reference_main.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if mod.find_reference_main() is None:
+        pytest.skip("the reference's main.py is neither in /root/reference nor in baseline/_ref")
+    rc, text, ply = mod.run(n_frames=3)
+    assert rc == 0, text[-3000:]
+    assert text.count("Captured point cloud with") == 3 and "Saved point cloud to captured_data_on_the_fly.ply" in text
+    assert "Traceback" not in text and ply is not None
+    from b200recon import plyio
+    assert len(plyio.read_point_cloud(ply).points) > 1000
 
 
 def test_pair_pipeline_degenerate_frames(b3):
