@@ -58,6 +58,7 @@ struct b3d_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;  // host -> device copies that overlap the kernels of `stream` (created on first use)
     int sm_count = 148;
     int64_t launches = 0;      // hand-written kernels
     void* pinned = nullptr;    // pinned host staging block (results, counters); valid until the next call that uses it

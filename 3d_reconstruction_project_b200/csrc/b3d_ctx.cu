@@ -279,6 +279,7 @@ int b3d_ctx_destroy(b3d_ctx* ctx) {
         cudaEventDestroy(r.e1);
     }
     for (auto e : ctx->prof_pool) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return B3D_OK;

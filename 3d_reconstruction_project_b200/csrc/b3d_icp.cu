@@ -736,6 +736,12 @@ __device__ __noinline__ void icp2_finish_pair(const IcpKernelArgs& A, int pair, 
     }
 }
 
+// cold: transforms with a projective last row (PointCloud::Transform divides by w)
+__device__ __noinline__ void icp2_perspective(const double* T, double x, double y, double z, double* px, double* py, double* pz) {
+    const double w = T[12] * x + T[13] * y + T[14] * z + T[15];
+    *px /= w; *py /= w; *pz /= w;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kernel(const __grid_constant__ IcpKernelArgs A) {
     extern __shared__ __align__(16) unsigned char icp2_smem[];
@@ -760,11 +766,12 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
     uint32_t parity = 0;
     const UnitFrame F = unit_frame(A.grid.lat[pair], A.grid.shift);
     const double inv_pm2 = (1.0 / F.per_m) * (1.0 / F.per_m);  // metres^2 per unit^2
+    const float inv_pm = (float)(1.0 / F.per_m);                   // metres per unit
     int op_p, op_q;
     icp_sum_operands(KIND, lane, op_p, op_q);
     double (*rows)[kIcpRow] = reinterpret_cast<double (*)[kIcpRow]>(S.buf);
     double acc = 0.0;  // lane j: running total of sum j
-    const double dmax = sqrt(A.r2);
+    const float dmax_up = (float)sqrt(A.r2) * 1.000001f;  // d_max, rounded up
     const bool affine = sT[12] == 0.0 && sT[13] == 0.0 && sT[14] == 0.0 && sT[15] == 1.0;
     const int32_t c_step = groups * (kIcpBlock / 32);
     int32_t c = c0 + blockIdx.x * (kIcpBlock / 32) + warp;
@@ -830,56 +837,62 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
             px = sT[0] * x + sT[1] * y + sT[2] * z + sT[3];
             py = sT[4] * x + sT[5] * y + sT[6] * z + sT[7];
             pz = sT[8] * x + sT[9] * y + sT[10] * z + sT[11];
-            if (!affine) {
-                const double w = sT[12] * x + sT[13] * y + sT[14] * z + sT[15];
-                px /= w; py /= w; pz /= w;
-            }
+            if (!affine) icp2_perspective(sT, x, y, z, &px, &py, &pz);
         }
         // ---- correspondence: sticky check, then one staged search bounded by the distance to the previous partner ---------
         double d2 = 0.0;
         int idx = 0, pos = -1;
         double4 q = make_double4(0.0, 0.0, 0.0, 0.0);  // the partner's point record
         bool need = valid;
-        double reach = dmax;  // this lane's search radius
+        float reach = dmax_up;  // this lane's search radius (float32, rounded up where it matters)
         if (valid && A.keep_ref != nullptr) {
-            const double mx = px - (double)kr.x, my = py - (double)kr.y, mz = pz - (double)kr.z;
-            // movement since the last search (+ the float rounding of the stored position)
-            const double moved = sqrt(mx * mx + my * my + mz * mz) + 2.0e-7 * (fabs(px) + fabs(py) + fabs(pz));
-            const double lim = (double)kr.w;  // every other target point was at least this far from the stored position (0: unknown)
+            // Everything here is a conservative float32 bound: movement and distances rounded UP, the stored bound was rounded DOWN.
+            // movement since the last search (+ the float roundings of the stored and of the current position)
+            const float pxf = (float)px, pyf = (float)py, pzf = (float)pz;
+            const float mx = pxf - kr.x, my = pyf - kr.y, mz = pzf - kr.z;
+            const float moved = sqrtf(fmaf(mz, mz, fmaf(my, my, mx * mx))) * 1.000001f + 4.0e-7f * (fabsf(pxf) + fabsf(pyf) + fabsf(pzf));
+            const float lim = kr.w;  // every other target point was at least this far from the stored position (0: unknown)
             if (kp >= 0) {
                 q = ld_point(A.grid.pts + kp);
                 const double dk = dist2<double>(px - q.x, py - q.y, pz - q.z);
-                const double u = sqrt(dk);
-                if (u * (1.0 + 1e-12) + moved < lim) {  // still strictly nearer than anything else can be
+                const float u = sqrtf((float)dk) * 1.000001f;
+                if ((u + moved) * 1.000001f < lim) {  // still strictly nearer than anything else can be
                     need = false;
                     pos = kp;
                     d2 = dk;
                     idx = point_index(q);
                 } else {
-                    const double slack = fmin(fmax(0.5 * moved, 0.01 * dmax), 0.1 * dmax);
-                    reach = fmin(u * (1.0 + 1e-9) + slack, dmax);  // nothing beyond d_max counts anyway
+                    const float slack = fminf(fmaxf(0.5f * moved, 0.01f * dmax_up), 0.1f * dmax_up);
+                    reach = fminf(u + slack, dmax_up);  // nothing beyond d_max counts anyway
                 }
-            } else if (lim > 0.0) {
-                if (dmax * (1.0 + 1e-12) + moved < lim) need = false;  // nothing was within lim, nothing can be within d_max now
-                else if (moved < 0.5 * (kIcpReach2 - 1.0) * dmax) reach = dmax * kIcpReach2;
+            } else if (lim > 0.0f) {
+                if ((dmax_up + moved) * 1.000001f < lim) need = false;  // nothing was within lim, nothing can be within d_max now
+                else if (moved < 0.5f * ((float)kIcpReach2 - 1.0f) * dmax_up) reach = dmax_up * (float)kIcpReach2;
             }
         }
         const unsigned int need_mask = __ballot_sync(0xffffffffu, need);
+#ifdef B3D_ICP2_STATS
         if (A.stats && lane == 0) {
             if (need_mask == 0u) atomicAdd(&g_icp_stats[6], 1ull);
             atomicAdd(&g_icp_stats[7], (unsigned long long)__popc(need_mask));
         }
+#endif
         if (need_mask != 0u) {
             // the chunk's box in fixed-point units of the target grid: every searching lane's ball, one unit of margin for the
             // floor() of the records and one for the roundings here
             const double ux = unit_coord_of_query(px, F.ox, F.per_m), uy = unit_coord_of_query(py, F.oy, F.per_m), uz = unit_coord_of_query(pz, F.oz, F.per_m);
-            const double ru = reach * F.per_m * (1.0 + 1e-12) + 2.0;
+            const double ru = (double)reach * F.per_m + 2.0;
             int lox = need ? unit_floor_clamped(ux - ru) : 0x7fffffff, loy = need ? unit_floor_clamped(uy - ru) : 0x7fffffff,
                 loz = need ? unit_floor_clamped(uz - ru) : 0x7fffffff;
             int hix = need ? unit_ceil_clamped(ux + ru) : (int)0x80000000, hiy = need ? unit_ceil_clamped(uy + ru) : (int)0x80000000,
                 hiz = need ? unit_ceil_clamped(uz + ru) : (int)0x80000000;
-            lox = max(__reduce_min_sync(0xffffffffu, lox), 0); loy = max(__reduce_min_sync(0xffffffffu, loy), 0); loz = max(__reduce_min_sync(0xffffffffu, loz), 0);
+            lox = __reduce_min_sync(0xffffffffu, lox); loy = __reduce_min_sync(0xffffffffu, loy); loz = __reduce_min_sync(0xffffffffu, loz);
             hix = __reduce_max_sync(0xffffffffu, hix); hiy = __reduce_max_sync(0xffffffffu, hiy); hiz = __reduce_max_sync(0xffffffffu, hiz);
+            // how far this lane's query is from the faces of the (unclamped) box: every target point that is NOT staged lies
+            // outside the box, i.e. at least this far away -- usually well beyond the lane's own reach (metres, rounded down)
+            const float d_out = (float)(fmin(fmin(fmin(ux - (double)lox, (double)hix - ux), fmin(uy - (double)loy, (double)hiy - uy)),
+                                             fmin(uz - (double)loz, (double)hiz - uz)) - 2.0) * inv_pm * 0.999999f;
+            lox = max(lox, 0); loy = max(loy, 0); loz = max(loz, 0);
             // this lane's query as an offset from the box centre (the centre stage2_run uses)
             const int ccx = (int)(((long long)lox + hix) >> 1), ccy = (int)(((long long)loy + hiy) >> 1), ccz = (int)(((long long)loz + hiz) >> 1);
             const double qdx = ux - (double)ccx, qdy = uy - (double)ccy, qdz = uz - (double)ccz;
@@ -896,6 +909,7 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                 if (!need) return;
                 float b = best, s2 = second;
                 int grp = -1;
+#pragma unroll 2
                 for (int gi = 0; gi < kept; gi += 4) {
                     const float ta = dot_t(S.buf[gi], fx, fy, fz), tb = dot_t(S.buf[gi + 1], fx, fy, fz);
                     const float tc = dot_t(S.buf[gi + 2], fx, fy, fz), td = dot_t(S.buf[gi + 3], fx, fy, fz);
@@ -918,12 +932,14 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                 second = s2;
             };
             const int nb = stage2_run<kIcp2Cap>(A.grid, F, pair, lox, loy, loz, hix, hiy, hiz, S, parity, scan);
+#ifdef B3D_ICP2_STATS
             if (A.stats && lane == 0) {
                 atomicAdd(&g_icp_stats[0], 1ull);
                 if (nb < 0) atomicAdd(&g_icp_stats[2], 1ull);
                 else atomicAdd(&g_icp_stats[3], (unsigned long long)last_kept);
                 if (nb > 1) atomicAdd(&g_icp_stats[1], 1ull);
             }
+#endif
             double others2 = 3.0e38;  // lower bound of the squared distance (metres) of every target point but the winner
             bool bounded = nb >= 0;   // every target point within `reach` of the query was looked at
             if (need) {
@@ -954,7 +970,7 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                 // what this search proved: the nearest point (if any within reach) and that every other point is at least
                 // min(runner-up, reach) away; stored rounded down
                 float lbf = 0.f;
-                if (bounded) lbf = (float)(fmin(sqrt(others2), reach) * (1.0 - 1.0e-6));
+                if (bounded) lbf = fminf(sqrtf((float)fmin(others2, 1.0e30)) * 0.999999f, fmaxf(d_out, reach * 0.999999f));
                 A.keep_ref[si] = make_float4((float)px, (float)py, (float)pz, lbf);
                 A.keep_pos[si] = pos;
             }

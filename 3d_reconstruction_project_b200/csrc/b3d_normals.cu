@@ -321,16 +321,16 @@ __global__ void __launch_bounds__(kNrmBlock) normals_staged_kernel(GridView<doub
 // Points that need the k-nearest cut (more than k in-radius neighbours, or more than 32), or whose box takes more than one
 // staging batch, are queued for the per-lane kernel exactly as before (their covariance slot is marked).
 #ifndef B3D_NRM2_CAP
-#define B3D_NRM2_CAP 380
+#define B3D_NRM2_CAP 476
 #endif
 #ifndef B3D_NRM2_MIN_BLOCKS
-#define B3D_NRM2_MIN_BLOCKS 5
+#define B3D_NRM2_MIN_BLOCKS 4
 #endif
 constexpr int kNrm2Cap = B3D_NRM2_CAP;
 constexpr int kNrm2List = 32;
 struct alignas(16) Nrm2Smem {
     StageSmem<kNrm2Cap> stage;
-    unsigned char list[32][kNrm2List + 4];  // per lane: candidate slots inside the radius, scan order (row stride 36 bytes)
+    unsigned int keys[32][kNrm2List + 1];  // per lane: (float bits of d2, low 9 bits = candidate slot) of the in-radius candidates (row stride 33 words)
 };
 
 #define B3D_CE(a, b)                          \
@@ -340,17 +340,37 @@ struct alignas(16) Nrm2Smem {
         k[a] = lo_;                           \
     }
 
+// Orders the first n (<= 32) keys of a lane's list ascending: into registers, a sorting network sized by the longest list of
+// the warp (uniform control flow), back to shared memory. Out of line: one copy of the unrolled networks, called once per chunk.
+__device__ __noinline__ void nrm2_sort_keys(unsigned int* __restrict__ list, int n, int nmax) {
+    unsigned int k[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) k[j] = j < n ? list[j] : 0xffffffffu;
+    if (nmax <= 16) {
+        B3D_SORTNET_16(B3D_CE)
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < n) list[j] = k[j];
+    } else {
+        B3D_SORTNET_32(B3D_CE)
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < n) list[j] = k[j];
+    }
+}
+#undef B3D_CE
+
 __global__ void __launch_bounds__(kNrmBlock, B3D_NRM2_MIN_BLOCKS) normals_cov2_kernel(GridView<double> g, const int32_t* __restrict__ chunk_start,
-                                                                   const int32_t* __restrict__ chunk_off, int B, int n_chunks, int k_nn, double radius,
-                                                                   double r2, double* __restrict__ cov6, int* __restrict__ todo,
-                                                                   int* __restrict__ todo_count, int stats) {
+                                                                                     const int32_t* __restrict__ chunk_off, int B, int n_chunks, int k_nn,
+                                                                                     double radius, double r2, double* __restrict__ cov6,
+                                                                                     int* __restrict__ todo, int* __restrict__ todo_count, int stats) {
     extern __shared__ __align__(16) unsigned char nrm2_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Nrm2Smem& W = reinterpret_cast<Nrm2Smem*>(nrm2_smem)[warp];
     auto& S = W.stage;
     stage2_init_barrier(&S.mbar);
     uint32_t parity = 0;
-    unsigned char* list = W.list[lane];
+    unsigned int* list = W.keys[lane];
     int cur_cloud = -1;
     UnitFrame F = {};
     float r2u = 0.f;   // radius^2 in units^2
@@ -408,24 +428,26 @@ __global__ void __launch_bounds__(kNrmBlock, B3D_NRM2_MIN_BLOCKS) normals_cov2_k
                         acc = dist2<double>(qx - pj.x, qy - pj.y, qz - pj.z) < r2;
                     }
                     if (acc) {
-                        if (n < kNrm2List) list[n] = (unsigned char)j;
+                        // ascending keys = (d2, scan order): the float bits of d2 with the low 9 bits replaced by the slot
+                        if (n < kNrm2List) list[n] = (__float_as_uint(fmaxf(d2f, 0.0f)) & ~511u) | (unsigned int)j;
                         ++n;
                     }
                 }
             }
         };
         const int nb = stage2_run<kNrm2Cap>(g, F, cloud, lox, loy, loz, hix, hiy, hiz, S, parity, scan);
+#ifdef B3D_NRM2_STATS
         const unsigned int valid_mask = __ballot_sync(0xffffffffu, valid);
         if (stats && lane == 0) {
             atomicAdd(&g_nrm_stats[0], 1ull);
             if (nb != 1) atomicAdd(&g_nrm_stats[1], 1ull); else atomicAdd(&g_nrm_stats[3], (unsigned long long)kept_all);
             atomicAdd(&g_nrm_stats[4], (unsigned long long)__popc(valid_mask));
         }
-        // one batch holds every candidate (slots fit a byte); anything else goes to the per-lane kernel
-        const bool chunk_ok = nb == 1 && kept_all <= 256;
+#endif
+        // one batch holds every candidate (slots fit 9 bits); anything else goes to the per-lane kernel
+        const bool chunk_ok = nb == 1 && kept_all <= 512;
         const bool punt = valid && (!chunk_ok || n > k_nn || n > kNrm2List);
         if (punt) {
-            if (stats && chunk_ok) atomicAdd(&g_nrm_stats[2], 1ull);
             todo[atomicAdd(todo_count, 1)] = i;
             cov6[6 * (int64_t)oi] = __longlong_as_double(0x7ff8000000000b3dll);  // marked: the eigen kernel skips it
         }
@@ -436,36 +458,16 @@ __global__ void __launch_bounds__(kNrmBlock, B3D_NRM2_MIN_BLOCKS) normals_cov2_k
             __syncwarp();
             continue;
         }
-        // ---- keys into registers: (float bits of d2 with the low 8 bits replaced by the candidate slot), ascending = (d2, scan order)
-        unsigned int k[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            k[j] = 0xffffffffu;
-            if (j < nmax && j < n) {
-                const int slot = list[j];
-                const float4 cj = S.buf[slot];
-                const float d2f = fmaf(fx, cj.x, fmaf(fy, cj.y, fmaf(fz, cj.z, cj.w))) + qq;
-                k[j] = (__float_as_uint(fmaxf(d2f, 0.0f)) & ~255u) | (unsigned int)slot;
-            }
-        }
-        if (nmax <= 8) {
-            B3D_SORTNET_8(B3D_CE)
-        } else if (nmax <= 16) {
-            B3D_SORTNET_16(B3D_CE)
-        } else {
-            B3D_SORTNET_32(B3D_CE)
-        }
+        if (nmax > 2) nrm2_sort_keys(list, n, nmax);
+        else if (n == 2 && list[1] < list[0]) { const unsigned int t = list[0]; list[0] = list[1]; list[1] = t; }
         // ---- raw-moment covariance over the neighbour set in distance order (float64 points re-gathered) ------------------
         double cu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (j < nmax && j < n) {
-                const double4 pj = ld_point(g.pts + S.pos[k[j] & 255u]);
-                const double x = pj.x, y = pj.y, z = pj.z;
-                cu[0] += x; cu[1] += y; cu[2] += z;
-                cu[3] += x * x; cu[4] += x * y; cu[5] += x * z;
-                cu[6] += y * y; cu[7] += y * z; cu[8] += z * z;
-            }
+        for (int j = 0; j < n; ++j) {
+            const double4 pj = ld_point(g.pts + S.pos[list[j] & 511u]);
+            const double x = pj.x, y = pj.y, z = pj.z;
+            cu[0] += x; cu[1] += y; cu[2] += z;
+            cu[3] += x * x; cu[4] += x * y; cu[5] += x * z;
+            cu[6] += y * y; cu[7] += y * z; cu[8] += z * z;
         }
         if (work) {
             double C[6] = {1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
@@ -487,7 +489,6 @@ __global__ void __launch_bounds__(kNrmBlock, B3D_NRM2_MIN_BLOCKS) normals_cov2_k
         __syncwarp();
     }
 }
-#undef B3D_CE
 
 // cov6[i] = {a00 a01 a02 a11 a12 a22} of point i (original index) -> unit normal, oriented against the prior
 __global__ void __launch_bounds__(256) normals_eig2_kernel(const double* __restrict__ cov6, int64_t n, const double* __restrict__ prior,

@@ -44,24 +44,12 @@ struct BackParams {
     int icp_max_iter;
 };
 
-// Everything after the deprojection: xyz holds 2P float32 clouds back to back (P sources, then P targets), raw_off their
-// offsets. n_raw_h[f] (optional) = raw points of frame f for the result records.
-static int register_clouds_f32(b3d_ctx* ctx, DevBuf<float>& xyz, const std::vector<int32_t>& raw_off, int P, const BackParams* pr,
-                               b3d_pair_result* results_h) {
+// Everything after the voxel down-sampling: vox holds the 2P down-sampled float32 clouds back to back (P sources, then P
+// targets), voff their offsets ([2P + 1]); raw_off the offsets of the raw clouds (for the result records).
+static int register_voxels_f32(b3d_ctx* ctx, DevBuf<float>& vox, const std::vector<int32_t>& voff, const std::vector<int32_t>& raw_off, int P,
+                               const BackParams* pr, b3d_pair_result* results_h) {
     const int F = 2 * P;
-    const int64_t n_total = raw_off[F];
-    // 2. tensor voxel down-sampling of all 2P frames in one sort
-    DevBuf<int32_t> raw_off_d;
-    Segments raw_seg;
-    B3D_TRY(upload_segments(ctx, raw_off, &raw_off_d, &raw_seg));
-    DevBuf<float> vox;
-    B3D_TRY(vox.alloc(ctx, (size_t)(3 * n_total)));
-    SpatialSort vs;
-    B3D_TRY((voxel_downsample_batch<float, int64_t>(ctx, xyz.p, nullptr, nullptr, raw_seg, (double)pr->voxel_size, kLatTensorVoxel, vox.p, nullptr,
-                                                     nullptr, nullptr, nullptr, &vs, nullptr)));
-    xyz.release();
-    const int64_t M = vs.n_runs;
-    const std::vector<int32_t>& voff = vs.run_off_h;  // [F+1] offsets of the down-sampled clouds
+    const int64_t M = voff[F];
     const int32_t Ms = voff[P], Mt = (int32_t)M - voff[P];
 
     // 3. to_legacy: float32 -> float64 (exact)
@@ -147,6 +135,35 @@ static int register_clouds_f32(b3d_ctx* ctx, DevBuf<float>& xyz, const std::vect
     return B3D_OK;
 }
 
+// tensor voxel down-sampling of the frames [f0, f1) of xyz (raw offsets raw_off) into vox at row *m_done; appends their offsets
+static int voxel_group(b3d_ctx* ctx, const float* xyz, const std::vector<int32_t>& raw_off, int f0, int f1, float voxel_size, DevBuf<float>& vox,
+                       std::vector<int32_t>* voff, int64_t* m_done) {
+    std::vector<int32_t> goff(f1 - f0 + 1);
+    for (int f = f0; f <= f1; ++f) goff[f - f0] = raw_off[f] - raw_off[f0];
+    DevBuf<int32_t> goff_d;
+    Segments gseg;
+    B3D_TRY(upload_segments(ctx, goff, &goff_d, &gseg));
+    SpatialSort vs;
+    B3D_TRY((voxel_downsample_batch<float, int64_t>(ctx, xyz + 3 * (int64_t)raw_off[f0], nullptr, nullptr, gseg, (double)voxel_size, kLatTensorVoxel,
+                                                     vox.p + 3 * *m_done, nullptr, nullptr, nullptr, nullptr, &vs, nullptr)));
+    for (int f = f0; f < f1; ++f) (*voff)[f + 1] = (int32_t)(*m_done + vs.run_off_h[f - f0 + 1]);
+    *m_done += vs.n_runs;
+    return B3D_OK;
+}
+
+// Everything after the deprojection: xyz holds 2P float32 clouds back to back (P sources, then P targets), raw_off their offsets.
+static int register_clouds_f32(b3d_ctx* ctx, DevBuf<float>& xyz, const std::vector<int32_t>& raw_off, int P, const BackParams* pr,
+                               b3d_pair_result* results_h) {
+    const int F = 2 * P;
+    DevBuf<float> vox;
+    B3D_TRY(vox.alloc(ctx, (size_t)(3 * (int64_t)raw_off[F])));
+    std::vector<int32_t> voff(F + 1, 0);
+    int64_t m_done = 0;
+    B3D_TRY(voxel_group(ctx, xyz.p, raw_off, 0, F, pr->voxel_size, vox, &voff, &m_done));  // all 2P frames in one sort
+    xyz.release();
+    return register_voxels_f32(ctx, vox, voff, raw_off, P, pr, results_h);
+}
+
 }  // namespace b3d
 
 using namespace b3d;
@@ -170,27 +187,60 @@ int b3d_register_depth_pairs(b3d_ctx* ctx, const b3d_pair_params* pr, const uint
     const int64_t N = (int64_t)pr->w * pr->h;
     B3D_REQUIRE(N * F < (int64_t)INT32_MAX, "batch of %d frames x %lld pixels exceeds 2^31-1 points", F, (long long)N);
 
-    // 1. depth rasters -> device (e2e leg) -> float32 points, sources first then targets
-    DevBuf<uint16_t> depth_d;
-    const uint16_t* d_src = depth_src;
-    const uint16_t* d_tgt = depth_tgt;
-    if (!device_inputs) {
-        B3D_TRY(depth_d.alloc(ctx, (size_t)(N * F)));
-        B3D_CUDA(cudaMemcpyAsync(depth_d.p, depth_src, (size_t)(N * P) * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
-        B3D_CUDA(cudaMemcpyAsync(depth_d.p + N * P, depth_tgt, (size_t)(N * P) * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
-        d_src = depth_d.p;
-        d_tgt = depth_d.p + N * P;
-    }
-    DevBuf<float> xyz;
-    B3D_TRY(xyz.alloc(ctx, (size_t)(3 * N * F)));
-    B3D_TRY(deproject_z16_batch(ctx, d_src, nullptr, pr->w, pr->h, P, pr->fx, pr->fy, pr->ppx, pr->ppy, pr->depth_scale, xyz.p, nullptr));
-    B3D_TRY(deproject_z16_batch(ctx, d_tgt, nullptr, pr->w, pr->h, P, pr->fx, pr->fy, pr->ppx, pr->ppy, pr->depth_scale, xyz.p + 3 * N * P, nullptr));
-
     std::vector<int32_t> raw_off(F + 1);
     for (int f = 0; f <= F; ++f) raw_off[f] = (int32_t)(f * N);
     BackParams bp{pr->voxel_size, pr->normals_max_nn, pr->normals_radius, pr->icp_kind, pr->icp_max_dist, pr->icp_rel_fitness, pr->icp_rel_rmse,
                   pr->icp_max_iter};
-    return register_clouds_f32(ctx, xyz, raw_off, P, &bp, results_h);
+    DevBuf<float> xyz;
+    B3D_TRY(xyz.alloc(ctx, (size_t)(3 * N * F)));
+    if (device_inputs) {
+        // 1. rasters already resident: two deprojection launches (sources, targets), one sort over all 2P frames
+        B3D_TRY(deproject_z16_batch(ctx, depth_src, nullptr, pr->w, pr->h, P, pr->fx, pr->fy, pr->ppx, pr->ppy, pr->depth_scale, xyz.p, nullptr));
+        B3D_TRY(deproject_z16_batch(ctx, depth_tgt, nullptr, pr->w, pr->h, P, pr->fx, pr->fy, pr->ppx, pr->ppy, pr->depth_scale, xyz.p + 3 * N * P, nullptr));
+        return register_clouds_f32(ctx, xyz, raw_off, P, &bp, results_h);
+    }
+    // 1'. HOST rasters (the end-to-end leg): the frames go through the front end in groups (by default the sources, then the
+    // targets); the host -> device copy of group g + 1 runs on the copy stream while group g is deprojected and voxelised on
+    // the compute stream. Per-cloud results do not depend on the grouping (every cloud is sorted on its own).
+    if (ctx->copy_stream == nullptr) B3D_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    DevBuf<uint16_t> depth_d;
+    B3D_TRY(depth_d.alloc(ctx, (size_t)(N * F)));
+    static const int halves_env = getenv("B3D_E2E_HALVES") ? atoi(getenv("B3D_E2E_HALVES")) : 1;  // groups per side; every group costs ~0.6 ms of fixed work (profiles/r02_e2e_groups.txt)
+    const int halves = std::max(1, std::min(halves_env, P));
+    struct Group { int f0, f1; };
+    std::vector<Group> groups;
+    for (int side = 0; side < 2; ++side)
+        for (int hh = 0; hh < halves; ++hh) groups.push_back({side * P + (P * hh) / halves, side * P + (P * (hh + 1)) / halves});
+    std::vector<cudaEvent_t> ev(groups.size() + 1);
+    for (auto& e : ev) B3D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // the staging block may be a recycled scratch block: the copies start after everything already queued on the compute stream
+    B3D_CUDA(cudaEventRecord(ev.back(), ctx->stream));
+    B3D_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ev.back(), 0));
+    for (size_t g = 0; g < groups.size(); ++g) {
+        const Group& G = groups[g];
+        const uint16_t* host = G.f0 < P ? depth_src + N * G.f0 : depth_tgt + N * (G.f0 - P);
+        B3D_CUDA(cudaMemcpyAsync(depth_d.p + N * G.f0, host, (size_t)(N * (G.f1 - G.f0)) * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+        B3D_CUDA(cudaEventRecord(ev[g], ctx->copy_stream));
+    }
+    DevBuf<float> vox;
+    B3D_TRY(vox.alloc(ctx, (size_t)(3 * N * F)));
+    std::vector<int32_t> voff(F + 1, 0);
+    int64_t m_done = 0;
+    int rc = B3D_OK;
+    for (size_t g = 0; g < groups.size() && rc == B3D_OK; ++g) {
+        const Group& G = groups[g];
+        if (cudaStreamWaitEvent(ctx->stream, ev[g], 0) != cudaSuccess) rc = set_error(B3D_E_CUDA, "cudaStreamWaitEvent failed");
+        if (rc == B3D_OK)
+            rc = deproject_z16_batch(ctx, depth_d.p + N * G.f0, nullptr, pr->w, pr->h, G.f1 - G.f0, pr->fx, pr->fy, pr->ppx, pr->ppy, pr->depth_scale,
+                                     xyz.p + 3 * N * G.f0, nullptr);
+        if (rc == B3D_OK) rc = voxel_group(ctx, xyz.p, raw_off, G.f0, G.f1, pr->voxel_size, vox, &voff, &m_done);
+    }
+    if (rc != B3D_OK) cudaStreamSynchronize(ctx->copy_stream);  // nothing may still write into the staging block when it is released
+    for (auto& e : ev) cudaEventDestroy(e);
+    B3D_TRY(rc);
+    depth_d.release();
+    xyz.release();
+    return register_voxels_f32(ctx, vox, voff, raw_off, P, &bp, results_h);
 }
 
 int b3d_register_disparity_pairs(b3d_ctx* ctx, const b3d_disparity_params* pr, const int16_t* disp_src, const int16_t* disp_tgt, int n_pairs,

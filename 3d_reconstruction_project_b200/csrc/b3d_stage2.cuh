@@ -70,7 +70,11 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
                  : "memory");
 }
 // orders this thread's earlier generic-proxy accesses of shared memory before later async-proxy (bulk copy) writes
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() {
+#ifndef B3D_STAGE2_NO_FENCE  // measurement only: what the proxy fences cost
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
 
 // ---- fixed-point units of a search grid ----------------------------------------------------------------------------------
 // unit shift s of a grid whose Morton keys use `shift` bits (shift / 3 per axis): 2^s units per cell, every coordinate below 2^31
@@ -101,9 +105,9 @@ __device__ __forceinline__ int unit_coord_of_point(double x, double o, double ce
 }
 // a query position in units (float64; queries may lie anywhere, also outside the grid)
 __device__ __forceinline__ double unit_coord_of_query(double x, double o, double per_m) { return (x - o) * per_m; }
-// float64 units -> int32, rounded towards -inf / +inf and clamped to the int32 range
-__device__ __forceinline__ int unit_floor_clamped(double v) { return (int)fmax(fmin(floor(v), 2147483000.0), -2147483000.0); }
-__device__ __forceinline__ int unit_ceil_clamped(double v) { return (int)fmax(fmin(ceil(v), 2147483000.0), -2147483000.0); }
+// float64 units -> int32, rounded towards -inf / +inf; the conversion instruction saturates at the int32 range (NaN -> 0)
+__device__ __forceinline__ int unit_floor_clamped(double v) { return __double2int_rd(v); }
+__device__ __forceinline__ int unit_ceil_clamped(double v) { return __double2int_ru(v); }
 
 constexpr int kStage2MaxCells = 1024;  // cells of one box; beyond that (or beyond 256 on an axis) the caller falls back
 

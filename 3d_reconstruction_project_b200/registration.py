@@ -65,12 +65,15 @@ def _run(source, target, max_correspondence_distance, init, estimation, criteria
                                "for target PointCloud.")
         kw["tgt_normals"] = np.asarray(target.normals)
     if kind == N.ICP_GENERALIZED:
+        # InitializePointCloudForGeneralizedICP works on COPIES of the inputs: covariances the caller set are used as they are,
+        # missing ones are derived here (normals by KNN(20) if absent) and never written back into the caller's clouds
         eps = estimation.epsilon
+        covs = []
         for c in (source, target):
             if not c.has_covariances():
-                c.estimate_covariances_from_normals(eps)
-        kw["src_cov"] = source.covariances.reshape(-1, 9)
-        kw["tgt_cov"] = target.covariances.reshape(-1, 9)
+                c = c.clone().estimate_covariances_from_normals(eps)
+            covs.append(c.covariances.reshape(-1, 9))
+        kw["src_cov"], kw["tgt_cov"] = covs
     if not source.has_points() or not target.has_points():
         return RegistrationResult(dict(transformation=init.copy(), fitness=0.0, inlier_rmse=0.0, iterations=0, converged=False, corr=None))
     d = ops.icp(kind, np.asarray(source.points), np.asarray(target.points), max_correspondence_distance, init=init,

@@ -27,7 +27,7 @@ PY
 for v in "$@"; do
   case $v in
     new) run new B3D_DUMMY=1 ;;
-    stats) B3D_ICP_STATS=1 timeout 300 python tools/prof_step.py --pairs 16 --stats > gpurun_out/ab_stats.log 2>&1; tail -4 gpurun_out/ab_stats.log ;;
+    stats) B3D_LIB=$PWD/variants/libb200recon_stats.so B3D_ICP_STATS=1 timeout 300 python tools/prof_step.py --pairs 16 --stats > gpurun_out/ab_stats.log 2>&1; tail -4 gpurun_out/ab_stats.log ;;
     icp_v1) run icp_v1 B3D_ICP_V1=1 ;;
     nrm_v1) run nrm_v1 B3D_NRM_V1=1 ;;
     all_v1) run all_v1 B3D_ICP_V1=1 B3D_NRM_V1=1 B3D_SORT_PAIRS=1 ;;
