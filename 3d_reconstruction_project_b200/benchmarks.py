@@ -164,22 +164,27 @@ def config5_leg(world, rank, local, points_per_rank=10_000_000, iters=10, dmax=0
             continue
         config5_run(side, 2, dmax, world, rank, local, fused)  # warm-up: allocator, symmetric-memory rendezvous, NCCL channels
         res, ms, passes, T, n_local = config5_run(side, iters, dmax, world, rank, local, fused)
-        t = torch.tensor([ms], dtype=torch.float64, device=torch.device("cuda", local))
+        t = torch.zeros(world, dtype=torch.float64, device=torch.device("cuda", local))
+        t[rank] = ms
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        runs[name] = (res, float(t.item()), passes, T, n_local)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)  # every rank's own loop time (disjoint slots: a gather)
+        per_rank = [float(v) for v in t.tolist()]
+        runs[name] = (res, max(per_rank), passes, T, n_local, per_rank)
     if rank == 0:
-        res, ms, passes, T, _ = runs["nccl"]
+        res, ms, passes, T, _, _ = runs["nccl"]
         rot, tr = synth.transform_error(res["transformation"], T)
         bytes_per_pass = 12 * n + 24 * res["n_corr"]  # whole job: every rank's shard (point-to-plane)
         out = {"workload": C5_WORKLOAD, "n_points": n, "points_per_rank": n // world, "n_gpus": world, "passes": passes, "iterations": res["iterations"],
                "fitness": res["fitness"], "inlier_rmse": res["inlier_rmse"], "rot_err_rad": rot, "trans_err_m": tr, "variants": {}}
-        for name, (r, ms_v, p_v, _, _) in runs.items():
+        for name, (r, ms_v, p_v, _, _, per_rank) in runs.items():
             per_pass = ms_v / p_v
             gb = bytes_per_pass / (per_pass * 1e-3) / 1e9
             out["variants"][name] = {"exchange": "all-reduce inside the pass kernel over peer memory (NVLink)" if name == "fused" else ("nccl all_reduce" if world > 1 else "none (one rank)"),
                                      "ms_per_pass": per_pass, "mpoints_per_sec": n / (per_pass * 1e-3) / 1e6, "algorithmic_gbps": gb,
-                                     "frac_of_n_x_peak": (gb / (peak_gbs * world)) if peak_gbs else None}
+                                     "frac_of_n_x_peak": (gb / (peak_gbs * world)) if peak_gbs else None,
+                                     # each rank's own device time of the loop: with a collective per pass every rank waits for the
+                                     # slowest shard, so the spread here is clock / launch jitter, not shard imbalance
+                                     "rank_ms_per_pass": [v / p_v for v in per_rank]}
         if "fused" in runs:
             a, b = runs["nccl"][0], runs["fused"][0]
             out["fused_equals_nccl_bitwise"] = bool(np.array_equal(a["transformation"], b["transformation"]) and a["fitness"] == b["fitness"]

@@ -66,35 +66,154 @@ __global__ void __launch_bounds__(256) chunk_key_kernel(const double* __restrict
     }
 }
 
-// gap-based chunking: runs of consecutive sorted points without a jump longer than tau; chunks = every 32 points of a run
-struct GapPred {
-    const double4* pts;
-    const uint64_t* keys;
-    int shift;
-    double tau2;
-    __device__ __forceinline__ bool operator()(int64_t i) const {
-        if (i == 0 || (keys[i] >> shift) != (keys[i - 1] >> shift)) return true;  // first point of a cloud
-        const double4 a = pts[i], b = pts[i - 1];
-        const double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
-        return dx * dx + dy * dy + dz * dz > tau2;
-    }
-};
-struct RunChunkPred {
-    const int32_t* heads;  // sorted run heads
-    const int64_t* n_heads;
-    __device__ __forceinline__ bool operator()(int64_t i) const {
-        int lo = 0, hi = (int)*n_heads;  // last head <= i
-        while (hi - lo > 1) {
-            const int m = (lo + hi) >> 1;
-            if ((int64_t)heads[m] <= i) lo = m; else hi = m;
+// Gap-based chunking in ONE pass: runs of consecutive sorted points without a jump longer than tau (and without a change of
+// cloud); a chunk starts every 32 points of a run. Two chained scans with decoupled look-back inside one kernel: first the index
+// of the last run head at or before every point (a max-scan), from it the chunk-start flags, then their prefix count (the
+// compaction). Replaces two compaction passes and a binary search per point.
+constexpr int kCutBlock = 256;
+constexpr int kCutItems = 8;
+constexpr int kCutTile = kCutBlock * kCutItems;
+
+__global__ void __launch_bounds__(kCutBlock) cut_chunks_kernel(const uint64_t* __restrict__ keys, const double4* __restrict__ pts, int shift, double tau2,
+                                                               int32_t n, unsigned long long* __restrict__ st_head, unsigned long long* __restrict__ st_count,
+                                                               unsigned int* __restrict__ ticket, int32_t* __restrict__ chunk_start,
+                                                               int64_t* __restrict__ n_chunks) {
+    __shared__ unsigned int s_tile;
+    __shared__ int s_warp[kCutBlock / 32];
+    __shared__ long long s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned int tile = s_tile;
+    const int32_t base = (int32_t)tile * kCutTile + (int32_t)threadIdx.x * kCutItems;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr unsigned long long kAgg = 1ull << 62, kPre = 2ull << 62, kMask = (1ull << 62) - 1ull;
+    // ---- run heads of this thread's items; the last one (index + 1, 0 = none) ----------------------------------------------
+    unsigned int head_bits = 0;
+    int last = 0;
+    {
+        double4 prev = make_double4(0, 0, 0, 0);
+        uint64_t prev_cloud = 0;
+        if (base > 0 && base - 1 < n) {
+            prev = pts[base - 1];
+            prev_cloud = keys[base - 1] >> shift;
         }
-        return ((i - (int64_t)heads[lo]) & 31) == 0;
+#pragma unroll
+        for (int k = 0; k < kCutItems; ++k) {
+            const int32_t i = base + k;
+            if (i < n) {
+                const double4 a = pts[i];
+                const uint64_t cl = keys[i] >> shift;
+                const double dx = a.x - prev.x, dy = a.y - prev.y, dz = a.z - prev.z;
+                const bool head = i == 0 || cl != prev_cloud || dx * dx + dy * dy + dz * dz > tau2;
+                if (head) {
+                    head_bits |= 1u << k;
+                    last = i + 1;
+                }
+                prev = a;
+                prev_cloud = cl;
+            }
+        }
     }
-};
-struct ChunkEmit {
-    int32_t* chunk_start;
-    __device__ __forceinline__ void operator()(int64_t i, int64_t slot) const { chunk_start[slot] = (int32_t)i; }
-};
+    // inclusive max-scan of `last` over the block -> last head at or before the END of every thread's items, within the tile
+    int incl = last;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl = max(incl, v);
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int before = 0;  // last head (index + 1) in the tile BEFORE this thread's items
+    {
+        int wmax = 0;
+        for (int w = 0; w < warp; ++w) wmax = max(wmax, s_warp[w]);
+        const int up = __shfl_up_sync(0xffffffffu, incl, 1);
+        before = max(wmax, lane > 0 ? up : 0);
+    }
+    int tile_last = 0;
+    for (int w = 0; w < kCutBlock / 32; ++w) tile_last = max(tile_last, s_warp[w]);
+    __syncthreads();
+    // look-back 1: last head before the tile
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* st = st_head;
+        long long prefix = 0;
+        if (tile == 0) {
+            st[0] = kPre | (unsigned long long)tile_last;
+        } else {
+            st[tile] = kAgg | (unsigned long long)tile_last;
+            __threadfence();
+            long long look = (long long)tile - 1;
+            while (true) {
+                const unsigned long long v = st[look];
+                if (v == 0) continue;
+                prefix = max(prefix, (long long)(v & kMask));
+                if ((v & kPre) || prefix > 0) break;  // any head ends the search: earlier tiles cannot hold a later one
+                --look;
+            }
+            st[tile] = kPre | (unsigned long long)max(prefix, (long long)tile_last);
+        }
+        s_prefix = prefix;
+    }
+    __syncthreads();
+    int run_head = max(before, (int)s_prefix);  // index + 1 of the run head governing this thread's first item (>= 1: point 0 is a head)
+    __syncthreads();
+    // ---- chunk starts: every 32 points of a run ----------------------------------------------------------------------------
+    unsigned int flags = 0;
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < kCutItems; ++k) {
+        const int32_t i = base + k;
+        if (i < n) {
+            if (head_bits & (1u << k)) run_head = i + 1;
+            if (((i - (run_head - 1)) & 31) == 0) {
+                flags |= 1u << k;
+                ++cnt;
+            }
+        }
+    }
+    int cincl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, cincl, o);
+        if (lane >= o) cincl += v;
+    }
+    if (lane == 31) s_warp[warp] = cincl;
+    __syncthreads();
+    int warp_base = 0, tile_total = 0;
+    for (int w = 0; w < kCutBlock / 32; ++w) {
+        const int v = s_warp[w];
+        if (w < warp) warp_base += v;
+        tile_total += v;
+    }
+    // look-back 2: chunk starts before the tile
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* st = st_count;
+        long long prefix = 0;
+        if (tile == 0) {
+            st[0] = kPre | (unsigned long long)tile_total;
+        } else {
+            st[tile] = kAgg | (unsigned long long)tile_total;
+            __threadfence();
+            long long look = (long long)tile - 1;
+            while (true) {
+                const unsigned long long v = st[look];
+                if (v == 0) continue;
+                prefix += (long long)(v & kMask);
+                if (v & kPre) break;
+                --look;
+            }
+            st[tile] = kPre | (unsigned long long)(prefix + tile_total);
+        }
+        s_prefix = prefix;
+        if ((int64_t)(tile + 1) * kCutTile >= n) *n_chunks = prefix + tile_total;
+    }
+    __syncthreads();
+    int64_t slot = s_prefix + warp_base + cincl - cnt;
+#pragma unroll
+    for (int k = 0; k < kCutItems; ++k)
+        if (flags & (1u << k)) chunk_start[slot++] = base + k;
+}
+
 __global__ void chunk_sentinel_kernel(int32_t* chunk_start, const int64_t* n_chunks, int32_t n) { chunk_start[*n_chunks] = n; }
 
 // chunk_off[b] = first chunk of cloud b (chunk_off[B] = n_chunks)
@@ -126,15 +245,24 @@ static int cut_chunks(b3d_ctx* ctx, const uint64_t* keys, const double4* pts, in
                       int32_t* chunk_start, int64_t* n_chunks_d) {
     // runs of spatially consecutive points (no jump longer than 1.5 cells), then a chunk every 32 points of a run: chunks
     // are full except at the end of a run, and compact because the curve does not jump inside a run
-    DevBuf<int32_t> heads;
-    DevBuf<int64_t> n_heads;
-    B3D_TRY(heads.alloc(ctx, (size_t)n));
-    B3D_TRY(n_heads.alloc(ctx, 1));
     double tau_cells = 1.5;  // measured on config 2 (1.0 / 1.25 / 1.5 / 2.0 / 3.0 cells: 49.7 / 47.9 / 47.5 / 47.8 / 51.5 ms per step)
     if (const char* e = getenv("B3D_CHUNK_GAP")) tau_cells = atof(e);
     const double tau = tau_cells * cell;
-    B3D_TRY(compact(ctx, GapPred{pts, keys, shift, tau * tau}, ChunkEmit{heads.p}, n, n_heads.p));
-    return compact(ctx, RunChunkPred{heads.p, n_heads.p}, ChunkEmit{chunk_start}, n, n_chunks_d);
+    const int64_t tiles = ((int64_t)n + kCutTile - 1) / kCutTile;
+    if (tiles == 0) {
+        B3D_CUDA(cudaMemsetAsync(n_chunks_d, 0, sizeof(int64_t), ctx->stream));
+        return B3D_OK;
+    }
+    DevBuf<unsigned long long> status;  // [2][tiles]: look-back words of the two scans
+    DevBuf<unsigned int> ticket;
+    B3D_TRY(status.alloc(ctx, (size_t)(2 * tiles)));
+    B3D_TRY(ticket.alloc(ctx, 1));
+    B3D_CUDA(cudaMemsetAsync(status.p, 0, (size_t)(2 * tiles) * sizeof(unsigned long long), ctx->stream));
+    B3D_CUDA(cudaMemsetAsync(ticket.p, 0, sizeof(unsigned int), ctx->stream));
+    B3D_LAUNCH(ctx, cut_chunks_kernel, (unsigned int)tiles, kCutBlock, 0, keys, pts, shift, tau * tau, n, status.p, status.p + tiles, ticket.p, chunk_start,
+               n_chunks_d);
+    ctx->prof_bytes((int64_t)n * 40);
+    return B3D_OK;
 }
 
 int build_query_chunks(b3d_ctx* ctx, const double* pts, const int32_t* off_d, const std::vector<int32_t>& off_h, const SpatialSort& lattices,

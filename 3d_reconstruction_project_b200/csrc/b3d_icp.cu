@@ -606,9 +606,7 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
 #endif
 constexpr int kIcp2Cap = B3D_ICP2_CAP;  // raw cell records per batch (+4 scan padding = 384 x 16 bytes)
 using Icp2Smem = StageSmem<kIcp2Cap>;
-static_assert(sizeof(float4) * (kIcp2Cap + 4) >= sizeof(double) * 32 * kIcpRow, "the row buffer of the reduction aliases the candidate buffer");
-
-__device__ __forceinline__ float dot_t(const float4& c, float fx, float fy, float fz) { return fmaf(fx, c.x, fmaf(fy, c.y, fmaf(fz, c.z, c.w))); }
+static_assert(sizeof(float4) * (kIcp2Cap + 8) >= sizeof(double) * 32 * kIcpRow, "the row buffer of the reduction aliases the candidate buffer");
 
 // cold: exact per-lane walk of the grid (box too large to stage, or a near-tie in a box that took several batches)
 __device__ __noinline__ int icp2_walk(const GridView<double>& g, int pair, double px, double py, double pz, double r2, int rmax, double* d2, int* idx,
@@ -623,8 +621,9 @@ __device__ __noinline__ int icp2_resolve_ties(const double4* __restrict__ pts, c
                                               float fx, float fy, float fz, float lim_t, double px, double py, double pz, int wpos, double* d2, int* idx,
                                               double4* q) {
     int pos = wpos;
+    const float2 f2x = make_float2(fx, fx), f2y = make_float2(fy, fy), f2z = make_float2(fz, fz);
     for (int i = 0; i < kept; ++i) {
-        if (dot_t(buf[i], fx, fy, fz) <= lim_t) {
+        if (cand_t(buf, i, f2x, f2y, f2z) <= lim_t) {
             const int p2 = posb[i];
             if (p2 == wpos) continue;
             const double4 q2 = ld_point(pts + p2);
@@ -904,6 +903,7 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
             float best = 3.0e38f, second = 3.0e38f;
             int wpos = -1;      // sorted position of the float winner
             int last_kept = 0;  // candidates of the last batch (still in shared memory after the call)
+            const float2 f2x = make_float2(fx, fx), f2y = make_float2(fy, fy), f2z = make_float2(fz, fz);
             auto scan = [&](int kept) {
                 last_kept = kept;
                 if (!need) return;
@@ -911,9 +911,8 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                 int grp = -1;
 #pragma unroll 2
                 for (int gi = 0; gi < kept; gi += 4) {
-                    const float ta = dot_t(S.buf[gi], fx, fy, fz), tb = dot_t(S.buf[gi + 1], fx, fy, fz);
-                    const float tc = dot_t(S.buf[gi + 2], fx, fy, fz), td = dot_t(S.buf[gi + 3], fx, fy, fz);
-                    const float m01 = fminf(ta, tb), M01 = fmaxf(ta, tb), m23 = fminf(tc, td), M23 = fmaxf(tc, td);
+                    const float2 t01 = pair_t(S.buf, gi >> 1, f2x, f2y, f2z), t23 = pair_t(S.buf, (gi >> 1) + 1, f2x, f2y, f2z);
+                    const float m01 = fminf(t01.x, t01.y), M01 = fmaxf(t01.x, t01.y), m23 = fminf(t23.x, t23.y), M23 = fmaxf(t23.x, t23.y);
                     const float m = fminf(m01, m23), Mm = fmaxf(m01, m23);
                     const float sg = fminf(fminf(M01, M23), Mm);  // second smallest of the four
                     s2 = fminf(s2, fminf(sg, fmaxf(m, b)));
@@ -922,10 +921,11 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                 }
                 if (grp >= 0) {
                     // the new best sits in group grp: the first of the four that reproduces it (ties end up in the float64 path)
+                    const float2 t01 = pair_t(S.buf, grp >> 1, f2x, f2y, f2z), t23 = pair_t(S.buf, (grp >> 1) + 1, f2x, f2y, f2z);
                     int w = grp + 3;
-                    if (dot_t(S.buf[grp + 2], fx, fy, fz) == b) w = grp + 2;
-                    if (dot_t(S.buf[grp + 1], fx, fy, fz) == b) w = grp + 1;
-                    if (dot_t(S.buf[grp], fx, fy, fz) == b) w = grp;
+                    if (t23.x == b) w = grp + 2;
+                    if (t01.y == b) w = grp + 1;
+                    if (t01.x == b) w = grp;
                     wpos = S.pos[w];
                 }
                 best = b;

@@ -398,29 +398,36 @@ __global__ void __launch_bounds__(kNrmBlock, B3D_NRM2_MIN_BLOCKS) normals_cov2_k
             qx = q.x; qy = q.y; qz = q.z;
             oi = point_index(q);
         }
-        // the chunk's box in fixed-point units: every query's ball, margins for the floor() of the records and the roundings here
         const double ux = unit_coord_of_query(qx, F.ox, F.per_m), uy = unit_coord_of_query(qy, F.oy, F.per_m), uz = unit_coord_of_query(qz, F.oz, F.per_m);
-        int lox = valid ? unit_floor_clamped(ux - ru) : 0x7fffffff, loy = valid ? unit_floor_clamped(uy - ru) : 0x7fffffff,
-            loz = valid ? unit_floor_clamped(uz - ru) : 0x7fffffff;
-        int hix = valid ? unit_ceil_clamped(ux + ru) : (int)0x80000000, hiy = valid ? unit_ceil_clamped(uy + ru) : (int)0x80000000,
-            hiz = valid ? unit_ceil_clamped(uz + ru) : (int)0x80000000;
-        lox = max(__reduce_min_sync(0xffffffffu, lox), 0); loy = max(__reduce_min_sync(0xffffffffu, loy), 0); loz = max(__reduce_min_sync(0xffffffffu, loz), 0);
-        hix = __reduce_max_sync(0xffffffffu, hix); hiy = __reduce_max_sync(0xffffffffu, hiy); hiz = __reduce_max_sync(0xffffffffu, hiz);
-        const int ccx = (int)(((long long)lox + hix) >> 1), ccy = (int)(((long long)loy + hiy) >> 1), ccz = (int)(((long long)loz + hiz) >> 1);
-        const float qox = (float)(ux - (double)ccx), qoy = (float)(uy - (double)ccy), qoz = (float)(uz - (double)ccz);
-        const float fx = -2.0f * qox, fy = -2.0f * qoy, fz = -2.0f * qoz;
-        const float qq = fmaf(qoz, qoz, fmaf(qoy, qoy, qox * qox));
-        const float H = fmaxf(fmaxf((float)(hix - ccx), (float)(hiy - ccy)), (float)(hiz - ccz)) + 1.0f;
-        // |d2f - d2| <= rounding of the scanned t (half of stage2_band would do) + of |q|^2 + of the add + of r2u itself
-        const float band = stage2_band(H) + 4.0e-7f * r2u;
-        int n = 0;
-        int kept_all = 0;
-        auto scan = [&](int kept) {
-            kept_all = kept;
-            if (!valid) return;
-            for (int j = 0; j < kept; ++j) {
-                const float4 cj = S.buf[j];
-                const float d2f = fmaf(fx, cj.x, fmaf(fy, cj.y, fmaf(fz, cj.z, cj.w))) + qq;
+        // The chunk is searched as one group of 32 lanes; a group whose box does not fit ONE staging batch (dense clouds: the
+        // neighbour lists refer to slots of the batch) is split in halves and retried, down to groups of four lanes; what still
+        // does not fit goes to the per-lane kernel.
+        unsigned int pending = __ballot_sync(0xffffffffu, valid);
+        int width = 32;
+        while (pending != 0u) {
+            const int g0 = (__ffs(pending) - 1) & ~(width - 1);
+            const unsigned int gmask = width == 32 ? 0xffffffffu : (((1u << width) - 1u) << g0);
+            const bool active = valid && ((gmask >> lane) & 1u);
+            // the group's box in fixed-point units: every query's ball, margins for the floor() of the records and the roundings here
+            int lox = active ? unit_floor_clamped(ux - ru) : 0x7fffffff, loy = active ? unit_floor_clamped(uy - ru) : 0x7fffffff,
+                loz = active ? unit_floor_clamped(uz - ru) : 0x7fffffff;
+            int hix = active ? unit_ceil_clamped(ux + ru) : (int)0x80000000, hiy = active ? unit_ceil_clamped(uy + ru) : (int)0x80000000,
+                hiz = active ? unit_ceil_clamped(uz + ru) : (int)0x80000000;
+            lox = max(__reduce_min_sync(0xffffffffu, lox), 0); loy = max(__reduce_min_sync(0xffffffffu, loy), 0); loz = max(__reduce_min_sync(0xffffffffu, loz), 0);
+            hix = __reduce_max_sync(0xffffffffu, hix); hiy = __reduce_max_sync(0xffffffffu, hiy); hiz = __reduce_max_sync(0xffffffffu, hiz);
+            const int ccx = (int)(((long long)lox + hix) >> 1), ccy = (int)(((long long)loy + hiy) >> 1), ccz = (int)(((long long)loz + hiz) >> 1);
+            const float qox = (float)(ux - (double)ccx), qoy = (float)(uy - (double)ccy), qoz = (float)(uz - (double)ccz);
+            const float fx = -2.0f * qox, fy = -2.0f * qoy, fz = -2.0f * qoz;
+            const float qq = fmaf(qoz, qoz, fmaf(qoy, qoy, qox * qox));
+            const float H = fmaxf(fmaxf((float)(hix - ccx), (float)(hiy - ccy)), (float)(hiz - ccz)) + 1.0f;
+            // |d2f - d2| <= rounding of the scanned t (half of stage2_band would do) + of |q|^2 + of the add + of r2u itself
+            const float band = stage2_band(H) + 4.0e-7f * r2u;
+            int n = 0;
+            int kept_all = 0;
+            const float2 f2x = make_float2(fx, fx), f2y = make_float2(fy, fy), f2z = make_float2(fz, fz);
+            // one candidate: accept when inside the radius (borderline ones confirmed in float64), append its key
+            auto take = [&](float t, int j) {
+                const float d2f = t + qq;
                 if (d2f <= r2u + band) {
                     bool acc = d2f < r2u - band;
                     if (!acc) {
@@ -433,60 +440,72 @@ __global__ void __launch_bounds__(kNrmBlock, B3D_NRM2_MIN_BLOCKS) normals_cov2_k
                         ++n;
                     }
                 }
-            }
-        };
-        const int nb = stage2_run<kNrm2Cap>(g, F, cloud, lox, loy, loz, hix, hiy, hiz, S, parity, scan);
+            };
+            auto scan = [&](int kept) {
+                kept_all = kept;
+                if (!active) return;
+                for (int j = 0; j < kept; j += 2) {  // an odd tail pairs with a padding candidate at +inf
+                    const float2 t = pair_t(S.buf, j >> 1, f2x, f2y, f2z);
+                    take(t.x, j);
+                    take(t.y, j + 1);
+                }
+            };
+            const int nb = stage2_run<kNrm2Cap>(g, F, cloud, lox, loy, loz, hix, hiy, hiz, S, parity, scan);
 #ifdef B3D_NRM2_STATS
-        const unsigned int valid_mask = __ballot_sync(0xffffffffu, valid);
-        if (stats && lane == 0) {
-            atomicAdd(&g_nrm_stats[0], 1ull);
-            if (nb != 1) atomicAdd(&g_nrm_stats[1], 1ull); else atomicAdd(&g_nrm_stats[3], (unsigned long long)kept_all);
-            atomicAdd(&g_nrm_stats[4], (unsigned long long)__popc(valid_mask));
-        }
-#endif
-        // one batch holds every candidate (slots fit 9 bits); anything else goes to the per-lane kernel
-        const bool chunk_ok = nb == 1 && kept_all <= 512;
-        const bool punt = valid && (!chunk_ok || n > k_nn || n > kNrm2List);
-        if (punt) {
-            todo[atomicAdd(todo_count, 1)] = i;
-            cov6[6 * (int64_t)oi] = __longlong_as_double(0x7ff8000000000b3dll);  // marked: the eigen kernel skips it
-        }
-        const bool work = valid && !punt;
-        if (!work) n = 0;
-        const int nmax = __reduce_max_sync(0xffffffffu, n);
-        if (nmax == 0) {
-            __syncwarp();
-            continue;
-        }
-        if (nmax > 2) nrm2_sort_keys(list, n, nmax);
-        else if (n == 2 && list[1] < list[0]) { const unsigned int t = list[0]; list[0] = list[1]; list[1] = t; }
-        // ---- raw-moment covariance over the neighbour set in distance order (float64 points re-gathered) ------------------
-        double cu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for (int j = 0; j < n; ++j) {
-            const double4 pj = ld_point(g.pts + S.pos[list[j] & 511u]);
-            const double x = pj.x, y = pj.y, z = pj.z;
-            cu[0] += x; cu[1] += y; cu[2] += z;
-            cu[3] += x * x; cu[4] += x * y; cu[5] += x * z;
-            cu[6] += y * y; cu[7] += y * z; cu[8] += z * z;
-        }
-        if (work) {
-            double C[6] = {1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
-            if (n >= 3) {
-                const double cn = (double)n;
-#pragma unroll
-                for (int j = 0; j < 9; ++j) cu[j] /= cn;
-                C[0] = cu[3] - cu[0] * cu[0];
-                C[1] = cu[4] - cu[0] * cu[1];
-                C[2] = cu[5] - cu[0] * cu[2];
-                C[3] = cu[6] - cu[1] * cu[1];
-                C[4] = cu[7] - cu[1] * cu[2];
-                C[5] = cu[8] - cu[2] * cu[2];
+            if (stats && lane == 0) {
+                atomicAdd(&g_nrm_stats[0], 1ull);
+                if (nb > 1 || nb < 0) atomicAdd(&g_nrm_stats[1], 1ull); else atomicAdd(&g_nrm_stats[3], (unsigned long long)kept_all);
+                atomicAdd(&g_nrm_stats[4], (unsigned long long)__popc(pending & gmask));
             }
-            double* out = cov6 + 6 * (int64_t)oi;
+#endif
+            // one batch holds every candidate (slots fit 9 bits); nb == 0: no point at all in the box (cannot happen: the queries are points)
+            const bool group_ok = nb <= 1 && nb >= 0 && kept_all <= 512;
+            if (!group_ok && width > 4) {
+                width >>= 1;  // retry this part of the chunk in two halves (warp-uniform)
+                continue;
+            }
+            pending &= ~gmask;
+            const bool punt = active && (!group_ok || n > k_nn || n > kNrm2List);
+            if (punt) {
+#ifdef B3D_NRM2_STATS
+                if (stats) atomicAdd(&g_nrm_stats[2], 1ull);
+#endif
+                todo[atomicAdd(todo_count, 1)] = i;
+                cov6[6 * (int64_t)oi] = __longlong_as_double(0x7ff8000000000b3dll);  // marked: the eigen kernel skips it
+            }
+            const bool work = active && !punt;
+            if (!work) n = 0;
+            const int nmax = __reduce_max_sync(0xffffffffu, n);
+            if (nmax > 2) nrm2_sort_keys(list, n, nmax);
+            else if (n == 2 && list[1] < list[0]) { const unsigned int t = list[0]; list[0] = list[1]; list[1] = t; }
+            // ---- raw-moment covariance over the neighbour set in distance order (float64 points re-gathered) ----------------
+            double cu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int j = 0; j < n; ++j) {
+                const double4 pj = ld_point(g.pts + S.pos[list[j] & 511u]);
+                const double x = pj.x, y = pj.y, z = pj.z;
+                cu[0] += x; cu[1] += y; cu[2] += z;
+                cu[3] += x * x; cu[4] += x * y; cu[5] += x * z;
+                cu[6] += y * y; cu[7] += y * z; cu[8] += z * z;
+            }
+            if (work) {
+                double C[6] = {1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
+                if (n >= 3) {
+                    const double cn = (double)n;
 #pragma unroll
-            for (int j = 0; j < 6; ++j) out[j] = C[j];
+                    for (int j = 0; j < 9; ++j) cu[j] /= cn;
+                    C[0] = cu[3] - cu[0] * cu[0];
+                    C[1] = cu[4] - cu[0] * cu[1];
+                    C[2] = cu[5] - cu[0] * cu[2];
+                    C[3] = cu[6] - cu[1] * cu[1];
+                    C[4] = cu[7] - cu[1] * cu[2];
+                    C[5] = cu[8] - cu[2] * cu[2];
+                }
+                double* out = cov6 + 6 * (int64_t)oi;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) out[j] = C[j];
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 

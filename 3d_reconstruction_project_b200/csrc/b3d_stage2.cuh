@@ -13,7 +13,8 @@
 //    lane issues the copy of the cell it probed) and waits ONCE on an mbarrier for all of them: no register staging, every copy
 //    of a box in flight at the same time.
 //  * The filter runs out of shared memory as one flat loop over the copied records (integer box test, ballot compaction IN
-//    PLACE) and leaves {float offset from the box centre, |offset|^2} (in units) for the dot-product scan.
+//    PLACE) and leaves {float offset from the box centre, |offset|^2} (in units), two candidates interleaved per block, for
+//    the dot-product scan: three packed FFMA2 evaluate two candidates.
 //  * Boxes that do not fit the buffer are processed in several batches (the scan state lives in registers); only a single cell
 //    larger than the buffer, or a box of more than kStage2MaxCells cells, falls back to the per-lane walk.
 #pragma once
@@ -24,8 +25,8 @@ namespace b3d {
 
 template <int CAP>
 struct alignas(16) StageSmem {
-    float4 buf[CAP + 4];      // raw cell records (int4 bit patterns), then (in place) the filtered candidates {ox, oy, oz, |o|^2}; +4: scan padding
-    int32_t pos[CAP + 4];     // sorted position of every filtered candidate
+    float4 buf[CAP + 8];      // raw cell records (int4 bit patterns), then (in place) the filtered candidates in PAIR BLOCKS (below); +8: scan padding
+    int32_t pos[CAP + 8];     // sorted position of every filtered candidate
     unsigned long long mbar;  // one phase per batch
     unsigned long long pad_;
 };
@@ -69,6 +70,29 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
                  "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
+// ---- filtered candidates: pair blocks ---------------------------------------------------------------------------------------
+// Candidate slot s lives in pair block s >> 1 = two float4: {x0 x1 y0 y1} {z0 z1 w0 w1} (offsets from the box centre in units,
+// w = |offset|^2): the scans evaluate t = w - 2 q.o for BOTH candidates of a block with three packed FFMA2 (fma.rn.f32x2).
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+// t of the two candidates of pair block p for the query factors f = -2 q (each component duplicated into a float2)
+__device__ __forceinline__ float2 pair_t(const float4* __restrict__ buf, int p, float2 fx, float2 fy, float2 fz) {
+    const float4 lo = buf[2 * p], hi = buf[2 * p + 1];
+    return ffma2(fx, make_float2(lo.x, lo.y), ffma2(fy, make_float2(lo.z, lo.w), ffma2(fz, make_float2(hi.x, hi.y), make_float2(hi.z, hi.w))));
+}
+__device__ __forceinline__ float cand_t(const float4* __restrict__ buf, int s, float2 fx, float2 fy, float2 fz) {
+    const float2 t = pair_t(buf, s >> 1, fx, fy, fz);
+    return (s & 1) ? t.y : t.x;
+}
+
 // orders this thread's earlier generic-proxy accesses of shared memory before later async-proxy (bulk copy) writes
 __device__ __forceinline__ void fence_async_smem() {
 #ifndef B3D_STAGE2_NO_FENCE  // measurement only: what the proxy fences cost
@@ -112,8 +136,8 @@ __device__ __forceinline__ int unit_ceil_clamped(double v) { return __double2int
 constexpr int kStage2MaxCells = 1024;  // cells of one box; beyond that (or beyond 256 on an axis) the caller falls back
 
 // Stages every point of `cloud` with lo <= record <= hi (absolute units, per axis; lo/hi identical on all lanes) batch by batch and
-// calls scan(kept) after each batch has been filtered: S.buf[0..kept) = {float offset from the box centre c = (lo + hi) >> 1,
-// |offset|^2} in units, S.pos[0..kept) = sorted positions, followed by four padding candidates at +inf.
+// calls scan(kept) after each batch has been filtered: candidate slots [0, kept) in the pair blocks of S.buf (float offsets from the
+// box centre c = (lo + hi) >> 1 and their squared length, in units), S.pos[0..kept) = sorted positions, then padding slots at +inf.
 // Returns the number of batches scanned (0: the box holds no point), or -1 when the caller has to fall back (box too large or
 // one cell with more than CAP points). parity: the warp's mbarrier phase.
 template <int CAP, typename Scan>
@@ -218,6 +242,7 @@ __device__ __forceinline__ int stage2_run(const GridView<double>& g, const UnitF
             parity ^= 1u;
             int kept = 0;
             const int4* raw = reinterpret_cast<const int4*>(S.buf);
+            float* fbuf = reinterpret_cast<float*>(S.buf);
             for (int j0 = 0; j0 < fill; j0 += 32) {
                 const int j = j0 + lane;
                 bool inside = false;
@@ -230,12 +255,17 @@ __device__ __forceinline__ int stage2_run(const GridView<double>& g, const UnitF
                 if (inside) {
                     const int slot = kept + __popc(m & ((1u << lane) - 1u));
                     const float ox = (float)(r.x - ccx), oy = (float)(r.y - ccy), oz = (float)(r.z - ccz);
-                    S.buf[slot] = make_float4(ox, oy, oz, fmaf(oz, oz, fmaf(oy, oy, ox * ox)));
+                    // in place: the block of slots (s & ~1, s | 1) overlays raw records of the same indices, all of them read already
+                    float* d = fbuf + 8 * (slot >> 1) + (slot & 1);
+                    d[0] = ox; d[2] = oy; d[4] = oz; d[6] = fmaf(oz, oz, fmaf(oy, oy, ox * ox));
                     S.pos[slot] = r.w;
                 }
                 kept += __popc(m);
             }
-            if (lane < 4) S.buf[kept + lane] = make_float4(0.f, 0.f, 0.f, 3.0e38f);
+            if (lane < 6) {  // padding candidates at +inf: the scans run in steps of four slots
+                float* d = fbuf + 8 * ((kept + lane) >> 1) + ((kept + lane) & 1);
+                d[0] = 0.f; d[2] = 0.f; d[4] = 0.f; d[6] = 3.0e38f;
+            }
             __syncwarp();
             scan(kept);
             __syncwarp();
