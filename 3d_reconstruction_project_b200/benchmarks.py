@@ -127,16 +127,23 @@ def config5_run(side, iters, dmax, world, rank, local, fused, T=None):
     use_fused = fused and world > 1
     if use_fused:
         sh.enable_peers()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    e0, e1 = ev(), ev()
     passes = 0
+    marks = []  # per pass: (before the shard's pass kernel, after it, after the all-reduce)
     e0.record(ctx.stream)
     while True:
         look = passes % 2 == 1  # the done flag is read back (host sync) every other pass only
         if use_fused:
             done = sh.pass_fused(look)
         else:
+            a, b, c = ev(), ev(), ev()
+            a.record(ctx.stream)
             sums = sh.accumulate()
+            b.record(ctx.stream)
             D.all_reduce_sums(sums)
+            c.record(ctx.stream)
+            marks.append((a, b, c))
             done = sh.update(look)
         passes += 1
         if done:
@@ -144,10 +151,13 @@ def config5_run(side, iters, dmax, world, rank, local, fused, T=None):
     e1.record(ctx.stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    # this rank's own kernel time and its wait in the collective (the wait includes the skew against the slowest shard)
+    acc_ms = sum(a.elapsed_time(b) for a, b, _ in marks) / max(1, len(marks))
+    red_ms = sum(b.elapsed_time(c) for _, b, c in marks) / max(1, len(marks))
     res = sh.finish()
     del sh, src, tgt, tn
     torch.cuda.empty_cache()
-    return res, ms, passes, T, hi - lo
+    return res, ms, passes, T, (hi - lo, acc_ms, red_ms)
 
 
 def config5_leg(world, rank, local, points_per_rank=10_000_000, iters=10, dmax=0.005, peak_gbs=None):
@@ -164,12 +174,12 @@ def config5_leg(world, rank, local, points_per_rank=10_000_000, iters=10, dmax=0
             continue
         config5_run(side, 2, dmax, world, rank, local, fused)  # warm-up: allocator, symmetric-memory rendezvous, NCCL channels
         res, ms, passes, T, n_local = config5_run(side, iters, dmax, world, rank, local, fused)
-        t = torch.zeros(world, dtype=torch.float64, device=torch.device("cuda", local))
-        t[rank] = ms
+        t = torch.zeros((world, 3), dtype=torch.float64, device=torch.device("cuda", local))
+        t[rank, 0], t[rank, 1], t[rank, 2] = ms, n_local[1], n_local[2]
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)  # every rank's own loop time (disjoint slots: a gather)
-        per_rank = [float(v) for v in t.tolist()]
-        runs[name] = (res, max(per_rank), passes, T, n_local, per_rank)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)  # every rank's own times (disjoint rows: a gather)
+        per_rank = t.tolist()
+        runs[name] = (res, max(r[0] for r in per_rank), passes, T, n_local, per_rank)
     if rank == 0:
         res, ms, passes, T, _, _ = runs["nccl"]
         rot, tr = synth.transform_error(res["transformation"], T)
@@ -182,9 +192,12 @@ def config5_leg(world, rank, local, points_per_rank=10_000_000, iters=10, dmax=0
             out["variants"][name] = {"exchange": "all-reduce inside the pass kernel over peer memory (NVLink)" if name == "fused" else ("nccl all_reduce" if world > 1 else "none (one rank)"),
                                      "ms_per_pass": per_pass, "mpoints_per_sec": n / (per_pass * 1e-3) / 1e6, "algorithmic_gbps": gb,
                                      "frac_of_n_x_peak": (gb / (peak_gbs * world)) if peak_gbs else None,
-                                     # each rank's own device time of the loop: with a collective per pass every rank waits for the
-                                     # slowest shard, so the spread here is clock / launch jitter, not shard imbalance
-                                     "rank_ms_per_pass": [v / p_v for v in per_rank]}
+                                     # per rank: the whole loop; for the NCCL variant also the shard's own pass kernel and its time in the
+                                     # all-reduce per pass (232 bytes: that time is the wait for the slowest shard, i.e. the skew)
+                                     "rank_loop_ms_per_pass": [r[0] / p_v for r in per_rank]}
+            if name == "nccl":
+                out["variants"][name]["rank_pass_kernel_ms"] = [r[1] for r in per_rank]
+                out["variants"][name]["rank_allreduce_ms"] = [r[2] for r in per_rank]
         if "fused" in runs:
             a, b = runs["nccl"][0], runs["fused"][0]
             out["fused_equals_nccl_bitwise"] = bool(np.array_equal(a["transformation"], b["transformation"]) and a["fitness"] == b["fitness"]

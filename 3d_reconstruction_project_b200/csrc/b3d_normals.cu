@@ -340,23 +340,25 @@ struct alignas(16) Nrm2Smem {
         k[a] = lo_;                           \
     }
 
-// Orders the first n (<= 32) keys of a lane's list ascending: into registers, a sorting network sized by the longest list of
-// the warp (uniform control flow), back to shared memory. Out of line: one copy of the unrolled networks, called once per chunk.
-__device__ __noinline__ void nrm2_sort_keys(unsigned int* __restrict__ list, int n, int nmax) {
+// Orders the first n keys of a lane's list ascending: into registers, a sorting network (uniform control flow: every lane runs
+// it, shorter lists are padded with +inf), back to shared memory. Out of line: one copy of each unrolled network.
+__device__ __noinline__ void nrm2_sort_keys16(unsigned int* __restrict__ list, int n) {
+    unsigned int k[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) k[j] = j < n ? list[j] : 0xffffffffu;
+    B3D_SORTNET_16(B3D_CE)
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (j < n) list[j] = k[j];
+}
+__device__ __noinline__ void nrm2_sort_keys32(unsigned int* __restrict__ list, int n) {
     unsigned int k[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) k[j] = j < n ? list[j] : 0xffffffffu;
-    if (nmax <= 16) {
-        B3D_SORTNET_16(B3D_CE)
+    B3D_SORTNET_32(B3D_CE)
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (j < n) list[j] = k[j];
-    } else {
-        B3D_SORTNET_32(B3D_CE)
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < n) list[j] = k[j];
-    }
+    for (int j = 0; j < 32; ++j)
+        if (j < n) list[j] = k[j];
 }
 #undef B3D_CE
 
@@ -428,18 +430,15 @@ __global__ void __launch_bounds__(kNrmBlock, B3D_NRM2_MIN_BLOCKS) normals_cov2_k
             // one candidate: accept when inside the radius (borderline ones confirmed in float64), append its key
             auto take = [&](float t, int j) {
                 const float d2f = t + qq;
-                if (d2f <= r2u + band) {
-                    bool acc = d2f < r2u - band;
-                    if (!acc) {
-                        const double4 pj = ld_point(g.pts + S.pos[j]);
-                        acc = dist2<double>(qx - pj.x, qy - pj.y, qz - pj.z) < r2;
-                    }
-                    if (acc) {
-                        // ascending keys = (d2, scan order): the float bits of d2 with the low 9 bits replaced by the slot
-                        if (n < kNrm2List) list[n] = (__float_as_uint(fmaxf(d2f, 0.0f)) & ~511u) | (unsigned int)j;
-                        ++n;
-                    }
+                bool acc = d2f < r2u - band;
+                if (!acc && d2f <= r2u + band) {  // borderline (rare): decide in float64
+                    const double4 pj = ld_point(g.pts + S.pos[j]);
+                    acc = dist2<double>(qx - pj.x, qy - pj.y, qz - pj.z) < r2;
                 }
+                // ascending keys = (d2, scan order): the float bits of d2 with the low 9 bits replaced by the slot. Branch-free
+                // append: rejected candidates (and overflowing lists) write the spare entry at the end of the row
+                list[acc && n < kNrm2List ? n : kNrm2List] = (__float_as_uint(fmaxf(d2f, 0.0f)) & ~511u) | (unsigned int)j;
+                n += acc ? 1 : 0;
             };
             auto scan = [&](int kept) {
                 kept_all = kept;
@@ -476,7 +475,8 @@ __global__ void __launch_bounds__(kNrmBlock, B3D_NRM2_MIN_BLOCKS) normals_cov2_k
             const bool work = active && !punt;
             if (!work) n = 0;
             const int nmax = __reduce_max_sync(0xffffffffu, n);
-            if (nmax > 2) nrm2_sort_keys(list, n, nmax);
+            if (nmax > 16) nrm2_sort_keys32(list, n);
+            else if (nmax > 2) nrm2_sort_keys16(list, n);
             else if (n == 2 && list[1] < list[0]) { const unsigned int t = list[0]; list[0] = list[1]; list[1] = t; }
             // ---- raw-moment covariance over the neighbour set in distance order (float64 points re-gathered) ----------------
             double cu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
