@@ -608,18 +608,19 @@ constexpr int kIcp2Cap = B3D_ICP2_CAP;  // raw cell records per batch (+4 scan p
 using Icp2Smem = StageSmem<kIcp2Cap>;
 static_assert(sizeof(float4) * (kIcp2Cap + 8) >= sizeof(double) * 32 * kIcpRow, "the row buffer of the reduction aliases the candidate buffer");
 
-// cold: exact per-lane walk of the grid (box too large to stage, or a near-tie in a box that took several batches)
-__device__ __noinline__ int icp2_walk(const GridView<double>& g, int pair, double px, double py, double pz, double r2, int rmax, double* d2, int* idx,
-                                      double4* q) {
-    const int pos = nn_within_query<double>(g, pair, px, py, pz, r2, rmax, d2, idx);
-    if (pos >= 0) *q = ld_point(g.pts + pos);
-    return pos;
+// cold: exact per-lane walk of the grid (box too large to stage, or a near-tie in a box that took several batches). The cold helpers
+// take and return VALUES: a variable whose address is passed to an out-of-line function lives in local memory for the whole
+// kernel (px, py, pz, d2, idx and q did: ~17 local loads / stores per chunk, profiles/r02c_ncu_icp_pass2_p64_digest.txt).
+__device__ __noinline__ int icp2_walk(const GridView<double>& g, int pair, double px, double py, double pz, double r2, int rmax) {
+    double d2;
+    int idx;
+    return nn_within_query<double>(g, pair, px, py, pz, r2, rmax, &d2, &idx);
 }
 
 // cold: more than one staged candidate inside the rounding band of the best -- decide in float64 with the (d2, index) rule
+// (d2, idx: the float winner's). Returns the sorted position of the exact winner.
 __device__ __noinline__ int icp2_resolve_ties(const double4* __restrict__ pts, const float4* __restrict__ buf, const int* __restrict__ posb, int kept,
-                                              float fx, float fy, float fz, float lim_t, double px, double py, double pz, int wpos, double* d2, int* idx,
-                                              double4* q) {
+                                              float fx, float fy, float fz, float lim_t, double px, double py, double pz, int wpos, double d2, int idx) {
     int pos = wpos;
     const float2 f2x = make_float2(fx, fx), f2y = make_float2(fy, fy), f2z = make_float2(fz, fz);
     for (int i = 0; i < kept; ++i) {
@@ -629,7 +630,7 @@ __device__ __noinline__ int icp2_resolve_ties(const double4* __restrict__ pts, c
             const double4 q2 = ld_point(pts + p2);
             const double e2 = dist2<double>(px - q2.x, py - q2.y, pz - q2.z);
             const int i2 = point_index(q2);
-            if (e2 < *d2 || (e2 == *d2 && i2 < *idx)) { *d2 = e2; *idx = i2; pos = p2; *q = q2; }
+            if (e2 < d2 || (e2 == d2 && i2 < idx)) { d2 = e2; idx = i2; pos = p2; }
         }
     }
     return pos;
@@ -736,9 +737,8 @@ __device__ __noinline__ void icp2_finish_pair(const IcpKernelArgs& A, int pair, 
 }
 
 // cold: transforms with a projective last row (PointCloud::Transform divides by w)
-__device__ __noinline__ void icp2_perspective(const double* T, double x, double y, double z, double* px, double* py, double* pz) {
-    const double w = T[12] * x + T[13] * y + T[14] * z + T[15];
-    *px /= w; *py /= w; *pz /= w;
+__device__ __noinline__ double icp2_perspective_w(const double* T, double x, double y, double z) {
+    return T[12] * x + T[13] * y + T[14] * z + T[15];
 }
 
 template <int KIND>
@@ -772,50 +772,24 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
     double acc = 0.0;  // lane j: running total of sum j
     const float dmax_up = (float)sqrt(A.r2) * 1.000001f;  // d_max, rounded up
     const bool affine = sT[12] == 0.0 && sT[13] == 0.0 && sT[14] == 0.0 && sT[15] == 1.0;
-    const int32_t c_step = groups * (kIcpBlock / 32);
-    int32_t c = c0 + blockIdx.x * (kIcpBlock / 32) + warp;
-#ifdef B3D_ICP2_PREFETCH
-    // the next chunk's query is fetched while the current one is processed
-    double4 nsp = make_double4(0.0, 0.0, 0.0, 0.0);
-    float4 nkr = make_float4(0.f, 0.f, 0.f, 0.f);
-    int nkp = -1;
-    int32_t ni = 0;
-    bool nvalid = false;
-    if (c < c1) {
-        ni = A.chunk_start[c] + lane;
-        nvalid = ni < A.chunk_start[c + 1];
-        if (nvalid) {
-            nsp = ld_point(A.src_sorted + ni);
-            if (A.keep_ref != nullptr) {
-                nkr = A.keep_ref[ni];
-                nkp = A.keep_pos[ni];
-            }
-        }
-    }
-#endif
-    for (; c < c1; c += c_step) {
-#ifdef B3D_ICP2_PREFETCH
-        const double4 sp = nsp;
-        const float4 kr = nkr;
-        const int kp = nkp;
-        const int32_t si = ni;
-        const bool valid = nvalid;
-        nvalid = false;
-        if (c + c_step < c1) {
-            ni = A.chunk_start[c + c_step] + lane;
-            nvalid = ni < A.chunk_start[c + c_step + 1];
-            if (nvalid) {
-                nsp = ld_point(A.src_sorted + ni);
-                if (A.keep_ref != nullptr) {
-                    nkr = A.keep_ref[ni];
-                    nkp = A.keep_pos[ni];
-                }
-            }
-        }
-#else
-        // no software prefetch of the next chunk: the registers it would hold across the search are worth more (spills)
+    // A block owns a CONTIGUOUS range of the pair's chunks (Hilbert neighbours: their boxes overlap, so the hash slots, the partner
+    // gathers and the normals one warp's chunk touched are in L1 for the next one); the warps interleave inside the range.
+    const int32_t c_per = (c1 - c0 + groups - 1) / groups;
+    const int32_t c_step = kIcpBlock / 32;
+    int32_t c = c0 + (int32_t)blockIdx.x * c_per + warp;
+    const int32_t c_end = min(c1, c0 + ((int32_t)blockIdx.x + 1) * c_per);
+    for (; c < c_end; c += c_step) {
+        // The warp's next chunk is announced to the caches, not held in registers (prefetching into registers spilled): its source
+        // points and sticky state are prefetched into L1 once this chunk's own loads are under way; the one word that is fetched
+        // for real (the previous partner's position) addresses the prefetch of that partner's point and normal.
         const int32_t si = A.chunk_start[c] + lane;
         const bool valid = si < A.chunk_start[c + 1];
+        int32_t nsi = -1, nkp = -1;
+        if (c + c_step < c_end) {
+            nsi = A.chunk_start[c + c_step] + lane;
+            if (nsi >= s1) nsi = -1;
+            else if (A.keep_pos != nullptr) nkp = A.keep_pos[nsi];
+        }
         double4 sp = make_double4(0.0, 0.0, 0.0, 0.0);
         float4 kr = make_float4(0.f, 0.f, 0.f, 0.f);
         int kp = -1;
@@ -826,7 +800,6 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                 kp = A.keep_pos[si];
             }
         }
-#endif
         double px = 0, py = 0, pz = 0;
         int oi = 0;
         if (valid) {
@@ -836,7 +809,10 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
             px = sT[0] * x + sT[1] * y + sT[2] * z + sT[3];
             py = sT[4] * x + sT[5] * y + sT[6] * z + sT[7];
             pz = sT[8] * x + sT[9] * y + sT[10] * z + sT[11];
-            if (!affine) icp2_perspective(sT, x, y, z, &px, &py, &pz);
+            if (!affine) {
+                const double w = icp2_perspective_w(sT, x, y, z);
+                px /= w; py /= w; pz /= w;
+            }
         }
         // ---- correspondence: sticky check, then one staged search bounded by the distance to the previous partner ---------
         double d2 = 0.0;
@@ -853,6 +829,7 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
             const float lim = kr.w;  // every other target point was at least this far from the stored position (0: unknown)
             if (kp >= 0) {
                 q = ld_point(A.grid.pts + kp);
+                if (KIND == B3D_ICP_POINT_TO_PLANE) prefetch_l1(A.tgt_nrm_sorted + 3 * (int64_t)kp);  // most lanes keep this partner
                 const double dk = dist2<double>(px - q.x, py - q.y, pz - q.z);
                 const float u = sqrtf((float)dk) * 1.000001f;
                 if ((u + moved) * 1.000001f < lim) {  // still strictly nearer than anything else can be
@@ -876,6 +853,10 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
             atomicAdd(&g_icp_stats[7], (unsigned long long)__popc(need_mask));
         }
 #endif
+        if (nsi >= 0) {
+            prefetch_l1(A.src_sorted + nsi);
+            if (A.keep_ref != nullptr) prefetch_l1(A.keep_ref + nsi);
+        }
         if (need_mask != 0u) {
             // the chunk's box in fixed-point units of the target grid: every searching lane's ball, one unit of margin for the
             // floor() of the records and one for the roundings here
@@ -943,25 +924,35 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
             double others2 = 3.0e38;  // lower bound of the squared distance (metres) of every target point but the winner
             bool bounded = nb >= 0;   // every target point within `reach` of the query was looked at
             if (need) {
-                if (nb < 0) {
-                    pos = icp2_walk(A.grid, pair, px, py, pz, A.r2, A.rmax, &d2, &idx, &q);
-                } else if (wpos >= 0) {
-                    const bool ambiguous = second <= best + band_w;
-                    if (ambiguous && nb > 1) {
-                        // near-tie in a box that took several batches (the earlier candidates are gone)
-                        pos = icp2_walk(A.grid, pair, px, py, pz, A.r2, A.rmax, &d2, &idx, &q);
-                        bounded = false;
-                    } else {
-                        pos = wpos;
-                        q = ld_point(A.grid.pts + pos);
-                        d2 = dist2<double>(px - q.x, py - q.y, pz - q.z);
-                        idx = point_index(q);
-                        if (ambiguous) {
-                            pos = icp2_resolve_ties(A.grid.pts, S.buf, S.pos, last_kept, fx, fy, fz, best + band_w, px, py, pz, wpos, &d2, &idx, &q);
-                            others2 = d2;
-                        } else {
-                            others2 = fmax(d2, ((qdx * qdx + qdy * qdy + qdz * qdz) + (double)second - (double)band_w) * inv_pm2);
+                const bool ambiguous = nb >= 0 && wpos >= 0 && second <= best + band_w;
+                if (nb < 0 || (ambiguous && nb > 1)) {
+                    // box too large to stage, or a near-tie in a box that took several batches (the earlier candidates are gone)
+                    pos = icp2_walk(A.grid, pair, px, py, pz, A.r2, A.rmax);
+                    if (nb >= 0) bounded = false;
+                } else {
+                    pos = wpos;
+                }
+                if (pos >= 0) {
+                    q = ld_point(A.grid.pts + pos);
+                    if (KIND == B3D_ICP_POINT_TO_PLANE) {  // the normal's latency runs in parallel with the point's
+                        prefetch_l1(A.tgt_nrm_sorted + 3 * (int64_t)pos);
+                        prefetch_l1(A.tgt_nrm_sorted + 3 * (int64_t)pos + 2);
+                    }
+                    d2 = dist2<double>(px - q.x, py - q.y, pz - q.z);
+                    idx = point_index(q);
+                }
+                if (nb >= 0 && wpos >= 0 && !(ambiguous && nb > 1)) {
+                    if (ambiguous) {
+                        const int tpos = icp2_resolve_ties(A.grid.pts, S.buf, S.pos, last_kept, fx, fy, fz, best + band_w, px, py, pz, wpos, d2, idx);
+                        if (tpos != pos) {
+                            pos = tpos;
+                            q = ld_point(A.grid.pts + pos);
+                            d2 = dist2<double>(px - q.x, py - q.y, pz - q.z);
+                            idx = point_index(q);
                         }
+                        others2 = d2;
+                    } else {
+                        others2 = fmax(d2, ((qdx * qdx + qdy * qdy + qdz * qdz) + (double)second - (double)band_w) * inv_pm2);
                     }
                 }
             }
@@ -974,6 +965,10 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                 A.keep_ref[si] = make_float4((float)px, (float)py, (float)pz, lbf);
                 A.keep_pos[si] = pos;
             }
+        }
+        if (nkp >= 0) {
+            prefetch_l1(A.grid.pts + nkp);
+            if (KIND == B3D_ICP_POINT_TO_PLANE) prefetch_l1(A.tgt_nrm_sorted + 3 * (int64_t)nkp);
         }
         if (pos >= 0 && !(d2 < A.r2)) pos = -1;
         double e[kIcpRow];

@@ -377,7 +377,11 @@ __global__ void __launch_bounds__(kNrmBlock, B3D_NRM2_MIN_BLOCKS) normals_cov2_k
     UnitFrame F = {};
     float r2u = 0.f;   // radius^2 in units^2
     double ru = 0.0;   // radius in units (+ margins)
-    for (int c = blockIdx.x * (kNrmBlock / 32) + warp; c < n_chunks; c += gridDim.x * (kNrmBlock / 32)) {
+    // a block owns a contiguous range of chunks (Morton neighbours: overlapping boxes, so the hash slots and the float64 points one
+    // warp gathered are in L1 for the next one); its warps interleave inside the range
+    const int c_per = (n_chunks + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int c_end = min(n_chunks, ((int)blockIdx.x + 1) * c_per);
+    for (int c = (int)blockIdx.x * c_per + warp; c < c_end; c += kNrmBlock / 32) {
         // cloud of this chunk: last b with chunk_off[b] <= c
         int lo_b = 0, hi_b = B;
         while (hi_b - lo_b > 1) {
@@ -720,7 +724,8 @@ int estimate_normals_batch(b3d_ctx* ctx, const T* xyz, const Segments& seg, int 
             if (!v1 && grid->rec.p != nullptr) {
                 DevBuf<double> cov6;
                 B3D_TRY(cov6.alloc(ctx, (size_t)n * 6));
-                const int sblocks = std::max(1, std::min((qc.n_chunks + kNrmBlock / 32 - 1) / (kNrmBlock / 32), ctx->sm_count * 20));
+                // contiguous chunk ranges per block: many more blocks than resident slots, so that the ranges' uneven costs even out
+                const int sblocks = std::max(1, std::min((qc.n_chunks + kNrmBlock / 32 - 1) / (kNrmBlock / 32), ctx->sm_count * 64));
                 const size_t smem = sizeof(Nrm2Smem) * (kNrmBlock / 32);
                 B3D_CUDA(cudaFuncSetAttribute(normals_cov2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 B3D_LAUNCH(ctx, normals_cov2_kernel, sblocks, kNrmBlock, smem, grid->view(), qc.chunk_start.p, qc.chunk_off.p, seg.B, qc.n_chunks, max_nn,

@@ -25,6 +25,8 @@ __host__ __device__ __forceinline__ uint32_t hash_key(unsigned long long k) {
     return h;
 }
 
+// announces a global address to L1 (no register, no scoreboard: the data is simply there when the load comes)
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 ld_point(const float4* p) { return __ldg(p); }
 __device__ __forceinline__ double4 ld_point(const double4* p) {
     const double2* q = reinterpret_cast<const double2*>(p);
