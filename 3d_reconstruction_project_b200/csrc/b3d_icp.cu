@@ -31,17 +31,22 @@ constexpr int kIcpInformation = 3;  // internal kind: G^T G of get_information_m
 // longer-lived blocks amortise every warp's cold start (four dependent loads before its first chunk is under way); more
 // blocks fill the machine when a single pair runs alone. Measured on config 2, ICP ms per 64-pair step / per single pair:
 // 128: 20.3 / 1.70, 256: 20.6 / 1.15, 384: 21.1 / 0.97, 512: 21.5 / 0.89, 1024: 23.4 / 0.89.
+// Round 2 (contiguous chunk ranges per block): a block's start (state, lattice, first chunk: ~6 dependent loads) and end (fence,
+// ticket) cost about 0.7 chunk-times per warp; 8 / 16 / 32 chunks per warp: 17.75 / 16.98 / 17.06 ms per 64-pair step.
 #ifndef B3D_ICP_GROUPS
-#define B3D_ICP_GROUPS 384
+#define B3D_ICP_GROUPS 256
+#endif
+#ifndef B3D_ICP_CHUNKS_PER_WARP
+#define B3D_ICP_CHUNKS_PER_WARP 16
 #endif
 constexpr int kIcpMinGroups = B3D_ICP_GROUPS * (128 / kIcpBlock);  // partial-sum groups (blocks) of an ordinary pair
 constexpr int kIcpMaxGroups = 4096 * (128 / kIcpBlock);            // ... of a very large one
 // Groups of a pair with `chunks` warp chunks: one chunk per warp while the pair is tiny, kIcpMinGroups blocks for ordinary
-// frame pairs, about eight chunks per warp beyond that (a 1e8-point cloud must still fill the machine on its own).
+// frame pairs, about B3D_ICP_CHUNKS_PER_WARP (16) chunks per warp beyond that (a 1e8-point cloud must still fill the machine on its own).
 __host__ __device__ inline int icp_groups(int chunks) {
     const int wpb = kIcpBlock / 32;
     const int one_each = (chunks + wpb - 1) / wpb;
-    int g = (chunks + 8 * wpb - 1) / (8 * wpb);
+    int g = (chunks + B3D_ICP_CHUNKS_PER_WARP * wpb - 1) / (B3D_ICP_CHUNKS_PER_WARP * wpb);
     const int floor_g = one_each < kIcpMinGroups ? one_each : kIcpMinGroups;
     g = g < floor_g ? floor_g : g;
     g = g > kIcpMaxGroups ? kIcpMaxGroups : g;
@@ -606,7 +611,12 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
 #endif
 constexpr int kIcp2Cap = B3D_ICP2_CAP;  // raw cell records per batch (+4 scan padding = 384 x 16 bytes)
 using Icp2Smem = StageSmem<kIcp2Cap>;
-static_assert(sizeof(float4) * (kIcp2Cap + 8) >= sizeof(double) * 32 * kIcpRow, "the row buffer of the reduction aliases the candidate buffer");
+// The reduction's row buffer aliases the candidate buffer, TRANSPOSED: value j of lane l at [j][l], rows 34 doubles apart (272 bytes:
+// the eight distinct operand rows a warp reads at once start in eight different 16-byte bank groups). Lane j fetches its two operands
+// for TWO source lanes with one 16-byte load each: 32 loads + 32 fused multiply-adds per chunk, one wavefront per load (the [l][j]
+// layout took 64 8-byte loads at 1.8 wavefronts, a quarter of the kernel's shared-memory traffic).
+constexpr int kIcpRowStride = 34;
+static_assert(sizeof(float4) * Icp2Smem::kSlots >= sizeof(double) * kIcpRowStride * kIcpRow, "the row buffer of the reduction aliases the candidate buffer");
 
 // cold: exact per-lane walk of the grid (box too large to stage, or a near-tie in a box that took several batches). The cold helpers
 // take and return VALUES: a variable whose address is passed to an out-of-line function lives in local memory for the whole
@@ -768,7 +778,9 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
     const float inv_pm = (float)(1.0 / F.per_m);                   // metres per unit
     int op_p, op_q;
     icp_sum_operands(KIND, lane, op_p, op_q);
-    double (*rows)[kIcpRow] = reinterpret_cast<double (*)[kIcpRow]>(S.buf);
+    double* rows_t = reinterpret_cast<double*>(S.buf);
+    const double2* row_p = reinterpret_cast<const double2*>(rows_t + op_p * kIcpRowStride);
+    const double2* row_q = reinterpret_cast<const double2*>(rows_t + op_q * kIcpRowStride);
     double acc = 0.0;  // lane j: running total of sum j
     const float dmax_up = (float)sqrt(A.r2) * 1.000001f;  // d_max, rounded up
     const bool affine = sT[12] == 0.0 && sT[13] == 0.0 && sT[14] == 0.0 && sT[15] == 1.0;
@@ -890,23 +902,29 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                 if (!need) return;
                 float b = best, s2 = second;
                 int grp = -1;
-#pragma unroll 2
-                for (int gi = 0; gi < kept; gi += 4) {
-                    const float2 t01 = pair_t(S.buf, gi >> 1, f2x, f2y, f2z), t23 = pair_t(S.buf, (gi >> 1) + 1, f2x, f2y, f2z);
-                    const float m01 = fminf(t01.x, t01.y), M01 = fmaxf(t01.x, t01.y), m23 = fminf(t23.x, t23.y), M23 = fmaxf(t23.x, t23.y);
-                    const float m = fminf(m01, m23), Mm = fmaxf(m01, m23);
-                    const float sg = fminf(fminf(M01, M23), Mm);  // second smallest of the four
-                    s2 = fminf(s2, fminf(sg, fmaxf(m, b)));
-                    grp = m < b ? gi : grp;
-                    b = fminf(b, m);
+                // eight candidates (two quads of one slot group) per step along a running pointer: the group layout costs one
+                // conditional bump per step, no address arithmetic per quad; the padding covers the ragged tail
+                const float4* qp = S.buf;
+                for (int gi = 0; gi < kept; gi += 8) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 t = quad_t_at(qp + h, f2x, f2y, f2z);
+                        const float m01 = fminf(t.x, t.y), M01 = fmaxf(t.x, t.y), m23 = fminf(t.z, t.w), M23 = fmaxf(t.z, t.w);
+                        const float m = fminf(m01, m23), Mm = fmaxf(m01, m23);
+                        const float sg = fminf(fminf(M01, M23), Mm);  // second smallest of the four
+                        s2 = fminf(s2, fminf(sg, fmaxf(m, b)));
+                        grp = m < b ? gi + 4 * h : grp;
+                        b = fminf(b, m);
+                    }
+                    qp += (gi & 24) == 24 ? 26 : 2;  // next pair of quads; past the group's fourth pair, the next group
                 }
                 if (grp >= 0) {
                     // the new best sits in group grp: the first of the four that reproduces it (ties end up in the float64 path)
-                    const float2 t01 = pair_t(S.buf, grp >> 1, f2x, f2y, f2z), t23 = pair_t(S.buf, (grp >> 1) + 1, f2x, f2y, f2z);
+                    const float4 t = quad_t(S.buf, grp, f2x, f2y, f2z);
                     int w = grp + 3;
-                    if (t23.x == b) w = grp + 2;
-                    if (t01.y == b) w = grp + 1;
-                    if (t01.x == b) w = grp;
+                    if (t.z == b) w = grp + 2;
+                    if (t.y == b) w = grp + 1;
+                    if (t.x == b) w = grp;
                     wpos = S.pos[w];
                 }
                 best = b;
@@ -1039,13 +1057,19 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                 }
             }
 #pragma unroll
-            for (int j = 0; j < kIcpRow; ++j) rows[lane][j] = e[j];
+            for (int j = 0; j < kIcpRow; ++j) rows_t[j * kIcpRowStride + lane] = e[j];
             __syncwarp();
             if ((KIND == B3D_ICP_GENERALIZED || KIND == kIcpInformation) && row > 0 && lane >= 27) {
                 // count and sum d2 are taken once per correspondence (row 0)
             } else {
+                // fused multiply-add on purpose (the file is built with -fmad=false): the order of these sums is this kernel's own (lane
+                // order inside a chunk, chunk order inside a warp), nothing compares them bit for bit with the CPU
 #pragma unroll 8
-                for (int l = 0; l < 32; ++l) acc += rows[l][op_p] * rows[l][op_q];
+                for (int l2 = 0; l2 < 16; ++l2) {
+                    const double2 a = row_p[l2], b = row_q[l2];
+                    acc = fma(a.x, b.x, acc);
+                    acc = fma(a.y, b.y, acc);
+                }
             }
             __syncwarp();
         }

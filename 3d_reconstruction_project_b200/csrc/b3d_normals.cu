@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kNrmBlock) normals_staged_kernel(GridView<doub
 // Points that need the k-nearest cut (more than k in-radius neighbours, or more than 32), or whose box takes more than one
 // staging batch, are queued for the per-lane kernel exactly as before (their covariance slot is marked).
 #ifndef B3D_NRM2_CAP
-#define B3D_NRM2_CAP 476
+#define B3D_NRM2_CAP 472  // + 8 padding slots = 15 groups of 32: four blocks of four warps still fit one SM's shared memory
 #endif
 #ifndef B3D_NRM2_MIN_BLOCKS
 #define B3D_NRM2_MIN_BLOCKS 4
@@ -447,10 +447,12 @@ __global__ void __launch_bounds__(kNrmBlock, B3D_NRM2_MIN_BLOCKS) normals_cov2_k
             auto scan = [&](int kept) {
                 kept_all = kept;
                 if (!active) return;
-                for (int j = 0; j < kept; j += 2) {  // an odd tail pairs with a padding candidate at +inf
-                    const float2 t = pair_t(S.buf, j >> 1, f2x, f2y, f2z);
+                for (int j = 0; j < kept; j += 4) {  // a ragged tail meets padding candidates at +inf
+                    const float4 t = quad_t(S.buf, j, f2x, f2y, f2z);
                     take(t.x, j);
                     take(t.y, j + 1);
+                    take(t.z, j + 2);
+                    take(t.w, j + 3);
                 }
             };
             const int nb = stage2_run<kNrm2Cap>(g, F, cloud, lox, loy, loz, hix, hiy, hiz, S, parity, scan);

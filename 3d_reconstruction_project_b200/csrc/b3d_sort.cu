@@ -2,6 +2,8 @@
 // per-cloud bounds -> per-cloud lattice -> composite cell keys -> stable LSD radix sort of (key, point index) ->
 // run heads -> hashed cell table. All hand-written (the radix sort is b3d_radix.cu).
 #include "b3d_common.cuh"
+
+#include <cstdlib>
 #include "b3d_scan.cuh"
 #include "b3d_search.cuh"
 #include "b3d_stage2.cuh"
@@ -334,8 +336,13 @@ int grid_build(b3d_ctx* ctx, const T* xyz, const Segments& seg, double cell, con
     if (sizeof(T) == 8) B3D_TRY(out->rec.alloc(ctx, n));
     B3D_LAUNCH(ctx, gather_sorted_kernel<T>, ctx->grid_for(n, 256, 1, 16), 256, 0, xyz, out->sort.order.p, (int32_t)n, out->pts.p, out->sort.keys.p,
                out->sort.lat.p, out->sort.shift, sizeof(T) == 8 ? out->rec.p : (int4*)nullptr);
+    // Open addressing with linear probing; a warp's staging round waits for the SLOWEST of its 32 lookups, and most of them ask
+    // for empty cells (the box of a surface patch is mostly air), i.e. run to the first empty slot. At a load of 1/2 that is 2.5
+    // dependent loads on average and ~8 for the slowest lane; at 1/8 .. 1/16 nearly every lookup is ONE load. Slots are 16 bytes
+    // and touched sparsely, so the larger table costs address space, not cache (B3D_HASH_SLOTS_PER_CELL, default 8).
+    static const int per_cell = getenv("B3D_HASH_SLOTS_PER_CELL") ? std::max(2, atoi(getenv("B3D_HASH_SLOTS_PER_CELL"))) : 8;
     uint32_t n_slots = 1024;
-    while ((int64_t)n_slots < 2 * out->sort.n_runs) n_slots <<= 1;
+    while ((int64_t)n_slots < (int64_t)per_cell * out->sort.n_runs && n_slots < (1u << 30)) n_slots <<= 1;
     out->mask = n_slots - 1;
     out->cell = cell;
     B3D_TRY(out->slots.alloc(ctx, n_slots));

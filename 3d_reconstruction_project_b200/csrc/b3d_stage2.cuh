@@ -13,8 +13,9 @@
 //    lane issues the copy of the cell it probed) and waits ONCE on an mbarrier for all of them: no register staging, every copy
 //    of a box in flight at the same time.
 //  * The filter runs out of shared memory as one flat loop over the copied records (integer box test, ballot compaction IN
-//    PLACE) and leaves {float offset from the box centre, |offset|^2} (in units), two candidates interleaved per block, for
-//    the dot-product scan: three packed FFMA2 evaluate two candidates.
+//    PLACE) and leaves {float offset from the box centre, |offset|^2} (in units) in groups of 32 slots, component by component
+//    (x[32] y[32] z[32] w[32]: the filter's stores and the scan's 16-byte loads are free of bank conflicts), for the
+//    dot-product scan: six packed FFMA2 evaluate four candidates.
 //  * Boxes that do not fit the buffer are processed in several batches (the scan state lives in registers); only a single cell
 //    larger than the buffer, or a box of more than kStage2MaxCells cells, falls back to the per-lane walk.
 #pragma once
@@ -25,8 +26,9 @@ namespace b3d {
 
 template <int CAP>
 struct alignas(16) StageSmem {
-    float4 buf[CAP + 8];      // raw cell records (int4 bit patterns), then (in place) the filtered candidates in PAIR BLOCKS (below); +8: scan padding
-    int32_t pos[CAP + 8];     // sorted position of every filtered candidate
+    static constexpr int kSlots = (CAP + 8 + 31) / 32 * 32;  // whole groups of 32 slots; +8: scan padding
+    float4 buf[kSlots];       // raw cell records (int4 bit patterns), then (in place) the filtered candidates in SLOT GROUPS (below)
+    int32_t pos[kSlots];      // sorted position of every filtered candidate
     unsigned long long mbar;  // one phase per batch
     unsigned long long pad_;
 };
@@ -70,9 +72,11 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
                  "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
-// ---- filtered candidates: pair blocks ---------------------------------------------------------------------------------------
-// Candidate slot s lives in pair block s >> 1 = two float4: {x0 x1 y0 y1} {z0 z1 w0 w1} (offsets from the box centre in units,
-// w = |offset|^2): the scans evaluate t = w - 2 q.o for BOTH candidates of a block with three packed FFMA2 (fma.rn.f32x2).
+// ---- filtered candidates: slot groups ------------------------------------------------------------------------------------------
+// Candidate slot s lives in group s >> 5 (512 bytes: x[32] y[32] z[32] w[32], offsets from the box centre in units, w = |offset|^2)
+// at index s & 31. The filter writes consecutive slots to consecutive words (no bank conflicts; the pair blocks of the first
+// round-2 version cost 4 wavefronts per store), the scans read four candidates with four 16-byte loads and evaluate
+// t = w - 2 q.o for them with six packed FFMA2 (fma.rn.f32x2).
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     float2 d;
     asm("{.reg .b64 ra, rb, rc, rd;\n\t"
@@ -83,14 +87,27 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
         : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
     return d;
 }
-// t of the two candidates of pair block p for the query factors f = -2 q (each component duplicated into a float2)
-__device__ __forceinline__ float2 pair_t(const float4* __restrict__ buf, int p, float2 fx, float2 fy, float2 fz) {
-    const float4 lo = buf[2 * p], hi = buf[2 * p + 1];
-    return ffma2(fx, make_float2(lo.x, lo.y), ffma2(fy, make_float2(lo.z, lo.w), ffma2(fz, make_float2(hi.x, hi.y), make_float2(hi.z, hi.w))));
+__device__ __forceinline__ float* cand_slot(float4* buf, int s) { return reinterpret_cast<float*>(buf) + 128 * (s >> 5) + (s & 31); }
+__device__ __forceinline__ const float* cand_slot(const float4* buf, int s) { return reinterpret_cast<const float*>(buf) + 128 * (s >> 5) + (s & 31); }
+// t of the four candidates gi .. gi + 3 (gi a multiple of 4) for the query factors f = -2 q (each component duplicated into a float2)
+// (p: the quad's x entry, i.e. (const float4*)cand_slot(buf, gi))
+__device__ __forceinline__ float4 quad_t_at(const float4* __restrict__ p, float2 fx, float2 fy, float2 fz) {
+    const float4 X = p[0], Y = p[8], Z = p[16], W = p[24];
+    const float2 a = ffma2(fx, make_float2(X.x, X.y), ffma2(fy, make_float2(Y.x, Y.y), ffma2(fz, make_float2(Z.x, Z.y), make_float2(W.x, W.y))));
+    const float2 b = ffma2(fx, make_float2(X.z, X.w), ffma2(fy, make_float2(Y.z, Y.w), ffma2(fz, make_float2(Z.z, Z.w), make_float2(W.z, W.w))));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float4 quad_t(const float4* __restrict__ buf, int gi, float2 fx, float2 fy, float2 fz) {
+    return quad_t_at(reinterpret_cast<const float4*>(cand_slot(buf, gi)), fx, fy, fz);
+}
+// t of the two candidates s, s + 1 (s even)
+__device__ __forceinline__ float2 pair_t(const float4* __restrict__ buf, int s, float2 fx, float2 fy, float2 fz) {
+    const float2* p = reinterpret_cast<const float2*>(cand_slot(buf, s));
+    return ffma2(fx, p[0], ffma2(fy, p[16], ffma2(fz, p[32], p[48])));
 }
 __device__ __forceinline__ float cand_t(const float4* __restrict__ buf, int s, float2 fx, float2 fy, float2 fz) {
-    const float2 t = pair_t(buf, s >> 1, fx, fy, fz);
-    return (s & 1) ? t.y : t.x;
+    const float* p = cand_slot(buf, s);
+    return fmaf(fx.x, p[0], fmaf(fy.x, p[32], fmaf(fz.x, p[64], p[96])));
 }
 
 // orders this thread's earlier generic-proxy accesses of shared memory before later async-proxy (bulk copy) writes
@@ -136,7 +153,7 @@ __device__ __forceinline__ int unit_ceil_clamped(double v) { return __double2int
 constexpr int kStage2MaxCells = 1024;  // cells of one box; beyond that (or beyond 256 on an axis) the caller falls back
 
 // Stages every point of `cloud` with lo <= record <= hi (absolute units, per axis; lo/hi identical on all lanes) batch by batch and
-// calls scan(kept) after each batch has been filtered: candidate slots [0, kept) in the pair blocks of S.buf (float offsets from the
+// calls scan(kept) after each batch has been filtered: candidate slots [0, kept) in the slot groups of S.buf (float offsets from the
 // box centre c = (lo + hi) >> 1 and their squared length, in units), S.pos[0..kept) = sorted positions, then padding slots at +inf.
 // Returns the number of batches scanned (0: the box holds no point), or -1 when the caller has to fall back (box too large or
 // one cell with more than CAP points). parity: the warp's mbarrier phase.
@@ -242,7 +259,6 @@ __device__ __forceinline__ int stage2_run(const GridView<double>& g, const UnitF
             parity ^= 1u;
             int kept = 0;
             const int4* raw = reinterpret_cast<const int4*>(S.buf);
-            float* fbuf = reinterpret_cast<float*>(S.buf);
             for (int j0 = 0; j0 < fill; j0 += 32) {
                 const int j = j0 + lane;
                 bool inside = false;
@@ -255,16 +271,16 @@ __device__ __forceinline__ int stage2_run(const GridView<double>& g, const UnitF
                 if (inside) {
                     const int slot = kept + __popc(m & ((1u << lane) - 1u));
                     const float ox = (float)(r.x - ccx), oy = (float)(r.y - ccy), oz = (float)(r.z - ccz);
-                    // in place: the block of slots (s & ~1, s | 1) overlays raw records of the same indices, all of them read already
-                    float* d = fbuf + 8 * (slot >> 1) + (slot & 1);
-                    d[0] = ox; d[2] = oy; d[4] = oz; d[6] = fmaf(oz, oz, fmaf(oy, oy, ox * ox));
+                    // in place: the group of slot s overlays the raw records 32 (s >> 5) .. + 31, all of them read already (s <= j0 + 31)
+                    float* d = cand_slot(S.buf, slot);
+                    d[0] = ox; d[32] = oy; d[64] = oz; d[96] = fmaf(oz, oz, fmaf(oy, oy, ox * ox));
                     S.pos[slot] = r.w;
                 }
                 kept += __popc(m);
             }
-            if (lane < 6) {  // padding candidates at +inf: the scans run in steps of four slots
-                float* d = fbuf + 8 * ((kept + lane) >> 1) + ((kept + lane) & 1);
-                d[0] = 0.f; d[2] = 0.f; d[4] = 0.f; d[6] = 3.0e38f;
+            if (lane < 8) {  // padding candidates at +inf: the scans run in steps of four or eight slots
+                float* d = cand_slot(S.buf, kept + lane);
+                d[0] = 0.f; d[32] = 0.f; d[64] = 0.f; d[96] = 3.0e38f;
             }
             __syncwarp();
             scan(kept);
