@@ -700,7 +700,7 @@ __device__ __noinline__ void icp2_finish_pair(const IcpKernelArgs& A, int pair, 
                 double v;
                 asm volatile("ld.acquire.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(flag) : "memory");
                 if (v == stamp) break;
-                if (clock64() - t0c > 4000000000ll) {  // ~2 s: a peer never arrived
+                if (clock64() - t0c > 20000000000ll) {  // ~10 s (a rank may lag by a module load on a cold box): a peer never arrived
                     timeout = 1;
                     break;
                 }
@@ -828,6 +828,8 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
         }
         // ---- correspondence: sticky check, then one staged search bounded by the distance to the previous partner ---------
         double d2 = 0.0;
+        double nr0 = 0.0, nr1 = 0.0, nr2 = 0.0;  // the partner's normal when the search fetched it together with the point
+        bool have_nrm = false;
         int idx = 0, pos = -1;
         double4 q = make_double4(0.0, 0.0, 0.0, 0.0);  // the partner's point record
         bool need = valid;
@@ -953,8 +955,9 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                 if (pos >= 0) {
                     q = ld_point(A.grid.pts + pos);
                     if (KIND == B3D_ICP_POINT_TO_PLANE) {  // the normal's latency runs in parallel with the point's
-                        prefetch_l1(A.tgt_nrm_sorted + 3 * (int64_t)pos);
-                        prefetch_l1(A.tgt_nrm_sorted + 3 * (int64_t)pos + 2);
+                        const double* nq = A.tgt_nrm_sorted + 3 * (int64_t)pos;
+                        nr0 = __ldg(nq); nr1 = __ldg(nq + 1); nr2 = __ldg(nq + 2);
+                        have_nrm = true;
                     }
                     d2 = dist2<double>(px - q.x, py - q.y, pz - q.z);
                     idx = point_index(q);
@@ -963,6 +966,7 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                     if (ambiguous) {
                         const int tpos = icp2_resolve_ties(A.grid.pts, S.buf, S.pos, last_kept, fx, fy, fz, best + band_w, px, py, pz, wpos, d2, idx);
                         if (tpos != pos) {
+                            have_nrm = false;
                             pos = tpos;
                             q = ld_point(A.grid.pts + pos);
                             d2 = dist2<double>(px - q.x, py - q.y, pz - q.z);
@@ -1006,8 +1010,11 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                     e[0] = px; e[1] = py; e[2] = pz;
                     e[3] = q.x; e[4] = q.y; e[5] = q.z;
                 } else if (KIND == B3D_ICP_POINT_TO_PLANE) {
-                    const double* nq = A.tgt_nrm_sorted + 3 * (int64_t)pos;
-                    const double n0 = __ldg(nq), n1 = __ldg(nq + 1), n2 = __ldg(nq + 2);
+                    if (!have_nrm) {
+                        const double* nq = A.tgt_nrm_sorted + 3 * (int64_t)pos;
+                        nr0 = __ldg(nq); nr1 = __ldg(nq + 1); nr2 = __ldg(nq + 2);
+                    }
+                    const double n0 = nr0, n1 = nr1, n2 = nr2;
                     e[0] = py * n2 - pz * n1; e[1] = pz * n0 - px * n2; e[2] = px * n1 - py * n0;
                     e[3] = n0; e[4] = n1; e[5] = n2;
                     e[6] = (px - q.x) * n0 + (py - q.y) * n1 + (pz - q.z) * n2;
@@ -1186,7 +1193,6 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
     }
     B3D_LAUNCH(ctx, icp_init_state_kernel, (P + 127) / 128, 128, 0, w->state.p, init_h ? init_d.p : (const double*)nullptr, P);
     const Grid<double>& g = *pb.tgt_grid;
-    const int32_t nt = (int32_t)g.sort.n;
     // order the source points along a Morton curve of the target lattice and cut them into compact warp chunks
     B3D_TRY(build_query_chunks(ctx, pb.src, pb.src_off, pb.src_off_h, g.sort, reinterpret_cast<const double*>(w->state.p),
                                (int)(sizeof(IcpPairState) / sizeof(double)), &w->chunks));
@@ -1206,6 +1212,7 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
     // partial-sum groups per pair depend only on that pair's own chunk count (results do not depend on the batch)
     w->blocks = icp_groups(w->chunks.most);
     B3D_TRY(w->partial.alloc(ctx, (size_t)P * w->blocks * kIcpSums));
+    const int32_t nt = (int32_t)g.sort.n;
     if (pb.kind == B3D_ICP_POINT_TO_PLANE) {
         B3D_TRY(w->tgt_nrm_sorted.alloc(ctx, (size_t)nt * 3));
         B3D_LAUNCH(ctx, gather_by_sorted_kernel, ctx->grid_for((int64_t)nt * 3, 256, 1, 8), 256, 0, g.pts.p, nt, pb.tgt_normals, 3, w->tgt_nrm_sorted.p);

@@ -54,6 +54,32 @@ __device__ __forceinline__ bool grid_lookup(const GridView<T>& g, unsigned long 
     }
 }
 
+// two lookups side by side: both first slot loads are issued before either is looked at (want0 / want1: whether to look at all;
+// a missing or unwanted cell returns start == end == 0)
+template <typename T>
+__device__ __forceinline__ void grid_lookup2(const GridView<T>& g, bool want0, unsigned long long key0, bool want1, unsigned long long key1, int& start0,
+                                             int& end0, int& start1, int& end1) {
+    uint32_t s0 = hash_key(key0) & g.mask, s1 = hash_key(key1) & g.mask;
+    uint4 r0 = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u), r1 = r0;  // kEmptyKey: nothing there
+    if (want0) r0 = __ldg(reinterpret_cast<const uint4*>(g.slots + s0));
+    if (want1) r1 = __ldg(reinterpret_cast<const uint4*>(g.slots + s1));
+    start0 = end0 = start1 = end1 = 0;
+    while (true) {
+        const unsigned long long k = ((unsigned long long)r0.y << 32) | r0.x;
+        if (k == key0) { start0 = (int)r0.z; end0 = (int)r0.w; break; }
+        if (k == kEmptyKey) break;
+        s0 = (s0 + 1) & g.mask;
+        r0 = __ldg(reinterpret_cast<const uint4*>(g.slots + s0));
+    }
+    while (true) {
+        const unsigned long long k = ((unsigned long long)r1.y << 32) | r1.x;
+        if (k == key1) { start1 = (int)r1.z; end1 = (int)r1.w; break; }
+        if (k == kEmptyKey) break;
+        s1 = (s1 + 1) & g.mask;
+        r1 = __ldg(reinterpret_cast<const uint4*>(g.slots + s1));
+    }
+}
+
 template <typename T>
 struct SearchSlack;
 template <>

@@ -187,25 +187,39 @@ __device__ __forceinline__ int stage2_run(const GridView<double>& g, const UnitF
     bool pending = false;
     int lane_cursor = 32;  // < 32: the pending round is being issued one cell at a time, next cell = lane_cursor
     int s = 0, cnt = 0, incl = 0, total = 0;
+    int s_nx = 0, cnt_nx = 0;  // the second half of a 64-cell probe, queued as the next round
+    bool have_nx = false;
+    // cell ci of the box -> its slice of the grid (count 0: empty cell); the first slot load of both halves of a probe are independent
+    auto cell_key = [&](int ci) {
+        const int t = (int)(((float)ci + 0.5f) * rz);
+        const int zc = ci - t * cnz;
+        const int xc = (int)(((float)t + 0.5f) * ry);
+        const int yc = t - xc * cny;
+        return grid_slot_key(g.shift, cloud, cx0 + xc, cy0 + yc, cz0 + zc);
+    };
     for (;;) {
         bool cells_left = true;
         for (;;) {
             if (!pending) {
-                if (base >= ncell) {
-                    cells_left = false;
-                    break;
-                }
-                const int ci = base + lane;
-                base += 32;
-                s = 0;
-                cnt = 0;
-                if (ci < ncell) {
-                    const int t = (int)(((float)ci + 0.5f) * rz);
-                    const int zc = ci - t * cnz;
-                    const int xc = (int)(((float)t + 0.5f) * ry);
-                    const int yc = t - xc * cny;
-                    int e;
-                    if (grid_lookup(g, grid_slot_key(g.shift, cloud, cx0 + xc, cy0 + yc, cz0 + zc), s, e)) cnt = e - s;
+                if (have_nx) {
+                    s = s_nx;
+                    cnt = cnt_nx;
+                    have_nx = false;
+                } else {
+                    if (base >= ncell) {
+                        cells_left = false;
+                        break;
+                    }
+                    // 64 cells per probe, two per lane: the two hash lookups run side by side (one memory latency instead of two
+                    // for the typical 3 x 4 x 3-cell box); the second half is queued as the next round
+                    const int ci = base + lane, cj = base + 32 + lane;
+                    have_nx = base + 32 < ncell;
+                    base += 64;
+                    s = 0; cnt = 0; s_nx = 0; cnt_nx = 0;
+                    int e0 = 0, e1 = 0;
+                    grid_lookup2(g, ci < ncell, cell_key(ci), cj < ncell, cell_key(cj), s, e0, s_nx, e1);
+                    cnt = e0 - s;
+                    cnt_nx = e1 - s_nx;
                 }
                 if (__any_sync(0xffffffffu, cnt > CAP)) return -1;  // one cell alone overflows the buffer
                 incl = cnt;
@@ -290,7 +304,7 @@ __device__ __forceinline__ int stage2_run(const GridView<double>& g, const UnitF
             fill = 0;
             ++batches;
         }
-        if (!cells_left && !pending) break;
+        if (!cells_left && !pending && !have_nx) break;
     }
     return batches;
 }

@@ -137,6 +137,8 @@ class ShardedICP:
         views = [hdl.get_buffer(r, (n,), torch.float64) for r in range(world)]
         for v in views:
             assert float(v.sum().item()) == 0.0
+        # nobody may launch its first fused pass (it writes into every peer's buffer) while a slower rank is still checking
+        dist.barrier(group)
         ptrs = (C.c_void_p * world)(*[C.c_void_p(v.data_ptr()) for v in views])
         N.check(N.lib().b3d_icp_set_peers(self.ctx.handle, self.handle, rank, world, ptrs))
         self._peer = (buf, hdl, views)  # keep the mapping alive

@@ -330,7 +330,7 @@ def test_fused_peer_exchange_two_gpus(b3):
         assert r.returncode == 0, r.stderr[-2000:]
         out.append(json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1]))
     for key in ("fitness", "inlier_rmse", "rot_err_rad", "trans_err_m", "iterations", "passes"):
-        assert out[0][key] == out[1][key], key
+        assert out[0][key] == out[1][key], (key, out[0], out[1])
     assert out[1]["exchange"].startswith("peer-memory")
 
 
