@@ -52,62 +52,59 @@ __host__ __device__ inline int icp_groups(int chunks) {
     g = g > kIcpMaxGroups ? kIcpMaxGroups : g;
     return g < 1 ? 1 : g;
 }
+constexpr int kIcpMaxRunLog2 = 6;  // runs of up to 64 chunk groups (1024 chunks)
 constexpr double kIcpReach2 = 1.25;   // search radius of a lane that found nothing last time, in units of d_max (see the pass kernel)
 
 // ---- small dense helpers (device) ----------------------------------------------------------------------------------
-// (M^-1)^(1/2) of a symmetric positive-definite 3x3 (GICP weight, one per correspondence per pass). Closed-form
-// eigen-decomposition (the trigonometric solver of b3d_common.cuh, all three eigenpairs): W = sum_i lambda_i^(-1/2) v_i v_i^T
-// with an orthonormal basis by construction. The CPU oracle iterates Jacobi sweeps to an exactly diagonal matrix; both are
-// accurate to a few ulp, the closed form costs a tenth of the instructions (profiles/r01g_ncu_gicp_jacobi_digest.txt).
-__device__ void inv_sqrt_sym3(const double* M, double* W) {
-    Sym3<double> A{M[0], M[1], M[2], M[4], M[5], M[8]};
-    double mx = A.a00;
-    mx = A.a01 > mx ? A.a01 : mx;
-    mx = A.a02 > mx ? A.a02 : mx;
-    mx = A.a11 > mx ? A.a11 : mx;
-    mx = A.a12 > mx ? A.a12 : mx;
-    mx = A.a22 > mx ? A.a22 : mx;
-    double lam[3] = {M[0], M[4], M[8]};
-    Vec3<double> v[3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-    if (mx > 0) {
-        A.a00 /= mx; A.a01 /= mx; A.a02 /= mx; A.a11 /= mx; A.a12 /= mx; A.a22 /= mx;
-        const double norm = A.a01 * A.a01 + A.a02 * A.a02 + A.a12 * A.a12;
-        if (norm > 0) {
-            const double q = (A.a00 + A.a11 + A.a22) / 3;
-            const double b00 = A.a00 - q, b11 = A.a11 - q, b22 = A.a22 - q;
-            const double p = sqrt((b00 * b00 + b11 * b11 + b22 * b22 + norm * 2) / 6);
-            const double c00 = b11 * b22 - A.a12 * A.a12;
-            const double c01 = A.a01 * b22 - A.a12 * A.a02;
-            const double c02 = A.a01 * A.a12 - b11 * A.a02;
-            const double det = (b00 * c00 - A.a01 * c01 + A.a02 * c02) / (p * p * p);
-            double half = det * 0.5;
-            half = half < -1.0 ? -1.0 : (half > 1.0 ? 1.0 : half);
-            const double angle = acos(half) / 3.0;
-            const double beta2 = cos(angle) * 2;
-            const double beta0 = cos(angle + 2.09439510239319549) * 2;
-            const double beta1 = -(beta0 + beta2);
-            const double e0 = q + p * beta0, e1 = q + p * beta1, e2 = q + p * beta2;
-            if (half >= 0) {
-                v[2] = sym3_eigvec0(A, e2);
-                v[1] = sym3_eigvec1(A, v[2], e1);
-                v[0] = cross3(v[1], v[2]);
-            } else {
-                v[0] = sym3_eigvec0(A, e0);
-                v[1] = sym3_eigvec1(A, v[0], e1);
-                v[2] = cross3(v[0], v[1]);
+// (M^-1)^(1/2) of a symmetric positive-definite 3x3 (GICP weight, one per correspondence per pass) by the coupled Newton-Schulz
+// iteration  T = (3 I - Z Y) / 2,  Y <- Y T,  Z <- T Z  from  Y = M / trace(M), Z = I  (Y -> (M/s)^(1/2), Z -> (M/s)^(-1/2)):
+// three 3x3 products per step in a loop of ~120 instructions, 14-20 steps for the covariances GICP builds (eigenvalues 1e-3 .. 2),
+// relative error ~1e-14 against scipy's sqrtm(inv(M)). The closed-form eigen-decomposition used before (and the Jacobi sweeps of the
+// CPU oracle) is as accurate, but it is ~2 500 straight-line float64 instructions (divisions, square roots, acos, cos): with it in
+// the pass kernel a third of the warps' time went to instruction fetch (profiles/r02e_c3_gicp_stalls.txt). FULL products on
+// purpose: the iteration is only stable with the exact product structure (an upper-triangle shortcut diverges).
+__device__ __noinline__ void inv_sqrt_sym3(const double* M, double* W) {
+    const double s = M[0] + M[4] + M[8];  // >= the largest eigenvalue of a positive-definite M
+    if (!(s > 0.0) || !(s < 1.0e300)) {   // not positive definite / not finite: the diagonal rule of the closed form's fallback
+#pragma unroll
+        for (int i = 0; i < 9; ++i) W[i] = 0.0;
+        W[0] = 1.0 / sqrt(M[0]); W[4] = 1.0 / sqrt(M[4]); W[8] = 1.0 / sqrt(M[8]);
+        return;
+    }
+    const double inv_s = 1.0 / s;
+    double Y[9], Z[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Y[i] = M[i] * inv_s;
+#pragma unroll 1
+    for (int it = 0; it < 100; ++it) {
+        double T[9], P[9];
+        double err = 0.0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double zy = fma(Z[3 * r], Y[c], fma(Z[3 * r + 1], Y[3 + c], Z[3 * r + 2] * Y[6 + c]));
+                const double t = (r == c ? 1.5 : 0.0) - 0.5 * zy;
+                T[3 * r + c] = t;
+                err = fmax(err, fabs(t - (r == c ? 1.0 : 0.0)));
             }
-            lam[0] = e0 * mx; lam[1] = e1 * mx; lam[2] = e2 * mx;
-        }
-    }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) W[i] = 0.0;
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const double f = 1.0 / sqrt(lam[k]);
-        const double vx = v[k].x, vy = v[k].y, vz = v[k].z;
-        W[0] += f * vx * vx; W[1] += f * vx * vy; W[2] += f * vx * vz;
-        W[4] += f * vy * vy; W[5] += f * vy * vz; W[8] += f * vz * vz;
+            for (int c = 0; c < 3; ++c) P[3 * r + c] = fma(Y[3 * r], T[c], fma(Y[3 * r + 1], T[3 + c], Y[3 * r + 2] * T[6 + c]));
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Y[i] = P[i];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) P[3 * r + c] = fma(T[3 * r], Z[c], fma(T[3 * r + 1], Z[3 + c], T[3 * r + 2] * Z[6 + c]));
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Z[i] = P[i];
+        if (!(err >= 1.0e-14)) break;  // converged (quadratically: this step already took the error to ~1e-28), or NaN
     }
+    const double f = 1.0 / sqrt(s);
+    W[0] = Z[0] * f; W[1] = Z[1] * f; W[2] = Z[2] * f;
+    W[4] = Z[4] * f; W[5] = Z[5] * f; W[8] = Z[8] * f;
     W[3] = W[1]; W[6] = W[2]; W[7] = W[5];
 }
 
@@ -218,6 +215,8 @@ struct IcpKernelArgs {
     int peer_world, peer_rank;
     double* peer_buf[8];
     int stats;  // count chunks / rounds / staged candidates into g_icp_stats
+    int run_log2;    // round-2 kernel: a run = 2^run_log2 adjacent chunk groups (the level of the sum tree a launch's blocks work at)
+    int run_stride;  // round-2 kernel: nodes reserved per pair and strand in `partial` (>= every pair's run count)
 };
 
 // Source points are visited in the order of the TARGET cell they fall into (sorted once per ICP run, icp_prepare), so the
@@ -646,31 +645,43 @@ __device__ __noinline__ int icp2_resolve_ties(const double4* __restrict__ pts, c
     return pos;
 }
 
-// cold: the last warp of the last block of a pair -- the pair's rows in a fixed order (lane j sums column j), the optional
-// all-reduce over peer memory, and the solve / update of the loop state
-__device__ __noinline__ void icp2_finish_pair(const IcpKernelArgs& A, int pair, int groups, int ns_local) {
+// cold: the last block of a pair -- warp w adds strand w's run nodes up to the strand's root (lane j: sum j). Node i of the next level
+// = node 2i + node 2i+1 (an odd last node moves up alone), in place; sixteen outputs (32 loads) are in flight per step.
+__device__ __noinline__ double icp2_reduce_strand(const IcpKernelArgs& A, int pair, int n_runs, int strand) {
+    const int lane = threadIdx.x & 31;
+    if (lane >= kIcpSums) return 0.0;
+    const int64_t step = 4 * kIcpSums;  // doubles between consecutive runs of one strand
+    double* col = A.partial + ((int64_t)pair * A.run_stride * 4 + strand) * kIcpSums + lane;
+    int n = n_runs;
+    while (n > 1) {
+        const int nn = (n + 1) >> 1;
+        for (int i0 = 0; i0 < nn; i0 += 16) {
+            double t[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const int j = 2 * i0 + k;
+                t[k] = j < n ? __ldcg(col + (int64_t)j * step) : 0.0;
+            }
+#pragma unroll
+            for (int o = 0; o < 16; ++o) {
+                if (i0 + o < nn) {
+                    double v = t[2 * o];
+                    if (2 * (i0 + o) + 1 < n) v += t[2 * o + 1];
+                    __stcg(col + (int64_t)(i0 + o) * step, v);
+                }
+            }
+        }
+        n = nn;
+    }
+    return __ldcg(col);
+}
+
+// cold: warp 0 of the last block of a pair with the pair's 29 sums (lane j: sum j) -- the optional all-reduce over peer memory, and
+// the solve / update of the loop state
+__device__ __noinline__ void icp2_finish_pair(const IcpKernelArgs& A, int pair, double total, int ns_local) {
     const int lane = threadIdx.x & 31;
     IcpPairState* st = A.state + pair;
-    const double* base = A.partial + (int64_t)pair * gridDim.x * kIcpSums;
-    double total = 0.0;
-    if (lane < kIcpSums) {
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-        int b = 0;
-        for (; b + 16 <= groups; b += 16) {
-            double t[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) t[k] = __ldcg(base + (int64_t)(b + k) * kIcpSums + lane);
-#pragma unroll
-            for (int k = 0; k < 16; k += 4) { v0 += t[k]; v1 += t[k + 1]; v2 += t[k + 2]; v3 += t[k + 3]; }
-        }
-        for (; b < groups; ++b) {
-            const double t = __ldcg(base + (int64_t)b * kIcpSums + lane);
-            const int r = b & 3;
-            if (r == 0) v0 += t; else if (r == 1) v1 += t; else if (r == 2) v2 += t; else v3 += t;
-        }
-        total = (v0 + v1) + (v2 + v3);
-        A.sums[(int64_t)pair * kIcpSums + lane] = total;
-    }
+    if (lane < kIcpSums) A.sums[(int64_t)pair * kIcpSums + lane] = total;
     __syncwarp();
     if (A.peer_world > 1) {
         // ---- all-reduce over peer memory. Buffer of a rank: slots [2 parities][world][32] doubles, then flags [2][world]
@@ -757,17 +768,29 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
     const int pair = blockIdx.y;
     IcpPairState* st = A.state + pair;
     __shared__ double sT[16];
-    __shared__ double sm[kIcpBlock / 32][32];
-    __shared__ unsigned int s_arrived;
+    static_assert(kIcpBlock == 128, "the sum tree is built on four warps per block");
+    __shared__ double stk[kIcpMaxRunLog2 + 1][kIcpBlock / 32][32];  // [level][warp][sum]: the waiting nodes of the run under way
+    __shared__ double s_tot[kIcpBlock / 32][32];                     // the strands' totals (last block of a pair)
+    __shared__ unsigned int s_ticket;
     const int done = st->done;
     if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
-    if (threadIdx.x == 0) s_arrived = 0u;
     const int32_t s0 = A.src_off[pair], s1 = A.src_off[pair + 1];
     const int32_t t0 = A.tgt_off[pair];
     const int32_t c0 = A.chunk_off[pair], c1 = A.chunk_off[pair + 1];
     if (done) return;  // uniform over the block
-    const int groups = icp_groups(c1 - c0);
-    if ((int)blockIdx.x >= groups) return;
+    // The 29 sums of a pair are added in a FIXED order that no launch parameter can change, so a pair's result is bit-identical alone
+    // and inside any batch, on any grid. The chunks are dealt to four STRANDS (chunk i of the pair belongs to strand i mod 4 = the
+    // warp that takes it); a GROUP is 16 consecutive chunks; a strand's LEAF is the chain (from zero, in order) over its four chunks
+    // of a group; each strand adds its leaves in a binary tree over the groups (node i of a level = node 2i + node 2i+1 of the level
+    // below, an odd last node moves up alone); the pair's sum is ((T0 + T1) + T2) + T3 over the strands' roots. A launch chooses freely
+    // (from the size of the whole batch: icp_prepare) how many adjacent groups form a RUN (2^run_log2: a warp builds the strand's node
+    // of a run on its own, with a binary counter in shared memory, no hand-shake between warps) and how many blocks share a pair's
+    // runs (block b takes runs b, b + gridDim.x, ...): a big batch runs long-lived blocks, a single pair is cut to fill the machine
+    // exactly. The pair's last block adds the levels above the runs (one strand per warp) and finishes the pass.
+    const int32_t n_groups = max(1, (c1 - c0 + 15) >> 4);  // an empty source has one empty group: block 0 still finishes its pass
+    const int32_t n_runs = (n_groups + (1 << A.run_log2) - 1) >> A.run_log2;
+    const int n_active = min((int)gridDim.x, (int)n_runs);  // blocks of this pair that have a run
+    if ((int)blockIdx.x >= n_active) return;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Icp2Smem& S = reinterpret_cast<Icp2Smem*>(icp2_smem)[warp];
@@ -784,326 +807,329 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
     double acc = 0.0;  // lane j: running total of sum j
     const float dmax_up = (float)sqrt(A.r2) * 1.000001f;  // d_max, rounded up
     const bool affine = sT[12] == 0.0 && sT[13] == 0.0 && sT[14] == 0.0 && sT[15] == 1.0;
-    // A block owns a CONTIGUOUS range of the pair's chunks (Hilbert neighbours: their boxes overlap, so the hash slots, the partner
-    // gathers and the normals one warp's chunk touched are in L1 for the next one); the warps interleave inside the range.
-    const int32_t c_per = (c1 - c0 + groups - 1) / groups;
-    const int32_t c_step = kIcpBlock / 32;
-    int32_t c = c0 + (int32_t)blockIdx.x * c_per + warp;
-    const int32_t c_end = min(c1, c0 + ((int32_t)blockIdx.x + 1) * c_per);
-    for (; c < c_end; c += c_step) {
-        // The warp's next chunk is announced to the caches, not held in registers (prefetching into registers spilled): its source
-        // points and sticky state are prefetched into L1 once this chunk's own loads are under way; the one word that is fetched
-        // for real (the previous partner's position) addresses the prefetch of that partner's point and normal.
-        const int32_t si = A.chunk_start[c] + lane;
-        const bool valid = si < A.chunk_start[c + 1];
-        int32_t nsi = -1, nkp = -1;
-        if (c + c_step < c_end) {
-            nsi = A.chunk_start[c + c_step] + lane;
-            if (nsi >= s1) nsi = -1;
-            else if (A.keep_pos != nullptr) nkp = A.keep_pos[nsi];
-        }
-        double4 sp = make_double4(0.0, 0.0, 0.0, 0.0);
-        float4 kr = make_float4(0.f, 0.f, 0.f, 0.f);
-        int kp = -1;
-        if (valid) {
-            sp = ld_point(A.src_sorted + si);
-            if (A.keep_ref != nullptr) {
-                kr = A.keep_ref[si];
-                kp = A.keep_pos[si];
-            }
-        }
-        double px = 0, py = 0, pz = 0;
-        int oi = 0;
-        if (valid) {
-            oi = point_index(sp);  // original (batch-global) source index
-            const double x = sp.x, y = sp.y, z = sp.z;
-            // PointCloud::Transform: (T [p,1]).xyz / w
-            px = sT[0] * x + sT[1] * y + sT[2] * z + sT[3];
-            py = sT[4] * x + sT[5] * y + sT[6] * z + sT[7];
-            pz = sT[8] * x + sT[9] * y + sT[10] * z + sT[11];
-            if (!affine) {
-                const double w = icp2_perspective_w(sT, x, y, z);
-                px /= w; py /= w; pz /= w;
-            }
-        }
-        // ---- correspondence: sticky check, then one staged search bounded by the distance to the previous partner ---------
-        double d2 = 0.0;
-        double nr0 = 0.0, nr1 = 0.0, nr2 = 0.0;  // the partner's normal when the search fetched it together with the point
-        bool have_nrm = false;
-        int idx = 0, pos = -1;
-        double4 q = make_double4(0.0, 0.0, 0.0, 0.0);  // the partner's point record
-        bool need = valid;
-        float reach = dmax_up;  // this lane's search radius (float32, rounded up where it matters)
-        if (valid && A.keep_ref != nullptr) {
-            // Everything here is a conservative float32 bound: movement and distances rounded UP, the stored bound was rounded DOWN.
-            // movement since the last search (+ the float roundings of the stored and of the current position)
-            const float pxf = (float)px, pyf = (float)py, pzf = (float)pz;
-            const float mx = pxf - kr.x, my = pyf - kr.y, mz = pzf - kr.z;
-            const float moved = sqrtf(fmaf(mz, mz, fmaf(my, my, mx * mx))) * 1.000001f + 4.0e-7f * (fabsf(pxf) + fabsf(pyf) + fabsf(pzf));
-            const float lim = kr.w;  // every other target point was at least this far from the stored position (0: unknown)
-            if (kp >= 0) {
-                q = ld_point(A.grid.pts + kp);
-                if (KIND == B3D_ICP_POINT_TO_PLANE) prefetch_l1(A.tgt_nrm_sorted + 3 * (int64_t)kp);  // most lanes keep this partner
-                const double dk = dist2<double>(px - q.x, py - q.y, pz - q.z);
-                const float u = sqrtf((float)dk) * 1.000001f;
-                if ((u + moved) * 1.000001f < lim) {  // still strictly nearer than anything else can be
-                    need = false;
-                    pos = kp;
-                    d2 = dk;
-                    idx = point_index(q);
-                } else {
-                    const float slack = fminf(fmaxf(0.5f * moved, 0.01f * dmax_up), 0.1f * dmax_up);
-                    reach = fminf(u + slack, dmax_up);  // nothing beyond d_max counts anyway
+    // The warps of a block interleave over the chunks of a group (Hilbert neighbours at the same time: the hash slots, partner gathers
+    // and normals one warp fetched are in L1 for the other three; a contiguous range per warp measured 15 % slower), a block walks the
+    // runs b, b + gridDim.x, ... of its pair (R adjacent groups each: consecutive groups overlap in space).
+    const int R = 1 << A.run_log2;
+    for (int32_t r = blockIdx.x; r < n_runs; r += (int32_t)gridDim.x) {
+        int m = 0;  // leaves of this run pushed so far
+        for (int gi = 0; gi < R; ++gi) {
+            const int32_t g = r * R + gi;
+            if (g >= n_groups) break;
+            const int32_t ce = min(c1, c0 + 16 * g + 16);
+            for (int32_t c = c0 + 16 * g + warp; c < ce; c += kIcpBlock / 32) {
+                const int32_t si = A.chunk_start[c] + lane;
+                const bool valid = si < A.chunk_start[c + 1];
+                double4 sp = make_double4(0.0, 0.0, 0.0, 0.0);
+                float4 kr = make_float4(0.f, 0.f, 0.f, 0.f);
+                int kp = -1;
+                if (valid) {
+                    sp = ld_point(A.src_sorted + si);
+                    if (A.keep_ref != nullptr) {
+                        kr = A.keep_ref[si];
+                        kp = A.keep_pos[si];
+                    }
                 }
-            } else if (lim > 0.0f) {
-                if ((dmax_up + moved) * 1.000001f < lim) need = false;  // nothing was within lim, nothing can be within d_max now
-                else if (moved < 0.5f * ((float)kIcpReach2 - 1.0f) * dmax_up) reach = dmax_up * (float)kIcpReach2;
-            }
-        }
-        const unsigned int need_mask = __ballot_sync(0xffffffffu, need);
+                double px = 0, py = 0, pz = 0;
+                int oi = 0;
+                if (valid) {
+                    oi = point_index(sp);  // original (batch-global) source index
+                    const double x = sp.x, y = sp.y, z = sp.z;
+                    // PointCloud::Transform: (T [p,1]).xyz / w
+                    px = sT[0] * x + sT[1] * y + sT[2] * z + sT[3];
+                    py = sT[4] * x + sT[5] * y + sT[6] * z + sT[7];
+                    pz = sT[8] * x + sT[9] * y + sT[10] * z + sT[11];
+                    if (!affine) {
+                        const double w = icp2_perspective_w(sT, x, y, z);
+                        px /= w; py /= w; pz /= w;
+                    }
+                }
+                // ---- correspondence: sticky check, then one staged search bounded by the distance to the previous partner ---------
+                double d2 = 0.0;
+                double nr0 = 0.0, nr1 = 0.0, nr2 = 0.0;  // the partner's normal when the search fetched it together with the point
+                bool have_nrm = false;
+                int idx = 0, pos = -1;
+                double4 q = make_double4(0.0, 0.0, 0.0, 0.0);  // the partner's point record
+                bool need = valid;
+                float reach = dmax_up;  // this lane's search radius (float32, rounded up where it matters)
+                if (valid && A.keep_ref != nullptr) {
+                    // Everything here is a conservative float32 bound: movement and distances rounded UP, the stored bound was rounded DOWN.
+                    // movement since the last search (+ the float roundings of the stored and of the current position)
+                    const float pxf = (float)px, pyf = (float)py, pzf = (float)pz;
+                    const float mx = pxf - kr.x, my = pyf - kr.y, mz = pzf - kr.z;
+                    const float moved = sqrtf(fmaf(mz, mz, fmaf(my, my, mx * mx))) * 1.000001f + 4.0e-7f * (fabsf(pxf) + fabsf(pyf) + fabsf(pzf));
+                    const float lim = kr.w;  // every other target point was at least this far from the stored position (0: unknown)
+                    if (kp >= 0) {
+                        q = ld_point(A.grid.pts + kp);
+                        if (KIND == B3D_ICP_POINT_TO_PLANE) prefetch_l1(A.tgt_nrm_sorted + 3 * (int64_t)kp);  // most lanes keep this partner
+                        const double dk = dist2<double>(px - q.x, py - q.y, pz - q.z);
+                        const float u = sqrtf((float)dk) * 1.000001f;
+                        if ((u + moved) * 1.000001f < lim) {  // still strictly nearer than anything else can be
+                            need = false;
+                            pos = kp;
+                            d2 = dk;
+                            idx = point_index(q);
+                        } else {
+                            const float slack = fminf(fmaxf(0.5f * moved, 0.01f * dmax_up), 0.1f * dmax_up);
+                            reach = fminf(u + slack, dmax_up);  // nothing beyond d_max counts anyway
+                        }
+                    } else if (lim > 0.0f) {
+                        if ((dmax_up + moved) * 1.000001f < lim) need = false;  // nothing was within lim, nothing can be within d_max now
+                        else if (moved < 0.5f * ((float)kIcpReach2 - 1.0f) * dmax_up) reach = dmax_up * (float)kIcpReach2;
+                    }
+                }
+                const unsigned int need_mask = __ballot_sync(0xffffffffu, need);
 #ifdef B3D_ICP2_STATS
-        if (A.stats && lane == 0) {
-            if (need_mask == 0u) atomicAdd(&g_icp_stats[6], 1ull);
-            atomicAdd(&g_icp_stats[7], (unsigned long long)__popc(need_mask));
-        }
+                if (A.stats && lane == 0) {
+                    if (need_mask == 0u) atomicAdd(&g_icp_stats[6], 1ull);
+                    atomicAdd(&g_icp_stats[7], (unsigned long long)__popc(need_mask));
+                }
 #endif
-        if (nsi >= 0) {
-            prefetch_l1(A.src_sorted + nsi);
-            if (A.keep_ref != nullptr) prefetch_l1(A.keep_ref + nsi);
-        }
-        if (need_mask != 0u) {
-            // the chunk's box in fixed-point units of the target grid: every searching lane's ball, one unit of margin for the
-            // floor() of the records and one for the roundings here
-            const double ux = unit_coord_of_query(px, F.ox, F.per_m), uy = unit_coord_of_query(py, F.oy, F.per_m), uz = unit_coord_of_query(pz, F.oz, F.per_m);
-            const double ru = (double)reach * F.per_m + 2.0;
-            int lox = need ? unit_floor_clamped(ux - ru) : 0x7fffffff, loy = need ? unit_floor_clamped(uy - ru) : 0x7fffffff,
-                loz = need ? unit_floor_clamped(uz - ru) : 0x7fffffff;
-            int hix = need ? unit_ceil_clamped(ux + ru) : (int)0x80000000, hiy = need ? unit_ceil_clamped(uy + ru) : (int)0x80000000,
-                hiz = need ? unit_ceil_clamped(uz + ru) : (int)0x80000000;
-            lox = __reduce_min_sync(0xffffffffu, lox); loy = __reduce_min_sync(0xffffffffu, loy); loz = __reduce_min_sync(0xffffffffu, loz);
-            hix = __reduce_max_sync(0xffffffffu, hix); hiy = __reduce_max_sync(0xffffffffu, hiy); hiz = __reduce_max_sync(0xffffffffu, hiz);
-            // how far this lane's query is from the faces of the (unclamped) box: every target point that is NOT staged lies
-            // outside the box, i.e. at least this far away -- usually well beyond the lane's own reach (metres, rounded down)
-            const float d_out = (float)(fmin(fmin(fmin(ux - (double)lox, (double)hix - ux), fmin(uy - (double)loy, (double)hiy - uy)),
-                                             fmin(uz - (double)loz, (double)hiz - uz)) - 2.0) * inv_pm * 0.999999f;
-            lox = max(lox, 0); loy = max(loy, 0); loz = max(loz, 0);
-            // this lane's query as an offset from the box centre (the centre stage2_run uses)
-            const int ccx = (int)(((long long)lox + hix) >> 1), ccy = (int)(((long long)loy + hiy) >> 1), ccz = (int)(((long long)loz + hiz) >> 1);
-            const double qdx = ux - (double)ccx, qdy = uy - (double)ccy, qdz = uz - (double)ccz;
-            const float qfx = (float)qdx, qfy = (float)qdy, qfz = (float)qdz;
-            const float fx = -2.0f * qfx, fy = -2.0f * qfy, fz = -2.0f * qfz;
-            // largest offset component of a candidate or of this query
-            const float H = fmaxf(fmaxf(fmaxf((float)(hix - ccx), (float)(hiy - ccy)), (float)(hiz - ccz)) + 1.0f, fmaxf(fmaxf(fabsf(qfx), fabsf(qfy)), fabsf(qfz)));
-            const float band_w = stage2_band(H);
-            float best = 3.0e38f, second = 3.0e38f;
-            int wpos = -1;      // sorted position of the float winner
-            int last_kept = 0;  // candidates of the last batch (still in shared memory after the call)
-            const float2 f2x = make_float2(fx, fx), f2y = make_float2(fy, fy), f2z = make_float2(fz, fz);
-            auto scan = [&](int kept) {
-                last_kept = kept;
-                if (!need) return;
-                float b = best, s2 = second;
-                int grp = -1;
-                // eight candidates (two quads of one slot group) per step along a running pointer: the group layout costs one
-                // conditional bump per step, no address arithmetic per quad; the padding covers the ragged tail
-                const float4* qp = S.buf;
-                for (int gi = 0; gi < kept; gi += 8) {
+                if (need_mask != 0u) {
+                    // the chunk's box in fixed-point units of the target grid: every searching lane's ball, one unit of margin for the
+                    // floor() of the records and one for the roundings here
+                    const double ux = unit_coord_of_query(px, F.ox, F.per_m), uy = unit_coord_of_query(py, F.oy, F.per_m), uz = unit_coord_of_query(pz, F.oz, F.per_m);
+                    const double ru = (double)reach * F.per_m + 2.0;
+                    int lox = need ? unit_floor_clamped(ux - ru) : 0x7fffffff, loy = need ? unit_floor_clamped(uy - ru) : 0x7fffffff,
+                        loz = need ? unit_floor_clamped(uz - ru) : 0x7fffffff;
+                    int hix = need ? unit_ceil_clamped(ux + ru) : (int)0x80000000, hiy = need ? unit_ceil_clamped(uy + ru) : (int)0x80000000,
+                        hiz = need ? unit_ceil_clamped(uz + ru) : (int)0x80000000;
+                    lox = __reduce_min_sync(0xffffffffu, lox); loy = __reduce_min_sync(0xffffffffu, loy); loz = __reduce_min_sync(0xffffffffu, loz);
+                    hix = __reduce_max_sync(0xffffffffu, hix); hiy = __reduce_max_sync(0xffffffffu, hiy); hiz = __reduce_max_sync(0xffffffffu, hiz);
+                    // how far this lane's query is from the faces of the (unclamped) box: every target point that is NOT staged lies
+                    // outside the box, i.e. at least this far away -- usually well beyond the lane's own reach (metres, rounded down)
+                    const float d_out = (float)(fmin(fmin(fmin(ux - (double)lox, (double)hix - ux), fmin(uy - (double)loy, (double)hiy - uy)),
+                                                     fmin(uz - (double)loz, (double)hiz - uz)) - 2.0) * inv_pm * 0.999999f;
+                    lox = max(lox, 0); loy = max(loy, 0); loz = max(loz, 0);
+                    // this lane's query as an offset from the box centre (the centre stage2_run uses)
+                    const int ccx = (int)(((long long)lox + hix) >> 1), ccy = (int)(((long long)loy + hiy) >> 1), ccz = (int)(((long long)loz + hiz) >> 1);
+                    const double qdx = ux - (double)ccx, qdy = uy - (double)ccy, qdz = uz - (double)ccz;
+                    const float qfx = (float)qdx, qfy = (float)qdy, qfz = (float)qdz;
+                    const float fx = -2.0f * qfx, fy = -2.0f * qfy, fz = -2.0f * qfz;
+                    // largest offset component of a candidate or of this query
+                    const float H = fmaxf(fmaxf(fmaxf((float)(hix - ccx), (float)(hiy - ccy)), (float)(hiz - ccz)) + 1.0f, fmaxf(fmaxf(fabsf(qfx), fabsf(qfy)), fabsf(qfz)));
+                    const float band_w = stage2_band(H);
+                    float best = 3.0e38f, second = 3.0e38f;
+                    int wpos = -1;      // sorted position of the float winner
+                    int last_kept = 0;  // candidates of the last batch (still in shared memory after the call)
+                    const float2 f2x = make_float2(fx, fx), f2y = make_float2(fy, fy), f2z = make_float2(fz, fz);
+                    auto scan = [&](int kept) {
+                        last_kept = kept;
+                        if (!need) return;
+                        float b = best, s2 = second;
+                        int grp = -1;
+                        // eight candidates (two quads of one slot group) per step along a running pointer: the group layout costs one
+                        // conditional bump per step, no address arithmetic per quad; the padding covers the ragged tail
+                        const float4* qp = S.buf;
+#pragma unroll 1
+                        for (int gi = 0; gi < kept; gi += 8) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const float4 t = quad_t_at(qp + h, f2x, f2y, f2z);
-                        const float m01 = fminf(t.x, t.y), M01 = fmaxf(t.x, t.y), m23 = fminf(t.z, t.w), M23 = fmaxf(t.z, t.w);
-                        const float m = fminf(m01, m23), Mm = fmaxf(m01, m23);
-                        const float sg = fminf(fminf(M01, M23), Mm);  // second smallest of the four
-                        s2 = fminf(s2, fminf(sg, fmaxf(m, b)));
-                        grp = m < b ? gi + 4 * h : grp;
-                        b = fminf(b, m);
-                    }
-                    qp += (gi & 24) == 24 ? 26 : 2;  // next pair of quads; past the group's fourth pair, the next group
-                }
-                if (grp >= 0) {
-                    // the new best sits in group grp: the first of the four that reproduces it (ties end up in the float64 path)
-                    const float4 t = quad_t(S.buf, grp, f2x, f2y, f2z);
-                    int w = grp + 3;
-                    if (t.z == b) w = grp + 2;
-                    if (t.y == b) w = grp + 1;
-                    if (t.x == b) w = grp;
-                    wpos = S.pos[w];
-                }
-                best = b;
-                second = s2;
-            };
-            const int nb = stage2_run<kIcp2Cap>(A.grid, F, pair, lox, loy, loz, hix, hiy, hiz, S, parity, scan);
+                            for (int h = 0; h < 2; ++h) {
+                                const float4 t = quad_t_at(qp + h, f2x, f2y, f2z);
+                                const float m01 = fminf(t.x, t.y), M01 = fmaxf(t.x, t.y), m23 = fminf(t.z, t.w), M23 = fmaxf(t.z, t.w);
+                                const float m = fminf(m01, m23), Mm = fmaxf(m01, m23);
+                                const float sg = fminf(fminf(M01, M23), Mm);  // second smallest of the four
+                                s2 = fminf(s2, fminf(sg, fmaxf(m, b)));
+                                grp = m < b ? gi + 4 * h : grp;
+                                b = fminf(b, m);
+                            }
+                            qp += (gi & 24) == 24 ? 26 : 2;  // next pair of quads; past the group's fourth pair, the next group
+                        }
+                        if (grp >= 0) {
+                            // the new best sits in group grp: the first of the four that reproduces it (ties end up in the float64 path)
+                            const float4 t = quad_t(S.buf, grp, f2x, f2y, f2z);
+                            int w = grp + 3;
+                            if (t.z == b) w = grp + 2;
+                            if (t.y == b) w = grp + 1;
+                            if (t.x == b) w = grp;
+                            wpos = S.pos[w];
+                        }
+                        best = b;
+                        second = s2;
+                    };
+                    const int nb = stage2_run<kIcp2Cap>(A.grid, F, pair, lox, loy, loz, hix, hiy, hiz, S, parity, scan);
 #ifdef B3D_ICP2_STATS
-            if (A.stats && lane == 0) {
-                atomicAdd(&g_icp_stats[0], 1ull);
-                if (nb < 0) atomicAdd(&g_icp_stats[2], 1ull);
-                else atomicAdd(&g_icp_stats[3], (unsigned long long)last_kept);
-                if (nb > 1) atomicAdd(&g_icp_stats[1], 1ull);
-            }
-#endif
-            double others2 = 3.0e38;  // lower bound of the squared distance (metres) of every target point but the winner
-            bool bounded = nb >= 0;   // every target point within `reach` of the query was looked at
-            if (need) {
-                const bool ambiguous = nb >= 0 && wpos >= 0 && second <= best + band_w;
-                if (nb < 0 || (ambiguous && nb > 1)) {
-                    // box too large to stage, or a near-tie in a box that took several batches (the earlier candidates are gone)
-                    pos = icp2_walk(A.grid, pair, px, py, pz, A.r2, A.rmax);
-                    if (nb >= 0) bounded = false;
-                } else {
-                    pos = wpos;
-                }
-                if (pos >= 0) {
-                    q = ld_point(A.grid.pts + pos);
-                    if (KIND == B3D_ICP_POINT_TO_PLANE) {  // the normal's latency runs in parallel with the point's
-                        const double* nq = A.tgt_nrm_sorted + 3 * (int64_t)pos;
-                        nr0 = __ldg(nq); nr1 = __ldg(nq + 1); nr2 = __ldg(nq + 2);
-                        have_nrm = true;
+                    if (A.stats && lane == 0) {
+                        atomicAdd(&g_icp_stats[0], 1ull);
+                        if (nb < 0) atomicAdd(&g_icp_stats[2], 1ull);
+                        else atomicAdd(&g_icp_stats[3], (unsigned long long)last_kept);
+                        if (nb > 1) atomicAdd(&g_icp_stats[1], 1ull);
                     }
-                    d2 = dist2<double>(px - q.x, py - q.y, pz - q.z);
-                    idx = point_index(q);
-                }
-                if (nb >= 0 && wpos >= 0 && !(ambiguous && nb > 1)) {
-                    if (ambiguous) {
-                        const int tpos = icp2_resolve_ties(A.grid.pts, S.buf, S.pos, last_kept, fx, fy, fz, best + band_w, px, py, pz, wpos, d2, idx);
-                        if (tpos != pos) {
-                            have_nrm = false;
-                            pos = tpos;
+#endif
+                    double others2 = 3.0e38;  // lower bound of the squared distance (metres) of every target point but the winner
+                    bool bounded = nb >= 0;   // every target point within `reach` of the query was looked at
+                    if (need) {
+                        const bool ambiguous = nb >= 0 && wpos >= 0 && second <= best + band_w;
+                        if (nb < 0 || (ambiguous && nb > 1)) {
+                            // box too large to stage, or a near-tie in a box that took several batches (the earlier candidates are gone)
+                            pos = icp2_walk(A.grid, pair, px, py, pz, A.r2, A.rmax);
+                            if (nb >= 0) bounded = false;
+                        } else {
+                            pos = wpos;
+                        }
+                        if (pos >= 0) {
                             q = ld_point(A.grid.pts + pos);
+                            if (KIND == B3D_ICP_POINT_TO_PLANE) {  // the normal's latency runs in parallel with the point's
+                                const double* nq = A.tgt_nrm_sorted + 3 * (int64_t)pos;
+                                nr0 = __ldg(nq); nr1 = __ldg(nq + 1); nr2 = __ldg(nq + 2);
+                                have_nrm = true;
+                            }
                             d2 = dist2<double>(px - q.x, py - q.y, pz - q.z);
                             idx = point_index(q);
                         }
-                        others2 = d2;
+                        if (nb >= 0 && wpos >= 0 && !(ambiguous && nb > 1)) {
+                            if (ambiguous) {
+                                const int tpos = icp2_resolve_ties(A.grid.pts, S.buf, S.pos, last_kept, fx, fy, fz, best + band_w, px, py, pz, wpos, d2, idx);
+                                if (tpos != pos) {
+                                    have_nrm = false;
+                                    pos = tpos;
+                                    q = ld_point(A.grid.pts + pos);
+                                    d2 = dist2<double>(px - q.x, py - q.y, pz - q.z);
+                                    idx = point_index(q);
+                                }
+                                others2 = d2;
+                            } else {
+                                others2 = fmax(d2, ((qdx * qdx + qdy * qdy + qdz * qdz) + (double)second - (double)band_w) * inv_pm2);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (need && A.keep_ref != nullptr) {
+                        // what this search proved: the nearest point (if any within reach) and that every other point is at least
+                        // min(runner-up, reach) away; stored rounded down
+                        float lbf = 0.f;
+                        if (bounded) lbf = fminf(sqrtf((float)fmin(others2, 1.0e30)) * 0.999999f, fmaxf(d_out, reach * 0.999999f));
+                        A.keep_ref[si] = make_float4((float)px, (float)py, (float)pz, lbf);
+                        A.keep_pos[si] = pos;
+                    }
+                }
+                if (pos >= 0 && !(d2 < A.r2)) pos = -1;
+                double e[kIcpRow];
+#pragma unroll
+                for (int j = 0; j < kIcpRow; ++j) e[j] = 0.0;
+                double W[9], gd[3], gp[3];  // generalized ICP / information matrix only
+                bool matched = false;
+                if (valid) {
+                    if (A.corr != nullptr) A.corr[oi] = pos >= 0 ? idx - t0 : -1;
+                    if (pos >= 0) {
+                        matched = true;
+                        e[7] = 1.0;
+                        e[8] = d2;
+                        if (KIND == kIcpInformation) {
+                            gp[0] = q.x; gp[1] = q.y; gp[2] = q.z;
+                        } else if (KIND == B3D_ICP_POINT_TO_POINT) {
+                            e[0] = px; e[1] = py; e[2] = pz;
+                            e[3] = q.x; e[4] = q.y; e[5] = q.z;
+                        } else if (KIND == B3D_ICP_POINT_TO_PLANE) {
+                            if (!have_nrm) {
+                                const double* nq = A.tgt_nrm_sorted + 3 * (int64_t)pos;
+                                nr0 = __ldg(nq); nr1 = __ldg(nq + 1); nr2 = __ldg(nq + 2);
+                            }
+                            const double n0 = nr0, n1 = nr1, n2 = nr2;
+                            e[0] = py * n2 - pz * n1; e[1] = pz * n0 - px * n2; e[2] = px * n1 - py * n0;
+                            e[3] = n0; e[4] = n1; e[5] = n2;
+                            e[6] = (px - q.x) * n0 + (py - q.y) * n1 + (pz - q.z) * n2;
+                        } else {
+                            // generalized ICP: M = C_t + R C_s R^T, W = (M^-1)^(1/2), rows r_k = W_k (p - q), J = W [ -[p]x | I ]
+                            const double* Ct = A.tgt_cov_sorted + 9 * (int64_t)pos;
+                            const double* Cs = A.src_cov + 9 * (int64_t)oi;
+                            double RC[9], M[9];
+#pragma unroll
+                            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                                for (int cc = 0; cc < 3; ++cc) RC[3 * r + cc] = sT[4 * r] * Cs[cc] + sT[4 * r + 1] * Cs[3 + cc] + sT[4 * r + 2] * Cs[6 + cc];
+#pragma unroll
+                            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                                for (int cc = 0; cc < 3; ++cc)
+                                    M[3 * r + cc] = __ldg(Ct + 3 * r + cc) + (RC[3 * r] * sT[4 * cc] + RC[3 * r + 1] * sT[4 * cc + 1] + RC[3 * r + 2] * sT[4 * cc + 2]);
+                            inv_sqrt_sym3(M, W);
+                            gd[0] = px - q.x; gd[1] = py - q.y; gd[2] = pz - q.z;
+                            gp[0] = px; gp[1] = py; gp[2] = pz;
+                        }
+                    }
+                }
+                const int n_rows = (KIND == B3D_ICP_GENERALIZED || KIND == kIcpInformation) ? 3 : 1;
+                for (int row = 0; row < n_rows; ++row) {
+                    if (KIND == kIcpInformation) {
+                        if (matched) {
+                            // G = [ -[t]x | I ] for the target point t (kept in gp)
+                            e[0] = row == 0 ? 0.0 : (row == 1 ? -gp[2] : gp[1]);
+                            e[1] = row == 0 ? gp[2] : (row == 1 ? 0.0 : -gp[0]);
+                            e[2] = row == 0 ? -gp[1] : (row == 1 ? gp[0] : 0.0);
+                            e[3] = row == 0 ? 1.0 : 0.0; e[4] = row == 1 ? 1.0 : 0.0; e[5] = row == 2 ? 1.0 : 0.0;
+                            e[6] = 0.0;
+                            if (row > 0) { e[7] = 0.0; e[8] = 0.0; }
+                        }
+                    }
+                    if (KIND == B3D_ICP_GENERALIZED) {
+                        if (matched) {
+                            const double w0 = W[3 * row], w1 = W[3 * row + 1], w2 = W[3 * row + 2];
+                            // J = W_row [ -[p]x | I ],  -[p]x = [0 pz -py; -pz 0 px; py -px 0]
+                            e[0] = w1 * (-gp[2]) + w2 * gp[1];
+                            e[1] = w0 * gp[2] + w2 * (-gp[0]);
+                            e[2] = w0 * (-gp[1]) + w1 * gp[0];
+                            e[3] = w0; e[4] = w1; e[5] = w2;
+                            e[6] = w0 * gd[0] + w1 * gd[1] + w2 * gd[2];
+                            if (row > 0) { e[7] = 0.0; e[8] = 0.0; }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < kIcpRow; ++j) rows_t[j * kIcpRowStride + lane] = e[j];
+                    __syncwarp();
+                    if ((KIND == B3D_ICP_GENERALIZED || KIND == kIcpInformation) && row > 0 && lane >= 27) {
+                        // count and sum d2 are taken once per correspondence (row 0)
                     } else {
-                        others2 = fmax(d2, ((qdx * qdx + qdy * qdy + qdz * qdz) + (double)second - (double)band_w) * inv_pm2);
-                    }
-                }
-            }
-            __syncwarp();
-            if (need && A.keep_ref != nullptr) {
-                // what this search proved: the nearest point (if any within reach) and that every other point is at least
-                // min(runner-up, reach) away; stored rounded down
-                float lbf = 0.f;
-                if (bounded) lbf = fminf(sqrtf((float)fmin(others2, 1.0e30)) * 0.999999f, fmaxf(d_out, reach * 0.999999f));
-                A.keep_ref[si] = make_float4((float)px, (float)py, (float)pz, lbf);
-                A.keep_pos[si] = pos;
-            }
-        }
-        if (nkp >= 0) {
-            prefetch_l1(A.grid.pts + nkp);
-            if (KIND == B3D_ICP_POINT_TO_PLANE) prefetch_l1(A.tgt_nrm_sorted + 3 * (int64_t)nkp);
-        }
-        if (pos >= 0 && !(d2 < A.r2)) pos = -1;
-        double e[kIcpRow];
-#pragma unroll
-        for (int j = 0; j < kIcpRow; ++j) e[j] = 0.0;
-        double W[9], gd[3], gp[3];  // generalized ICP / information matrix only
-        bool matched = false;
-        if (valid) {
-            if (A.corr != nullptr) A.corr[oi] = pos >= 0 ? idx - t0 : -1;
-            if (pos >= 0) {
-                matched = true;
-                e[7] = 1.0;
-                e[8] = d2;
-                if (KIND == kIcpInformation) {
-                    gp[0] = q.x; gp[1] = q.y; gp[2] = q.z;
-                } else if (KIND == B3D_ICP_POINT_TO_POINT) {
-                    e[0] = px; e[1] = py; e[2] = pz;
-                    e[3] = q.x; e[4] = q.y; e[5] = q.z;
-                } else if (KIND == B3D_ICP_POINT_TO_PLANE) {
-                    if (!have_nrm) {
-                        const double* nq = A.tgt_nrm_sorted + 3 * (int64_t)pos;
-                        nr0 = __ldg(nq); nr1 = __ldg(nq + 1); nr2 = __ldg(nq + 2);
-                    }
-                    const double n0 = nr0, n1 = nr1, n2 = nr2;
-                    e[0] = py * n2 - pz * n1; e[1] = pz * n0 - px * n2; e[2] = px * n1 - py * n0;
-                    e[3] = n0; e[4] = n1; e[5] = n2;
-                    e[6] = (px - q.x) * n0 + (py - q.y) * n1 + (pz - q.z) * n2;
-                } else {
-                    // generalized ICP: M = C_t + R C_s R^T, W = (M^-1)^(1/2), rows r_k = W_k (p - q), J = W [ -[p]x | I ]
-                    const double* Ct = A.tgt_cov_sorted + 9 * (int64_t)pos;
-                    const double* Cs = A.src_cov + 9 * (int64_t)oi;
-                    double RC[9], M[9];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
-#pragma unroll
-                        for (int cc = 0; cc < 3; ++cc) RC[3 * r + cc] = sT[4 * r] * Cs[cc] + sT[4 * r + 1] * Cs[3 + cc] + sT[4 * r + 2] * Cs[6 + cc];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
-#pragma unroll
-                        for (int cc = 0; cc < 3; ++cc)
-                            M[3 * r + cc] = __ldg(Ct + 3 * r + cc) + (RC[3 * r] * sT[4 * cc] + RC[3 * r + 1] * sT[4 * cc + 1] + RC[3 * r + 2] * sT[4 * cc + 2]);
-                    inv_sqrt_sym3(M, W);
-                    gd[0] = px - q.x; gd[1] = py - q.y; gd[2] = pz - q.z;
-                    gp[0] = px; gp[1] = py; gp[2] = pz;
-                }
-            }
-        }
-        const int n_rows = (KIND == B3D_ICP_GENERALIZED || KIND == kIcpInformation) ? 3 : 1;
-        for (int row = 0; row < n_rows; ++row) {
-            if (KIND == kIcpInformation) {
-                if (matched) {
-                    // G = [ -[t]x | I ] for the target point t (kept in gp)
-                    e[0] = row == 0 ? 0.0 : (row == 1 ? -gp[2] : gp[1]);
-                    e[1] = row == 0 ? gp[2] : (row == 1 ? 0.0 : -gp[0]);
-                    e[2] = row == 0 ? -gp[1] : (row == 1 ? gp[0] : 0.0);
-                    e[3] = row == 0 ? 1.0 : 0.0; e[4] = row == 1 ? 1.0 : 0.0; e[5] = row == 2 ? 1.0 : 0.0;
-                    e[6] = 0.0;
-                    if (row > 0) { e[7] = 0.0; e[8] = 0.0; }
-                }
-            }
-            if (KIND == B3D_ICP_GENERALIZED) {
-                if (matched) {
-                    const double w0 = W[3 * row], w1 = W[3 * row + 1], w2 = W[3 * row + 2];
-                    // J = W_row [ -[p]x | I ],  -[p]x = [0 pz -py; -pz 0 px; py -px 0]
-                    e[0] = w1 * (-gp[2]) + w2 * gp[1];
-                    e[1] = w0 * gp[2] + w2 * (-gp[0]);
-                    e[2] = w0 * (-gp[1]) + w1 * gp[0];
-                    e[3] = w0; e[4] = w1; e[5] = w2;
-                    e[6] = w0 * gd[0] + w1 * gd[1] + w2 * gd[2];
-                    if (row > 0) { e[7] = 0.0; e[8] = 0.0; }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < kIcpRow; ++j) rows_t[j * kIcpRowStride + lane] = e[j];
-            __syncwarp();
-            if ((KIND == B3D_ICP_GENERALIZED || KIND == kIcpInformation) && row > 0 && lane >= 27) {
-                // count and sum d2 are taken once per correspondence (row 0)
-            } else {
-                // fused multiply-add on purpose (the file is built with -fmad=false): the order of these sums is this kernel's own (lane
-                // order inside a chunk, chunk order inside a warp), nothing compares them bit for bit with the CPU
+                        // fused multiply-add on purpose (the file is built with -fmad=false): the order of these sums is this kernel's own (lane
+                        // order inside a chunk, chunk order inside a warp), nothing compares them bit for bit with the CPU
 #pragma unroll 8
-                for (int l2 = 0; l2 < 16; ++l2) {
-                    const double2 a = row_p[l2], b = row_q[l2];
-                    acc = fma(a.x, b.x, acc);
-                    acc = fma(a.y, b.y, acc);
+                        for (int l2 = 0; l2 < 16; ++l2) {
+                            const double2 a = row_p[l2], b = row_q[l2];
+                            acc = fma(a.x, b.x, acc);
+                            acc = fma(a.y, b.y, acc);
+                        }
+                    }
+                    __syncwarp();
                 }
             }
-            __syncwarp();
+            // the leaf of this strand (this warp's chain over its chunks of the group, 0 if it has none) joins the run's node: a binary
+            // counter -- leaf i is added to the waiting node of every level whose bit is set in i, and parks at the first clear one
+            {
+                double v = acc;
+                acc = 0.0;
+                int level = 0;
+                for (int t = m; t & 1; t >>= 1, ++level) v = stk[level][warp][lane] + v;
+                stk[level][warp][lane] = v;
+                ++m;
+            }
+        }
+        // the run's node (a ragged last run: the waiting nodes from the lowest level up, the higher one on the left) -> global memory
+        {
+            double v = 0.0;
+            bool have = false;
+            for (int level = 0; (m >> level) != 0; ++level)
+                if ((m >> level) & 1) {
+                    v = have ? stk[level][warp][lane] + v : stk[level][warp][lane];
+                    have = true;
+                }
+            if (lane < kIcpSums) A.partial[(((int64_t)pair * A.run_stride + r) * 4 + warp) * kIcpSums + lane] = v;
         }
     }
-    // ---- the warp's 29 sums -> the block's row (the last warp of the block to arrive adds the four rows in warp order) ----
-    sm[warp][lane] = acc;
-    __threadfence_block();
-    __syncwarp();  // every lane's row entry is out before lane 0 announces the warp
-    unsigned int arrived = 0;
-    if (lane == 0) arrived = atomicAdd(&s_arrived, 1u);
-    arrived = __shfl_sync(0xffffffffu, arrived, 0);
-    if (arrived != (unsigned int)(kIcpBlock / 32 - 1)) return;
-    __threadfence_block();
+    // ---- end of the block: the LAST block of a pair adds the pair's nodes, one strand per warp, then warp 0 finishes the pass ----
+    __threadfence();  // this thread's partials are out (device scope) before the block's ticket is drawn
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&st->ticket, 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned int)n_active - 1u) return;  // uniform over the block
+    __threadfence();
     {
-        double v = sm[0][lane];
-#pragma unroll
-        for (int w = 1; w < kIcpBlock / 32; ++w) v += sm[w][lane];
-        if (lane < kIcpSums) A.partial[((int64_t)pair * gridDim.x + blockIdx.x) * kIcpSums + lane] = v;
+        const double t = icp2_reduce_strand(A, pair, n_runs, warp);
+        s_tot[warp][lane] = t;
     }
-    __threadfence();
-    __syncwarp();
-    unsigned int ticket = 0;
-    if (lane == 0) ticket = atomicAdd(&st->ticket, 1u);
-    ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    if (ticket != (unsigned int)groups - 1u) return;
-    __threadfence();
-    icp2_finish_pair(A, pair, groups, s1 - s0);
+    __syncthreads();
+    if (warp != 0) return;
+    const double total = ((s_tot[0][lane] + s_tot[1][lane]) + s_tot[2][lane]) + s_tot[3][lane];
+    icp2_finish_pair(A, pair, total, s1 - s0);
 }
 
 __global__ void icp_finalize_kernel(int kind, const double* __restrict__ sums, const int32_t* __restrict__ src_off, const int64_t* __restrict__ ns_global,
@@ -1210,8 +1236,46 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
         }
     }
     // partial-sum groups per pair depend only on that pair's own chunk count (results do not depend on the batch)
+    // How the pass kernel is cut into blocks (results do not depend on it, see the kernel): runs of R adjacent chunk groups (16 chunks
+    // each), nb blocks per pair sharing the pair's runs. A block start and hand-over costs ~0.7 chunk-times per warp, consecutive
+    // groups overlap in space (L1), so longer runs are better -- as long as the machine stays full:
+    //  * many waves (a batch of pairs, a very large cloud): one run of 4 groups per block (16 chunks per warp; measured on the 64-pair
+    //    batch at 4 / 16 / 32 chunks per warp: 19.2 / 17.0 / 17.1 ms of ICP); R grows to 16 / 64 for clouds of 1e8 points (the pair's
+    //    last block adds the run nodes);
+    //  * about one wave or less (a single pair): R in {4, 2, 1} and nb <= the resident slots, chosen to minimise the number of
+    //    group-times of the busiest block (an 8 MP pair, 1218 groups on 592 slots: R = 1, three groups per block at most).
+    {
+        const int64_t slots = (int64_t)ctx->sm_count * B3D_ICP2_MIN_BLOCKS;
+        auto groups_of = [&](int p) { return std::max<int64_t>(1, ((int64_t)w->chunks.chunk_off_h[p + 1] - w->chunks.chunk_off_h[p] + 15) / 16); };
+        auto runs_tot = [&](int lg) {
+            int64_t t = 0;
+            for (int p = 0; p < P; ++p) t += (groups_of(p) + (1 << lg) - 1) >> lg;
+            return t;
+        };
+        int64_t most_groups = 1;
+        for (int p = 0; p < P; ++p) most_groups = std::max(most_groups, groups_of(p));
+        int lg = 2;
+        int64_t nb = 0;  // 0: one run per block
+        if (runs_tot(2) >= 4 * slots) {
+            while (lg < kIcpMaxRunLog2 && runs_tot(lg) > 64 * slots) lg += 2;
+        } else {
+            int64_t best = INT64_MAX;
+            for (int cand = 2; cand >= 0; --cand) {
+                const int64_t waves = (runs_tot(cand) + slots - 1) / slots;
+                const int64_t cost = waves << cand;  // group-times of the busiest block
+                if (cost < best) { best = cost; lg = cand; }
+            }
+            nb = std::max<int64_t>(1, slots / std::max(P, 1));  // the pairs of a small batch share the resident slots
+        }
+        if (const char* e = getenv("B3D_ICP_RUN_LOG2")) lg = std::min(std::max(atoi(e), 0), kIcpMaxRunLog2);
+        const int64_t most_runs = (most_groups + (1 << lg) - 1) >> lg;
+        w->run_log2 = lg;
+        w->run_stride = (int)most_runs;
+        w->blocks2 = (int)(nb > 0 ? std::min(nb, most_runs) : most_runs);
+        if (const char* e = getenv("B3D_ICP_BLOCKS_PER_PAIR")) w->blocks2 = (int)std::min<int64_t>(std::max(atoi(e), 1), most_runs);
+    }
     w->blocks = icp_groups(w->chunks.most);
-    B3D_TRY(w->partial.alloc(ctx, (size_t)P * w->blocks * kIcpSums));
+    B3D_TRY(w->partial.alloc(ctx, (size_t)P * std::max((size_t)w->blocks, (size_t)w->run_stride * 4) * kIcpSums));
     const int32_t nt = (int32_t)g.sort.n;
     if (pb.kind == B3D_ICP_POINT_TO_PLANE) {
         B3D_TRY(w->tgt_nrm_sorted.alloc(ctx, (size_t)nt * 3));
@@ -1249,6 +1313,8 @@ static IcpKernelArgs make_args(const IcpProblem& pb, IcpWork* w, int32_t* corr, 
     A.fused = fused ? 1 : 0;
     A.keep_ref = w->keep_ref.p;
     A.keep_pos = w->keep_pos.p;
+    A.run_log2 = w->run_log2;
+    A.run_stride = w->run_stride;
     {
         static const int stats_on = getenv("B3D_ICP_STATS") ? 1 : 0;
         A.stats = stats_on;
@@ -1274,10 +1340,11 @@ int icp_pass(b3d_ctx* ctx, const IcpProblem& pb, IcpWork* w, int32_t* corr, bool
     const dim3 grid(w->blocks, pb.P);
     static const bool v1 = getenv("B3D_ICP_V1") != nullptr;  // the round-1 kernel (kept for A/B runs and as the reference of the equality test)
     if (!v1 && A.grid.rec != nullptr) {
-        if (pb.kind == B3D_ICP_POINT_TO_POINT) return launch_pass2<B3D_ICP_POINT_TO_POINT>(ctx, A, grid);
-        if (pb.kind == kIcpInformation) return launch_pass2<kIcpInformation>(ctx, A, grid);
-        if (pb.kind == B3D_ICP_POINT_TO_PLANE) return launch_pass2<B3D_ICP_POINT_TO_PLANE>(ctx, A, grid);
-        return launch_pass2<B3D_ICP_GENERALIZED>(ctx, A, grid);
+        const dim3 grid2(w->blocks2, pb.P);
+        if (pb.kind == B3D_ICP_POINT_TO_POINT) return launch_pass2<B3D_ICP_POINT_TO_POINT>(ctx, A, grid2);
+        if (pb.kind == kIcpInformation) return launch_pass2<kIcpInformation>(ctx, A, grid2);
+        if (pb.kind == B3D_ICP_POINT_TO_PLANE) return launch_pass2<B3D_ICP_POINT_TO_PLANE>(ctx, A, grid2);
+        return launch_pass2<B3D_ICP_GENERALIZED>(ctx, A, grid2);
     }
     if (pb.kind == B3D_ICP_POINT_TO_POINT) {
         B3D_LAUNCH(ctx, icp_pass_kernel<B3D_ICP_POINT_TO_POINT>, grid, kIcpBlock, 0, A);

@@ -46,7 +46,10 @@ struct IcpWork {
     DevBuf<int64_t> ns_global;
     DevBuf<float4> keep_ref;   // sticky correspondences of the pass kernel (per source point, sorted order)
     DevBuf<int32_t> keep_pos;
-    int blocks = 1;
+    int blocks = 1;            // round-1 kernel: partial-sum groups per pair
+    int blocks2 = 1;           // round-2 kernel: blocks per pair (grid.x)
+    int run_log2 = 0;          // round-2 kernel: a run = 2^run_log2 adjacent chunk groups
+    int run_stride = 1;        // round-2 kernel: run nodes reserved per pair and strand in `partial`
     int peer_world = 0, peer_rank = 0;  // exchange over peer memory (b3d_icp_set_peers)
     double* peer_buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
