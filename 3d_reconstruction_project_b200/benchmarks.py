@@ -231,7 +231,7 @@ def config1_leg(device=0, steps=10, peak_gbs=None, golden_dir=None):
                          "note": "18 k points: launch- and latency-bound, not a bandwidth case"}}
 
 
-def micro_voxel_leg(device=0, steps=5, n=10_000_000, voxel=0.05, peak_gbs=None):
+def micro_voxel_leg(device=0, steps=20, n=10_000_000, voxel=0.05, peak_gbs=None):
     """The reference's own micro-benchmark shape (test/gpu-performance.py:13-26): 10 M uniform [0,1)^3 float32 points, tensor
     voxel_down_sample(0.05)."""
     ctx = get_context(device)

@@ -56,53 +56,97 @@ constexpr int kIcpMaxRunLog2 = 6;  // runs of up to 64 chunk groups (1024 chunks
 constexpr double kIcpReach2 = 1.25;   // search radius of a lane that found nothing last time, in units of d_max (see the pass kernel)
 
 // ---- small dense helpers (device) ----------------------------------------------------------------------------------
-// (M^-1)^(1/2) of a symmetric positive-definite 3x3 (GICP weight, one per correspondence per pass) by the coupled Newton-Schulz
-// iteration  T = (3 I - Z Y) / 2,  Y <- Y T,  Z <- T Z  from  Y = M / trace(M), Z = I  (Y -> (M/s)^(1/2), Z -> (M/s)^(-1/2)):
-// three 3x3 products per step in a loop of ~120 instructions, 14-20 steps for the covariances GICP builds (eigenvalues 1e-3 .. 2),
-// relative error ~1e-14 against scipy's sqrtm(inv(M)). The closed-form eigen-decomposition used before (and the Jacobi sweeps of the
-// CPU oracle) is as accurate, but it is ~2 500 straight-line float64 instructions (divisions, square roots, acos, cos): with it in
-// the pass kernel a third of the warps' time went to instruction fetch (profiles/r02e_c3_gicp_stalls.txt). FULL products on
-// purpose: the iteration is only stable with the exact product structure (an upper-triangle shortcut diverges).
+// (M^-1)^(1/2) of a symmetric positive-definite 3x3 (GICP weight, one per correspondence per pass) WITHOUT eigenvectors. With
+// U = M^(1/2) and its invariants I = s1 + s2 + s3, II = s1 s2 + s2 s3 + s1 s3, III = s1 s2 s3 (s_i = sqrt of M's eigenvalues, from
+// the closed-form trigonometric solver), Cayley-Hamilton for U gives U (M + II) = I M + III, i.e.
+//     M^(-1/2) = (I M + III)^(-1) (M + II)
+// -- one well-conditioned 3x3 inverse (adjugate) and one product; the invariants are symmetric functions of the eigenvalues, so
+// nearly equal eigenvalues (parallel normals, the usual case) cost no accuracy. ~650 instructions, relative error ~1e-13 against
+// scipy's sqrtm(inv(M)) for the covariances GICP builds (eigenvalues 1e-3 .. 2). Matrices with a spectrum wider than 1e7 take the
+// coupled Newton-Schulz iteration  T = (3 I - Z Y) / 2,  Y <- Y T,  Z <- T Z  (Y = M / trace, Z = I; Z -> (M / trace)^(-1/2)):
+// three FULL 3x3 products per step (the iteration is only stable with the exact product structure), 15-35 steps, error ~1e-13 at
+// any conditioning. The eigen-DECOMPOSITION used before (and the Jacobi sweeps of the CPU oracle) is as accurate but ~2 500
+// straight-line float64 instructions: with it in the pass kernel a third of the warps' time went to instruction fetch
+// (profiles/r02e_c3_gicp_stalls.txt). Out of line: one copy, outside the pass kernel's main body.
 __device__ __noinline__ void inv_sqrt_sym3(const double* M, double* W) {
-    const double s = M[0] + M[4] + M[8];  // >= the largest eigenvalue of a positive-definite M
-    if (!(s > 0.0) || !(s < 1.0e300)) {   // not positive definite / not finite: the diagonal rule of the closed form's fallback
+    const double tr = M[0] + M[4] + M[8];  // >= the largest eigenvalue of a positive-definite M
+    if (!(tr > 0.0) || !(tr < 1.0e300)) {  // not positive definite / not finite: the diagonal rule of the old closed form's fallback
 #pragma unroll
         for (int i = 0; i < 9; ++i) W[i] = 0.0;
         W[0] = 1.0 / sqrt(M[0]); W[4] = 1.0 / sqrt(M[4]); W[8] = 1.0 / sqrt(M[8]);
         return;
     }
-    const double inv_s = 1.0 / s;
-    double Y[9], Z[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-#pragma unroll
-    for (int i = 0; i < 9; ++i) Y[i] = M[i] * inv_s;
-#pragma unroll 1
-    for (int it = 0; it < 100; ++it) {
-        double T[9], P[9];
-        double err = 0.0;
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const double zy = fma(Z[3 * r], Y[c], fma(Z[3 * r + 1], Y[3 + c], Z[3 * r + 2] * Y[6 + c]));
-                const double t = (r == c ? 1.5 : 0.0) - 0.5 * zy;
-                T[3 * r + c] = t;
-                err = fmax(err, fabs(t - (r == c ? 1.0 : 0.0)));
-            }
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) P[3 * r + c] = fma(Y[3 * r], T[c], fma(Y[3 * r + 1], T[3 + c], Y[3 * r + 2] * T[6 + c]));
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Y[i] = P[i];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) P[3 * r + c] = fma(T[3 * r], Z[c], fma(T[3 * r + 1], Z[3 + c], T[3 * r + 2] * Z[6 + c]));
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Z[i] = P[i];
-        if (!(err >= 1.0e-14)) break;  // converged (quadratically: this step already took the error to ~1e-28), or NaN
+    // ---- eigenvalues of A = M / tr (closed form; a diagonal A is its own answer) ----
+    const double inv_tr = 1.0 / tr;
+    const double a00 = M[0] * inv_tr, a01 = M[1] * inv_tr, a02 = M[2] * inv_tr, a11 = M[4] * inv_tr, a12 = M[5] * inv_tr, a22 = M[8] * inv_tr;
+    double l0 = a00, l1 = a11, l2 = a22;
+    const double off = a01 * a01 + a02 * a02 + a12 * a12;
+    if (off > 0.0) {
+        const double q = (1.0 / 3.0);  // trace(A) / 3 with trace(A) = 1
+        const double b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
+        const double p2 = (b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * off) * (1.0 / 6.0);
+        const double p = sqrt(p2);
+        const double c00 = b11 * b22 - a12 * a12, c01 = a01 * b22 - a12 * a02, c02 = a01 * a12 - b11 * a02;
+        const double ip = 1.0 / p;
+        double half = (b00 * c00 - a01 * c01 + a02 * c02) * (ip * ip * ip) * 0.5;
+        half = half < -1.0 ? -1.0 : (half > 1.0 ? 1.0 : half);
+        double sa, ca;
+        sincos(acos(half) * (1.0 / 3.0), &sa, &ca);
+        const double beta2 = 2.0 * ca, beta0 = -ca - 1.7320508075688772 * sa;  // 2 cos(angle + 2 pi / 3)
+        l0 = q + p * beta0;
+        l2 = q + p * beta2;
+        l1 = 1.0 - l0 - l2;
     }
-    const double f = 1.0 / sqrt(s);
+    const double lmin = fmin(l0, fmin(l1, l2)), lmax = fmax(l0, fmax(l1, l2));
+    double Z[9];
+    if (lmin > 1.0e-7 * lmax) {
+        const double s0 = sqrt(l0), s1 = sqrt(l1), s2 = sqrt(l2);
+        const double I1 = s0 + s1 + s2, I2 = s0 * s1 + s1 * s2 + s0 * s2, I3 = s0 * s1 * s2;
+        // B = I1 A + I3, its adjugate, C = A + I2; Z = B^-1 C = A^(-1/2)
+        const double B00 = I1 * a00 + I3, B01 = I1 * a01, B02 = I1 * a02, B11 = I1 * a11 + I3, B12 = I1 * a12, B22 = I1 * a22 + I3;
+        const double k00 = B11 * B22 - B12 * B12, k01 = B02 * B12 - B01 * B22, k02 = B01 * B12 - B02 * B11;
+        const double k11 = B00 * B22 - B02 * B02, k12 = B01 * B02 - B00 * B12, k22 = B00 * B11 - B01 * B01;
+        const double idet = 1.0 / (B00 * k00 + B01 * k01 + B02 * k02);
+        const double C00 = a00 + I2, C11 = a11 + I2, C22 = a22 + I2;
+        Z[0] = (k00 * C00 + k01 * a01 + k02 * a02) * idet;
+        Z[1] = (k00 * a01 + k01 * C11 + k02 * a12) * idet;
+        Z[2] = (k00 * a02 + k01 * a12 + k02 * C22) * idet;
+        Z[4] = (k01 * a01 + k11 * C11 + k12 * a12) * idet;
+        Z[5] = (k01 * a02 + k11 * a12 + k12 * C22) * idet;
+        Z[8] = (k02 * a02 + k12 * a12 + k22 * C22) * idet;
+    } else {
+        double Y[9] = {a00, a01, a02, a01, a11, a12, a02, a12, a22};
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Z[i] = (i % 4 == 0) ? 1.0 : 0.0;
+#pragma unroll 1
+        for (int it = 0; it < 100; ++it) {
+            double T[9], P[9];
+            double err = 0.0;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const double zy = fma(Z[3 * r], Y[c], fma(Z[3 * r + 1], Y[3 + c], Z[3 * r + 2] * Y[6 + c]));
+                    const double t = (r == c ? 1.5 : 0.0) - 0.5 * zy;
+                    T[3 * r + c] = t;
+                    err = fmax(err, fabs(t - (r == c ? 1.0 : 0.0)));
+                }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) P[3 * r + c] = fma(Y[3 * r], T[c], fma(Y[3 * r + 1], T[3 + c], Y[3 * r + 2] * T[6 + c]));
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Y[i] = P[i];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) P[3 * r + c] = fma(T[3 * r], Z[c], fma(T[3 * r + 1], Z[3 + c], T[3 * r + 2] * Z[6 + c]));
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Z[i] = P[i];
+            if (!(err >= 1.0e-14)) break;  // converged (quadratically: this step already took the error to ~1e-28), or NaN
+        }
+    }
+    const double f = 1.0 / sqrt(tr);  // A = M / tr
     W[0] = Z[0] * f; W[1] = Z[1] * f; W[2] = Z[2] * f;
     W[4] = Z[4] * f; W[5] = Z[5] * f; W[8] = Z[8] * f;
     W[3] = W[1]; W[6] = W[2]; W[7] = W[5];
@@ -1240,8 +1284,7 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
     // each), nb blocks per pair sharing the pair's runs. A block start and hand-over costs ~0.7 chunk-times per warp, consecutive
     // groups overlap in space (L1), so longer runs are better -- as long as the machine stays full:
     //  * many waves (a batch of pairs, a very large cloud): one run of 4 groups per block (16 chunks per warp; measured on the 64-pair
-    //    batch at 4 / 16 / 32 chunks per warp: 19.2 / 17.0 / 17.1 ms of ICP); R grows to 16 / 64 for clouds of 1e8 points (the pair's
-    //    last block adds the run nodes);
+    //    batch at 4 / 16 / 32 chunks per warp: 19.2 / 17.0 / 17.1 ms of ICP), longer runs for one very large cloud;
     //  * about one wave or less (a single pair): R in {4, 2, 1} and nb <= the resident slots, chosen to minimise the number of
     //    group-times of the busiest block (an 8 MP pair, 1218 groups on 592 slots: R = 1, three groups per block at most).
     {
@@ -1252,12 +1295,19 @@ int icp_prepare(b3d_ctx* ctx, const IcpProblem& pb, const double* init_h, IcpWor
             for (int p = 0; p < P; ++p) t += (groups_of(p) + (1 << lg) - 1) >> lg;
             return t;
         };
-        int64_t most_groups = 1;
-        for (int p = 0; p < P; ++p) most_groups = std::max(most_groups, groups_of(p));
+        int64_t most_groups = 1, tot_groups = 0;
+        for (int p = 0; p < P; ++p) {
+            most_groups = std::max(most_groups, groups_of(p));
+            tot_groups += groups_of(p);
+        }
         int lg = 2;
         int64_t nb = 0;  // 0: one run per block
         if (runs_tot(2) >= 4 * slots) {
-            while (lg < kIcpMaxRunLog2 && runs_tot(lg) > 64 * slots) lg += 2;
+            // one cloud that dominates the batch (a sharded 1e7 .. 1e8-point cloud): every pass has all its blocks, so the runs
+            // grow while ~2.4 waves remain (1e7 points, ms per pass at runs of 4 / 8 / 16 / 32 groups: 1.63 / 1.45 / 1.36 / 1.35).
+            // A batch of pairs stays at 4: its late passes have few active pairs left (64 pairs at 4 / 8 / 16: 17.1 / 17.1 / 17.9)
+            if (2 * most_groups >= tot_groups)
+                while (lg < kIcpMaxRunLog2 && 10 * runs_tot(lg + 1) >= 24 * slots) ++lg;
         } else {
             int64_t best = INT64_MAX;
             for (int cand = 2; cand >= 0; --cand) {

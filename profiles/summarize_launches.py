@@ -12,9 +12,12 @@ def main(path):
             hdr, start = r, i + 1
             break
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    mi = hdr.index("Metric Name") if "Metric Name" in hdr else None
     agg = collections.OrderedDict()
     for r in rows[start:]:
         if len(r) <= vi:
+            continue
+        if mi is not None and r[mi] != "gpu__time_duration.sum":  # launch lists may carry further metrics per launch
             continue
         name = r[ki].replace("<unnamed>::", "").replace("unnamed>::", "").replace("b3d::", "").replace("void ", "").split("(")[0]
         if name.startswith("compact_kernel<"):
