@@ -241,12 +241,18 @@ __global__ void __launch_bounds__(256) chunk_gather_kernel(const double* __restr
 }  // namespace
 
 // chunk_start / n_chunks from sorted keys (+ sorted points for the gap rule)
-static int cut_chunks(b3d_ctx* ctx, const uint64_t* keys, const double4* pts, int shift, double cell, int32_t n,
+constexpr double kChunkGapQuery = 1.5, kChunkGapGrid = 1.5;
+
+static double chunk_gap_cells(const char* own_env, double dflt) {
+    if (const char* e = getenv(own_env)) return atof(e);
+    if (const char* e = getenv("B3D_CHUNK_GAP")) return atof(e);
+    return dflt;
+}
+
+static int cut_chunks(b3d_ctx* ctx, const uint64_t* keys, const double4* pts, int shift, double cell, double tau_cells, int32_t n,
                       int32_t* chunk_start, int64_t* n_chunks_d) {
-    // runs of spatially consecutive points (no jump longer than 1.5 cells), then a chunk every 32 points of a run: chunks
+    // runs of spatially consecutive points (no jump longer than tau_cells cells), then a chunk every 32 points of a run: chunks
     // are full except at the end of a run, and compact because the curve does not jump inside a run
-    double tau_cells = 1.5;  // measured on config 2 (1.0 / 1.25 / 1.5 / 2.0 / 3.0 cells: 49.7 / 47.9 / 47.5 / 47.8 / 51.5 ms per step)
-    if (const char* e = getenv("B3D_CHUNK_GAP")) tau_cells = atof(e);
     const double tau = tau_cells * cell;
     const int64_t tiles = ((int64_t)n + kCutTile - 1) / kCutTile;
     if (tiles == 0) {
@@ -308,7 +314,9 @@ int build_query_chunks(b3d_ctx* ctx, const double* pts, const int32_t* off_d, co
     B3D_LAUNCH(ctx, chunk_gather_kernel, ctx->grid_for(n, 256, 1, 8), 256, 0, pts, o_out.p, n, out->pts.p);
     DevBuf<int64_t> n_chunks_d;
     B3D_TRY(n_chunks_d.alloc(ctx, 1));
-    B3D_TRY(cut_chunks(ctx, k_out.p, out->pts.p, shift, lattices.lat_h[0].cell, n, out->chunk_start.p, n_chunks_d.p));
+    // gap of the query chunks (Hilbert order): measured on config 2, see DESIGN.md 3.5
+    static const double gap_q = chunk_gap_cells("B3D_CHUNK_GAP_QUERY", kChunkGapQuery);
+    B3D_TRY(cut_chunks(ctx, k_out.p, out->pts.p, shift, lattices.lat_h[0].cell, gap_q, n, out->chunk_start.p, n_chunks_d.p));
     B3D_LAUNCH(ctx, chunk_sentinel_kernel, 1, 1, 0, out->chunk_start.p, n_chunks_d.p, n);
     B3D_LAUNCH(ctx, chunk_ranges_kernel, (B + 1 + 127) / 128, 128, 0, out->chunk_start.p, n_chunks_d.p, off_d, B, out->chunk_off.p);
     B3D_TRY(ctx->download(out->chunk_off_h.data(), out->chunk_off.p, (size_t)(B + 1) * sizeof(int32_t)));
@@ -336,7 +344,10 @@ int chunks_from_grid(b3d_ctx* ctx, const Grid<double>& grid, const int32_t* off_
     }
     DevBuf<int64_t> n_chunks_d;
     B3D_TRY(n_chunks_d.alloc(ctx, 1));
-    B3D_TRY(cut_chunks(ctx, ss.keys.p, grid.pts.p, ss.shift, grid.cell, n, out->chunk_start.p, n_chunks_d.p));
+    // gap of the chunks cut from a grid's own (Morton) order: 1.0 / 1.25 / 1.5 / 2.0 / 3.0 cells measured 49.7 / 47.9 / 47.5 / 47.8 / 51.5 ms
+    // per config-2 step in round 1, 1.0 / 1.5 / 2.5 cells 5.67 / 5.25 / 5.78 ms of normals in round 2
+    static const double gap_g = chunk_gap_cells("B3D_CHUNK_GAP_GRID", kChunkGapGrid);
+    B3D_TRY(cut_chunks(ctx, ss.keys.p, grid.pts.p, ss.shift, grid.cell, gap_g, n, out->chunk_start.p, n_chunks_d.p));
     B3D_LAUNCH(ctx, chunk_sentinel_kernel, 1, 1, 0, out->chunk_start.p, n_chunks_d.p, n);
     B3D_LAUNCH(ctx, chunk_ranges_kernel, (B + 1 + 127) / 128, 128, 0, out->chunk_start.p, n_chunks_d.p, off_d, B, out->chunk_off.p);
     B3D_TRY(ctx->download(out->chunk_off_h.data(), out->chunk_off.p, (size_t)(B + 1) * sizeof(int32_t)));

@@ -56,100 +56,32 @@ constexpr int kIcpMaxRunLog2 = 6;  // runs of up to 64 chunk groups (1024 chunks
 constexpr double kIcpReach2 = 1.25;   // search radius of a lane that found nothing last time, in units of d_max (see the pass kernel)
 
 // ---- small dense helpers (device) ----------------------------------------------------------------------------------
-// (M^-1)^(1/2) of a symmetric positive-definite 3x3 (GICP weight, one per correspondence per pass) WITHOUT eigenvectors. With
-// U = M^(1/2) and its invariants I = s1 + s2 + s3, II = s1 s2 + s2 s3 + s1 s3, III = s1 s2 s3 (s_i = sqrt of M's eigenvalues, from
-// the closed-form trigonometric solver), Cayley-Hamilton for U gives U (M + II) = I M + III, i.e.
-//     M^(-1/2) = (I M + III)^(-1) (M + II)
-// -- one well-conditioned 3x3 inverse (adjugate) and one product; the invariants are symmetric functions of the eigenvalues, so
-// nearly equal eigenvalues (parallel normals, the usual case) cost no accuracy. ~650 instructions, relative error ~1e-13 against
-// scipy's sqrtm(inv(M)) for the covariances GICP builds (eigenvalues 1e-3 .. 2). Matrices with a spectrum wider than 1e7 take the
-// coupled Newton-Schulz iteration  T = (3 I - Z Y) / 2,  Y <- Y T,  Z <- T Z  (Y = M / trace, Z = I; Z -> (M / trace)^(-1/2)):
-// three FULL 3x3 products per step (the iteration is only stable with the exact product structure), 15-35 steps, error ~1e-13 at
-// any conditioning. The eigen-DECOMPOSITION used before (and the Jacobi sweeps of the CPU oracle) is as accurate but ~2 500
-// straight-line float64 instructions: with it in the pass kernel a third of the warps' time went to instruction fetch
-// (profiles/r02e_c3_gicp_stalls.txt). Out of line: one copy, outside the pass kernel's main body.
-__device__ __noinline__ void inv_sqrt_sym3(const double* M, double* W) {
-    const double tr = M[0] + M[4] + M[8];  // >= the largest eigenvalue of a positive-definite M
-    if (!(tr > 0.0) || !(tr < 1.0e300)) {  // not positive definite / not finite: the diagonal rule of the old closed form's fallback
-#pragma unroll
-        for (int i = 0; i < 9; ++i) W[i] = 0.0;
-        W[0] = 1.0 / sqrt(M[0]); W[4] = 1.0 / sqrt(M[4]); W[8] = 1.0 / sqrt(M[8]);
-        return;
-    }
-    // ---- eigenvalues of A = M / tr (closed form; a diagonal A is its own answer) ----
-    const double inv_tr = 1.0 / tr;
-    const double a00 = M[0] * inv_tr, a01 = M[1] * inv_tr, a02 = M[2] * inv_tr, a11 = M[4] * inv_tr, a12 = M[5] * inv_tr, a22 = M[8] * inv_tr;
-    double l0 = a00, l1 = a11, l2 = a22;
-    const double off = a01 * a01 + a02 * a02 + a12 * a12;
-    if (off > 0.0) {
-        const double q = (1.0 / 3.0);  // trace(A) / 3 with trace(A) = 1
-        const double b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
-        const double p2 = (b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * off) * (1.0 / 6.0);
-        const double p = sqrt(p2);
-        const double c00 = b11 * b22 - a12 * a12, c01 = a01 * b22 - a12 * a02, c02 = a01 * a12 - b11 * a02;
-        const double ip = 1.0 / p;
-        double half = (b00 * c00 - a01 * c01 + a02 * c02) * (ip * ip * ip) * 0.5;
-        half = half < -1.0 ? -1.0 : (half > 1.0 ? 1.0 : half);
-        double sa, ca;
-        sincos(acos(half) * (1.0 / 3.0), &sa, &ca);
-        const double beta2 = 2.0 * ca, beta0 = -ca - 1.7320508075688772 * sa;  // 2 cos(angle + 2 pi / 3)
-        l0 = q + p * beta0;
-        l2 = q + p * beta2;
-        l1 = 1.0 - l0 - l2;
-    }
-    const double lmin = fmin(l0, fmin(l1, l2)), lmax = fmax(l0, fmax(l1, l2));
-    double Z[9];
-    if (lmin > 1.0e-7 * lmax) {
-        const double s0 = sqrt(l0), s1 = sqrt(l1), s2 = sqrt(l2);
-        const double I1 = s0 + s1 + s2, I2 = s0 * s1 + s1 * s2 + s0 * s2, I3 = s0 * s1 * s2;
-        // B = I1 A + I3, its adjugate, C = A + I2; Z = B^-1 C = A^(-1/2)
-        const double B00 = I1 * a00 + I3, B01 = I1 * a01, B02 = I1 * a02, B11 = I1 * a11 + I3, B12 = I1 * a12, B22 = I1 * a22 + I3;
-        const double k00 = B11 * B22 - B12 * B12, k01 = B02 * B12 - B01 * B22, k02 = B01 * B12 - B02 * B11;
-        const double k11 = B00 * B22 - B02 * B02, k12 = B01 * B02 - B00 * B12, k22 = B00 * B11 - B01 * B01;
-        const double idet = 1.0 / (B00 * k00 + B01 * k01 + B02 * k02);
-        const double C00 = a00 + I2, C11 = a11 + I2, C22 = a22 + I2;
-        Z[0] = (k00 * C00 + k01 * a01 + k02 * a02) * idet;
-        Z[1] = (k00 * a01 + k01 * C11 + k02 * a12) * idet;
-        Z[2] = (k00 * a02 + k01 * a12 + k02 * C22) * idet;
-        Z[4] = (k01 * a01 + k11 * C11 + k12 * a12) * idet;
-        Z[5] = (k01 * a02 + k11 * a12 + k12 * C22) * idet;
-        Z[8] = (k02 * a02 + k12 * a12 + k22 * C22) * idet;
-    } else {
-        double Y[9] = {a00, a01, a02, a01, a11, a12, a02, a12, a22};
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Z[i] = (i % 4 == 0) ? 1.0 : 0.0;
-#pragma unroll 1
-        for (int it = 0; it < 100; ++it) {
-            double T[9], P[9];
-            double err = 0.0;
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const double zy = fma(Z[3 * r], Y[c], fma(Z[3 * r + 1], Y[3 + c], Z[3 * r + 2] * Y[6 + c]));
-                    const double t = (r == c ? 1.5 : 0.0) - 0.5 * zy;
-                    T[3 * r + c] = t;
-                    err = fmax(err, fabs(t - (r == c ? 1.0 : 0.0)));
-                }
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) P[3 * r + c] = fma(Y[3 * r], T[c], fma(Y[3 * r + 1], T[3 + c], Y[3 * r + 2] * T[6 + c]));
-#pragma unroll
-            for (int i = 0; i < 9; ++i) Y[i] = P[i];
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) P[3 * r + c] = fma(T[3 * r], Z[c], fma(T[3 * r + 1], Z[3 + c], T[3 * r + 2] * Z[6 + c]));
-#pragma unroll
-            for (int i = 0; i < 9; ++i) Z[i] = P[i];
-            if (!(err >= 1.0e-14)) break;  // converged (quadratically: this step already took the error to ~1e-28), or NaN
-        }
-    }
-    const double f = 1.0 / sqrt(tr);  // A = M / tr
-    W[0] = Z[0] * f; W[1] = Z[1] * f; W[2] = Z[2] * f;
-    W[4] = Z[4] * f; W[5] = Z[5] * f; W[8] = Z[8] * f;
-    W[3] = W[1]; W[6] = W[2]; W[7] = W[5];
+// Generalized-ICP weight of one correspondence. Open3D (TransformationEstimationForGeneralizedICP::ComputeTransformation) forms
+// W = (M^-1)^(1/2) for M = C_t + R C_s R^T and the three rows J = W [ -[p]x | I ], r = W (p - q); what the Gauss-Newton step consumes
+// is only J^T J = G^T W^T W G = G^T M^-1 G and J^T r = G^T M^-1 (p - q). ANY factor F with F^T F = M^-1 gives the same two sums, so the
+// kernel takes the cheapest one: the inverse of M's Cholesky factor (M = L L^T, F = L^-1, lower triangular) -- three reciprocal
+// square roots and a dozen multiplications (~100 instructions) instead of a symmetric square root (closed-form
+// eigenvalues through acos / sincos + a Cayley-Hamilton inverse: ~650 executed instructions and 17 KB of code, which is what the
+// pass kernel of an 8 MP stereo pair waited for: profiles/r02e_c3_gicp_stalls.txt, instruction-fetch stalls). The covariances GICP
+// builds have eigenvalues in [1e-3, 2]: the factorisation is well conditioned. Results differ from the symmetric-root version
+// by rounding only (both are exact factorisations of the same M^-1); the CPU oracle keeps the library's formulation.
+// Not positive definite / not finite: the diagonal rule (weights 1 / sqrt(M_ii)), as before.
+__device__ __forceinline__ void gicp_factor(const double* M, double* F) {
+    const double m00 = M[0], m01 = M[1], m02 = M[2], m11 = M[4], m12 = M[5], m22 = M[8];
+    const double f00 = rsqrt(m00);             // 1 / l00 (rsqrt: 1 ulp, no slow path -- F^T F stays M^-1 to rounding)
+    const double l10 = m01 * f00, l20 = m02 * f00;
+    const double p1 = m11 - l10 * l10;
+    const double f11 = rsqrt(p1);              // 1 / l11
+    const double l21 = (m12 - l20 * l10) * f11;
+    const double p2 = m22 - l20 * l20 - l21 * l21;
+    const double f22 = rsqrt(p2);              // 1 / l22
+    const double f10 = -l10 * f00 * f11;
+    const double f21 = -l21 * f11 * f22;
+    const double f20 = -(l20 * f00 + l21 * f10) * f22;
+    const bool ok = m00 > 0.0 && p1 > 0.0 && p2 > 0.0 && f00 * f11 * f22 < 1.0e300;  // false for NaN as well
+    F[0] = ok ? f00 : rsqrt(m00); F[1] = 0.0; F[2] = 0.0;
+    F[3] = ok ? f10 : 0.0; F[4] = ok ? f11 : rsqrt(m11); F[5] = 0.0;
+    F[6] = ok ? f20 : 0.0; F[7] = ok ? f21 : 0.0; F[8] = ok ? f22 : rsqrt(m22);
 }
 
 // ---- per-warp reduction through shared memory ------------------------------------------------------------------------
@@ -485,7 +417,7 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP_MIN_BLOCKS) icp_pass_kernel
 #pragma unroll
                         for (int c = 0; c < 3; ++c)
                             M[3 * r + c] = __ldg(Ct + 3 * r + c) + (RC[3 * r] * sT[4 * c] + RC[3 * r + 1] * sT[4 * c + 1] + RC[3 * r + 2] * sT[4 * c + 2]);
-                    inv_sqrt_sym3(M, W);
+                    gicp_factor(M, W);
                     gd[0] = px - q.x; gd[1] = py - q.y; gd[2] = pz - q.z;
                     gp[0] = px; gp[1] = py; gp[2] = pz;
                 }
@@ -908,6 +840,13 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                         if (KIND == B3D_ICP_POINT_TO_PLANE) prefetch_l1(A.tgt_nrm_sorted + 3 * (int64_t)kp);  // most lanes keep this partner
                         const double dk = dist2<double>(px - q.x, py - q.y, pz - q.z);
                         const float u = sqrtf((float)dk) * 1.000001f;
+#ifdef B3D_ICP2_STATS_MOVES  // [1] lanes with a partner, [4] sum of their movement since the last search, [5] of the room lim - u (micrometres)
+                        if (A.stats) {
+                            atomicAdd(&g_icp_stats[1], 1ull);
+                            atomicAdd(&g_icp_stats[4], (unsigned long long)(1.0e6f * moved));
+                            atomicAdd(&g_icp_stats[5], (unsigned long long)(1.0e6f * fmaxf(lim - u, 0.f)));
+                        }
+#endif
                         if ((u + moved) * 1.000001f < lim) {  // still strictly nearer than anything else can be
                             need = false;
                             pos = kp;
@@ -997,7 +936,9 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                         atomicAdd(&g_icp_stats[0], 1ull);
                         if (nb < 0) atomicAdd(&g_icp_stats[2], 1ull);
                         else atomicAdd(&g_icp_stats[3], (unsigned long long)last_kept);
+#ifndef B3D_ICP2_STATS_MOVES
                         if (nb > 1) atomicAdd(&g_icp_stats[1], 1ull);
+#endif
                     }
 #endif
                     double others2 = 3.0e38;  // lower bound of the squared distance (metres) of every target point but the winner
@@ -1008,6 +949,9 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                             // box too large to stage, or a near-tie in a box that took several batches (the earlier candidates are gone)
                             pos = icp2_walk(A.grid, pair, px, py, pz, A.r2, A.rmax);
                             if (nb >= 0) bounded = false;
+#if defined(B3D_ICP2_STATS) && !defined(B3D_ICP2_STATS_MOVES)
+                            if (A.stats) atomicAdd(&g_icp_stats[4], 1ull);
+#endif
                         } else {
                             pos = wpos;
                         }
@@ -1023,6 +967,9 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
                         }
                         if (nb >= 0 && wpos >= 0 && !(ambiguous && nb > 1)) {
                             if (ambiguous) {
+#if defined(B3D_ICP2_STATS) && !defined(B3D_ICP2_STATS_MOVES)
+                                if (A.stats) atomicAdd(&g_icp_stats[5], 1ull);
+#endif
                                 const int tpos = icp2_resolve_ties(A.grid.pts, S.buf, S.pos, last_kept, fx, fy, fz, best + band_w, px, py, pz, wpos, d2, idx);
                                 if (tpos != pos) {
                                     have_nrm = false;
@@ -1087,7 +1034,7 @@ __global__ void __launch_bounds__(kIcpBlock, B3D_ICP2_MIN_BLOCKS) icp_pass2_kern
 #pragma unroll
                                 for (int cc = 0; cc < 3; ++cc)
                                     M[3 * r + cc] = __ldg(Ct + 3 * r + cc) + (RC[3 * r] * sT[4 * cc] + RC[3 * r + 1] * sT[4 * cc + 1] + RC[3 * r + 2] * sT[4 * cc + 2]);
-                            inv_sqrt_sym3(M, W);
+                            gicp_factor(M, W);
                             gd[0] = px - q.x; gd[1] = py - q.y; gd[2] = pz - q.z;
                             gp[0] = px; gp[1] = py; gp[2] = pz;
                         }

@@ -515,6 +515,143 @@ __global__ void __launch_bounds__(kNrmBlock, B3D_NRM2_MIN_BLOCKS) normals_cov2_k
     }
 }
 
+// ---- the queued points of the staged path, one WARP per point ----------------------------------------------------------------
+// A point is queued by normals_cov2_kernel when its radius holds more neighbours than k (or than 32), i.e. it needs the k NEAREST of
+// them by the library's (d2, index) order, or when its group's box did not fit one staging batch. The per-lane kernel redid such
+// points one thread each: on an 8 MP stereo cloud 0.2 % of the points (dense patches) cost 0.38 ms per cloud -- a handful of threads
+// each walking ~1000 candidates behind dependent loads. Here the warp stages the point's own ball batch by batch (b3d_stage2.cuh),
+// every lane takes candidates 32 apart (float pre-test, exact float64 distance for everything that may lie inside the radius), the
+// in-radius ones are compacted into the warp's key rows as {d2, sorted position, index}; whenever the rows fill up, and at the end,
+// the entries are RANKED BY COUNTING (rank = number of smaller entries; broadcast reads, no sort) and the k smallest move to the
+// front in rank order. Lane 0 then sums the nine raw moments in that order: the arithmetic of the per-lane kernel, bit for bit.
+constexpr int kNrmQCap = 232;  // 232 + 32 entries of 16 bytes = the 32 x 33 words of a warp's key rows
+struct NrmQEntry {
+    double d2;
+    int pos, idx;
+};
+static_assert(sizeof(NrmQEntry) == 16 && (kNrmQCap + 32) * 4 <= 32 * (kNrm2List + 1), "the entries alias the key rows");
+
+__global__ void __launch_bounds__(kNrmBlock) normals_queue2_kernel(GridView<double> g, const uint64_t* __restrict__ keys, const int32_t* __restrict__ off, int k_nn,
+                                                                  double radius, double r2, int rmax, const double* __restrict__ prior,
+                                                                  double* __restrict__ normals, const int* __restrict__ todo, const int* __restrict__ todo_count) {
+    extern __shared__ __align__(16) unsigned char nrm2_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Nrm2Smem& W = reinterpret_cast<Nrm2Smem*>(nrm2_smem)[warp];
+    auto& S = W.stage;
+    stage2_init_barrier(&S.mbar);
+    uint32_t parity = 0;
+    NrmQEntry* ent = reinterpret_cast<NrmQEntry*>(&W.keys[0][0]);
+    NrmQEntry* best = ent + kNrmQCap;  // the k smallest of a ranking, in rank order
+    const int n_work = *todo_count;
+    for (int t = (int)blockIdx.x * (kNrmBlock / 32) + warp; t < n_work; t += (int)gridDim.x * (kNrmBlock / 32)) {
+        const int i = todo[t];
+        const double4 q = ld_point(g.pts + i);
+        const int cloud = (int)(keys[i] >> g.shift);
+        const UnitFrame F = unit_frame(g.lat[cloud], g.shift);
+        const float r2u = (float)(r2 * F.per_m * F.per_m);
+        const double ru = radius * F.per_m * (1.0 + 1e-12) + 2.0;
+        const double ux = unit_coord_of_query(q.x, F.ox, F.per_m), uy = unit_coord_of_query(q.y, F.oy, F.per_m), uz = unit_coord_of_query(q.z, F.oz, F.per_m);
+        const int lox = max(unit_floor_clamped(ux - ru), 0), loy = max(unit_floor_clamped(uy - ru), 0), loz = max(unit_floor_clamped(uz - ru), 0);
+        const int hix = unit_ceil_clamped(ux + ru), hiy = unit_ceil_clamped(uy + ru), hiz = unit_ceil_clamped(uz + ru);
+        const int ccx = (int)(((long long)lox + hix) >> 1), ccy = (int)(((long long)loy + hiy) >> 1), ccz = (int)(((long long)loz + hiz) >> 1);
+        const float qox = (float)(ux - (double)ccx), qoy = (float)(uy - (double)ccy), qoz = (float)(uz - (double)ccz);
+        const float fx = -2.0f * qox, fy = -2.0f * qoy, fz = -2.0f * qoz;
+        const float qq = fmaf(qoz, qoz, fmaf(qoy, qoy, qox * qox));
+        const float H = fmaxf(fmaxf((float)(hix - ccx), (float)(hiy - ccy)), (float)(hiz - ccz)) + 1.0f;
+        const float band = stage2_band(H) + 4.0e-7f * r2u;  // as in normals_cov2_kernel
+        const float2 f2x = make_float2(fx, fx), f2y = make_float2(fy, fy), f2z = make_float2(fz, fz);
+        int n = 0;  // entries held (warp-uniform)
+        // ranks the n entries and moves the k smallest to the front, in (d2, index) order
+        auto keep_k_smallest = [&]() {
+            __syncwarp();
+            for (int e = lane; e < n; e += 32) {
+                const NrmQEntry a = ent[e];
+                int rank = 0;
+                for (int j = 0; j < n; ++j) {
+                    const double dj = ent[j].d2;
+                    rank += (dj < a.d2 || (dj == a.d2 && ent[j].idx < a.idx)) ? 1 : 0;
+                }
+                if (rank < k_nn) best[rank] = a;
+            }
+            __syncwarp();
+            n = min(n, k_nn);
+            if (lane < n) ent[lane] = best[lane];
+            __syncwarp();
+        };
+        auto scan = [&](int kept) {
+            for (int j0 = 0; j0 < kept; j0 += 32) {
+                if (n + 32 > kNrmQCap) keep_k_smallest();
+                const int j = j0 + lane;
+                bool acc = false;
+                NrmQEntry a{0.0, 0, 0};
+                if (j < kept && cand_t(S.buf, j, f2x, f2y, f2z) + qq <= r2u + band) {  // may lie inside the radius: exact distance
+                    a.pos = S.pos[j];
+                    const double4 pj = ld_point(g.pts + a.pos);
+                    a.d2 = dist2<double>(q.x - pj.x, q.y - pj.y, q.z - pj.z);
+                    a.idx = point_index(pj);
+                    acc = a.d2 < r2;
+                }
+                const unsigned int m = __ballot_sync(0xffffffffu, acc);
+                if (acc) ent[n + __popc(m & ((1u << lane) - 1u))] = a;
+                n += __popc(m);
+            }
+            __syncwarp();
+        };
+        const int nb = stage2_run<kNrm2Cap>(g, F, cloud, lox, loy, loz, hix, hiy, hiz, S, parity, scan);
+        double cu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        int c = 0;
+        if (nb < 0) {
+            // a box the staging cannot take (one cell beyond the buffer, > 1024 cells): the per-lane walk, on lane 0
+            if (lane == 0) {
+                TopK<double, 32> tk;
+                knn_hybrid_query<double, 32>(g, off, cloud, q.x, q.y, q.z, k_nn, true, r2, rmax, tk);
+                c = tk.n;
+                for (int j = 0; j < c; ++j) best[j].pos = tk.pos[j];
+            }
+        } else {
+            keep_k_smallest();
+            c = n;
+            if (lane < c) best[lane].pos = ent[lane].pos;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (int j = 0; j < c; ++j) {
+                const double4 pj = ld_point(g.pts + best[j].pos);
+                const double x = pj.x, y = pj.y, z = pj.z;
+                cu[0] += x; cu[1] += y; cu[2] += z;
+                cu[3] += x * x; cu[4] += x * y; cu[5] += x * z;
+                cu[6] += y * y; cu[7] += y * z; cu[8] += z * z;
+            }
+            Sym3<double> C{1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
+            if (c >= 3) {
+                const double cn = (double)c;
+#pragma unroll
+                for (int j = 0; j < 9; ++j) cu[j] /= cn;
+                C.a00 = cu[3] - cu[0] * cu[0];
+                C.a11 = cu[6] - cu[1] * cu[1];
+                C.a22 = cu[8] - cu[2] * cu[2];
+                C.a01 = cu[4] - cu[0] * cu[1];
+                C.a02 = cu[5] - cu[0] * cu[2];
+                C.a12 = cu[7] - cu[1] * cu[2];
+            }
+            Vec3<double> nrm = sym3_smallest_eigvec<double>(C);
+            const int64_t oi = point_index(q);
+            const double len = sqrt(nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z);
+            if (prior != nullptr) {
+                const double ox = prior[3 * oi], oy = prior[3 * oi + 1], oz = prior[3 * oi + 2];
+                if (len == 0.0) nrm = {ox, oy, oz};
+                else if (nrm.x * ox + nrm.y * oy + nrm.z * oz < 0.0) nrm = {-nrm.x, -nrm.y, -nrm.z};
+            } else if (len == 0.0) {
+                nrm = {0.0, 0.0, 1.0};
+            }
+            normals[3 * oi] = nrm.x;
+            normals[3 * oi + 1] = nrm.y;
+            normals[3 * oi + 2] = nrm.z;
+        }
+        __syncwarp();
+    }
+}
+
 // cov6[i] = {a00 a01 a02 a11 a12 a22} of point i (original index) -> unit normal, oriented against the prior
 __global__ void __launch_bounds__(256) normals_eig2_kernel(const double* __restrict__ cov6, int64_t n, const double* __restrict__ prior,
                                                            double* __restrict__ normals) {
@@ -733,6 +870,11 @@ int estimate_normals_batch(b3d_ctx* ctx, const T* xyz, const Segments& seg, int 
                 B3D_LAUNCH(ctx, normals_cov2_kernel, sblocks, kNrmBlock, smem, grid->view(), qc.chunk_start.p, qc.chunk_off.p, seg.B, qc.n_chunks, max_nn,
                            radius, r2, cov6.p, todo_buf.p, todo_count_buf.p, getenv("B3D_ICP_STATS") ? 1 : 0);
                 B3D_LAUNCH(ctx, normals_eig2_kernel, ctx->grid_for(n, 256, 1, 8), 256, 0, cov6.p, (int64_t)n, prior, normals);
+                // the queued points (k-nearest cuts, boxes beyond one batch): one warp each
+                B3D_CUDA(cudaFuncSetAttribute(normals_queue2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                B3D_LAUNCH(ctx, normals_queue2_kernel, std::max(1, std::min(sblocks, ctx->sm_count * 4)), kNrmBlock, smem, grid->view(), grid->sort.keys.p,
+                           seg.off, max_nn, radius, r2, rmax, prior, normals, todo_buf.p, todo_count_buf.p);
+                return B3D_OK;
             } else {
                 const int sblocks = std::max(1, std::min((qc.n_chunks + kNrmBlock / 32 - 1) / (kNrmBlock / 32), ctx->sm_count * 32));
                 const size_t smem = sizeof(NrmWarpSmem) * (kNrmBlock / 32);

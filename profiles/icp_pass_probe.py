@@ -40,8 +40,13 @@ for rep in range(2):  # the second repetition is the warm one
             break
     res = sh.finish()
 print(f"source {len(src)}, target {len(tgt)}, iterations {res['iterations']}, fitness {res['fitness']:.4f}, rmse {res['inlier_rmse'] * 1e3:.3f} mm")
-print("pass  us     chunks  kept%  lanes/searched-chunk  overflow  cand/staging  edge_cm")
+print("pass  us     chunks  kept%  lanes/searched-chunk  overflow  cand/staging  multi-batch%  walks/1k-lanes  ties/1k-lanes")
+moves = bool(os.environ.get("B3D_PROBE_MOVES"))  # library built with -DB3D_ICP2_STATS_MOVES: counters 1, 4, 5 mean something else
 for k, us, o in rows:
     c1, c2, ovf, cand, vol, edge, kept, lanes = o
+    if moves:
+        print(f"{k:3d} {us:7.1f} us  lanes with a partner {c2:8d}  mean movement since the last search {vol / max(c2, 1):8.1f} um  "
+              f"mean room (bound - distance) {edge / max(c2, 1):8.1f} um  searched lanes {lanes}")
+        continue
     print(f"{k:3d} {us:7.1f} {kept + c1:7d} {100.0 * kept / max(kept + c1, 1):6.1f} {lanes / max(c1, 1):10.1f} {ovf:8d} "
-          f"{cand / max(c1 + c2 - ovf, 1):10.1f} {edge / max(c1 + c2, 1) / 100:10.2f}")
+          f"{cand / max(c1 - ovf, 1):10.1f} {100.0 * c2 / max(c1, 1):10.1f} {1e3 * vol / max(lanes, 1):12.2f} {1e3 * edge / max(lanes, 1):12.2f}")

@@ -233,6 +233,23 @@ def test_normals_legacy_variants(ops):
     assert np.allclose(ops.estimate_normals_legacy(line, 10, 0.0), oracle.normals_legacy(line, 10, 0.0), atol=1e-12)
 
 
+def test_normals_dense_patches(ops):
+    """Points whose radius holds many more neighbours than k take the warp-per-point queue kernel (k-nearest cut by (d2, index)):
+    patches of 40 / 300 / 700 points inside one ball exercise the single batch, the ranking-with-pruning and the multi-batch path."""
+    rng = np.random.default_rng(77)
+    base = surface_cloud(20_000, seed=12)
+    blobs = []
+    for n_blob, c in ((40, 100), (300, 5000), (700, 12000), (700, 19000)):
+        ctr = base[c]
+        blobs.append(ctr + rng.normal(0.0, 0.002, (n_blob, 3)) * np.array([1.0, 1.0, 0.2]))
+    pts = np.concatenate([base] + blobs)
+    for k, r in ((30, 0.02), (5, 0.01), (32, 0.03)):
+        ref = oracle.normals_legacy(pts, k, r)
+        out = ops.estimate_normals_legacy(pts, k, r)
+        d = _normal_diff(out, ref)
+        assert np.quantile(d, 0.999) < 1e-9 and (d > 1e-6).sum() <= 3, (k, r, np.quantile(d, 0.999), d.max())
+
+
 def test_normals_tensor(ops):
     pts = surface_cloud(60_000, seed=13).astype(np.float32)
     for k, r in ((50, 0.05), (30, 0.01)):

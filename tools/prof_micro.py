@@ -47,6 +47,19 @@ def main():
                                            icp_max_dist=0.02, icp_max_iter=30)
         sd, td = torch.from_numpy(ds[None]).cuda(), torch.from_numpy(dt[None]).cuda()
         table(ctx, lambda: ops.register_disparity_pairs(sd, td, params))
+        if os.environ.get("B3D_ICP_STATS"):  # staged-normals counters of one call (needs a -DB3D_NRM2_STATS build, B3D_LIB=...)
+            import ctypes as C
+            from b200recon import _native as N
+            L = N.lib()
+            L.b3d_debug_normals_stats.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
+            L.b3d_debug_normals_stats(None, 1)
+            r = ops.register_disparity_pairs(sd, td, params)[0]
+            torch.cuda.synchronize()
+            out = (C.c_ulonglong * 8)()
+            L.b3d_debug_normals_stats(out, 1)
+            ch, ovf, cut, cand, lanes = [int(v) for v in out[:5]]
+            print(f"normals of both clouds ({r['m_source']} + {r['m_target']} points): stagings {ch}, multi-batch or fallback {ovf}, lanes queued for the "
+                  f"k-nearest cut {cut} ({100.0 * cut / max(lanes, 1):.1f} % of {lanes} lanes), candidates per staging {cand / max(ch - ovf, 1):.1f}")
     else:
         import bench
         src, tgt = bench.make_inputs(1, 1, 3000)
