@@ -30,6 +30,21 @@ constexpr int kRsMaxPasses = 8;
 // ---------------------------------------------------------------------------------------------------------------------
 // segmented packed onesweep
 // ---------------------------------------------------------------------------------------------------------------------
+// Block shape of the segmented onesweep sort: kOsThreads x kOsItems keys per tile (measured on config 2, ms of sort per 64-pair
+// step: 256 x 16: 2.98, 512 x 8: 3.34, 1024 x 4: 4.69 -- larger blocks wait longer at their barriers).
+#ifndef B3D_OS_THREADS
+#define B3D_OS_THREADS 256
+#endif
+#ifndef B3D_OS_ITEMS
+#define B3D_OS_ITEMS 16
+#endif
+constexpr int kOsThreads = B3D_OS_THREADS;
+constexpr int kOsWarps = kOsThreads / 32;
+constexpr int kOsItems = B3D_OS_ITEMS;
+constexpr int kOsTile = kOsThreads * kOsItems;
+constexpr int kOsWarpTile = 32 * kOsItems;
+static_assert(kOsThreads >= 256 && kOsTile % kRsThreads == 0, "one thread per digit; the histogram kernel walks a tile with kRsThreads threads");
+
 struct RsSegView {
     const int32_t* seg_off;     // [B + 1] element offsets
     const int32_t* tile_first;  // [B + 1] first tile of every segment
@@ -70,10 +85,10 @@ __global__ void __launch_bounds__(kRsThreads) rs_hist_all_kernel(const uint64_t*
             __syncthreads();
             seg = s;
         }
-        const int64_t base = (int64_t)sv.seg_off[seg] + (int64_t)(t - sv.tile_first[seg]) * kRsTile;
+        const int64_t base = (int64_t)sv.seg_off[seg] + (int64_t)(t - sv.tile_first[seg]) * kOsTile;
         const int64_t end = sv.seg_off[seg + 1];
 #pragma unroll 4
-        for (int k = 0; k < kRsItems; ++k) {
+        for (int k = 0; k < kOsTile / kRsThreads; ++k) {
             const int64_t i = base + k * kRsThreads + threadIdx.x;
             if (i < end) {
                 const uint64_t key = __ldg(keys + i) & low_mask;  // the segment bits above low_bits are not sorted
@@ -115,35 +130,35 @@ constexpr uint32_t kLbAgg = 1u << 30, kLbPrefix = 2u << 30, kLbMask = (1u << 30)
 // One pass. FIRST: reads the caller's keys and packs (key_low << ib | position); LAST: unpacks into keys_out / order_out.
 // status: [n_tiles][256] look-back words of this pass (zeroed), ticket: this pass's tile counter (zeroed).
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(kRsThreads) rs_onesweep_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, uint32_t* __restrict__ order_out,
+__global__ void __launch_bounds__(kOsThreads) rs_onesweep_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, uint32_t* __restrict__ order_out,
                                                                  RsSegView sv, int low_bits, int ib, int pass, int passes,
                                                                  const uint32_t* __restrict__ gbase, uint32_t* __restrict__ status,
                                                                  unsigned int* __restrict__ ticket) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
     uint64_t* skeys = reinterpret_cast<uint64_t*>(rs_smem);
-    __shared__ uint32_t warp_cnt[kRsWarps][256];
+    __shared__ uint32_t warp_cnt[kOsWarps][256];
     __shared__ uint32_t digit_base[256];   // global position of the tile's first key of each digit
     __shared__ uint32_t digit_start[256];  // tile-local position of the same
-    __shared__ uint32_t s_wsum[kRsWarps];
+    __shared__ uint32_t s_wsum[kOsWarps];
     __shared__ unsigned int s_tile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int k = threadIdx.x; k < kRsWarps * 256; k += kRsThreads) (&warp_cnt[0][0])[k] = 0;
+    for (int k = threadIdx.x; k < kOsWarps * 256; k += kOsThreads) (&warp_cnt[0][0])[k] = 0;
     __syncthreads();
     const int tile = (int)s_tile;
     const int seg = rs_find_segment(sv, tile);
     const int tile_in_seg = tile - sv.tile_first[seg];
-    const int64_t tbase = (int64_t)sv.seg_off[seg] + (int64_t)tile_in_seg * kRsTile;
+    const int64_t tbase = (int64_t)sv.seg_off[seg] + (int64_t)tile_in_seg * kOsTile;
     const int64_t seg_end = sv.seg_off[seg + 1];
-    const int64_t wbase = tbase + (int64_t)warp * kRsWarpTile;
-    const int tile_count = (int)min((int64_t)kRsTile, seg_end - tbase);
+    const int64_t wbase = tbase + (int64_t)warp * kOsWarpTile;
+    const int tile_count = (int)min((int64_t)kOsTile, seg_end - tbase);
     const int shift = ib + 8 * pass;
     const uint64_t low_mask = low_bits >= 64 ? ~0ull : ((1ull << low_bits) - 1ull);
-    uint64_t key[kRsItems];
-    uint32_t rank[kRsItems];
+    uint64_t key[kOsItems];
+    uint32_t rank[kOsItems];
     // all loads first (16 independent requests in flight per thread), then the ranking
 #pragma unroll
-    for (int s = 0; s < kRsItems; ++s) {
+    for (int s = 0; s < kOsItems; ++s) {
         const int64_t i = wbase + s * 32 + lane;
         uint64_t e = ~0ull;
         if (i < seg_end) {
@@ -154,7 +169,7 @@ __global__ void __launch_bounds__(kRsThreads) rs_onesweep_kernel(const uint64_t*
     }
     // rank 32 consecutive keys per step inside the warp (stable: steps in order, lanes in order)
 #pragma unroll
-    for (int s = 0; s < kRsItems; ++s) {
+    for (int s = 0; s < kOsItems; ++s) {
         const int64_t i = wbase + s * 32 + lane;
         const bool valid = i < seg_end;
         const uint32_t d = valid ? ((uint32_t)(key[s] >> shift) & 255u) : 256u;  // 256: the out-of-range lanes group together, unused
@@ -169,56 +184,62 @@ __global__ void __launch_bounds__(kRsThreads) rs_onesweep_kernel(const uint64_t*
     }
     __syncthreads();
     // per-digit exclusive scan over the tile's warps, digit totals -> tile-local digit starts; look-back -> global bases
+    // (thread d < 256 owns digit d)
     {
         const int d = threadIdx.x;
-        uint32_t acc = 0;
+        const bool dig = d < 256;
+        uint32_t acc = 0, incl = 0;
+        if (dig) {
 #pragma unroll
-        for (int w = 0; w < kRsWarps; ++w) {
-            const uint32_t c = warp_cnt[w][d];
-            warp_cnt[w][d] = acc;
-            acc += c;
-        }
-        // publish this tile's count of digit d, then sum the counts of the preceding tiles of the segment
-        volatile uint32_t* st = status;
-        uint32_t excl = 0;
-        if (tile_in_seg == 0) {
-            st[(int64_t)tile * 256 + d] = kLbPrefix | acc;
-        } else {
-            st[(int64_t)tile * 256 + d] = kLbAgg | acc;
-            int look = tile - 1;
-            const int first = tile - tile_in_seg;
-            uint32_t spins = 0;
-            while (true) {
-                const uint32_t v = st[(int64_t)look * 256 + d];
-                if (v == 0u) {  // predecessor not published yet (it holds an earlier ticket, so it is running)
-                    if (++spins > (1u << 22)) __trap();  // never in a correct run: fail loudly instead of hanging the device
-                    continue;
-                }
-                excl += v & kLbMask;
-                if ((v & kLbPrefix) || look == first) break;
-                --look;
+            for (int w = 0; w < kOsWarps; ++w) {
+                const uint32_t c = warp_cnt[w][d];
+                warp_cnt[w][d] = acc;
+                acc += c;
             }
-            st[(int64_t)tile * 256 + d] = kLbPrefix | (excl + acc);
-        }
-        digit_base[d] = gbase[((int64_t)seg * passes + pass) * 256 + d] + excl;
-        uint32_t incl = acc;  // block-wide exclusive scan of the digit totals
+            // publish this tile's count of digit d, then sum the counts of the preceding tiles of the segment
+            volatile uint32_t* st = status;
+            uint32_t excl = 0;
+            if (tile_in_seg == 0) {
+                st[(int64_t)tile * 256 + d] = kLbPrefix | acc;
+            } else {
+                st[(int64_t)tile * 256 + d] = kLbAgg | acc;
+                int look = tile - 1;
+                const int first = tile - tile_in_seg;
+                uint32_t spins = 0;
+                while (true) {
+                    const uint32_t v = st[(int64_t)look * 256 + d];
+                    if (v == 0u) {  // predecessor not published yet (it holds an earlier ticket, so it is running)
+                        if (++spins > (1u << 22)) __trap();  // never in a correct run: fail loudly instead of hanging the device
+                        continue;
+                    }
+                    excl += v & kLbMask;
+                    if ((v & kLbPrefix) || look == first) break;
+                    --look;
+                }
+                st[(int64_t)tile * 256 + d] = kLbPrefix | (excl + acc);
+            }
+            digit_base[d] = gbase[((int64_t)seg * passes + pass) * 256 + d] + excl;
+            incl = acc;  // block-wide exclusive scan of the digit totals (the first eight warps hold the digits)
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_wsum[warp] = incl;
         }
-        if (lane == 31) s_wsum[warp] = incl;
         __syncthreads();
-        uint32_t wb = 0;
+        if (dig) {
+            uint32_t wb = 0;
 #pragma unroll
-        for (int w = 0; w < kRsWarps; ++w)
-            if (w < warp) wb += s_wsum[w];
-        digit_start[d] = wb + incl - acc;
+            for (int w = 0; w < 8; ++w)
+                if (w < warp) wb += s_wsum[w];
+            digit_start[d] = wb + incl - acc;
+        }
     }
     __syncthreads();
     // re-order the tile by digit in shared memory
 #pragma unroll
-    for (int s = 0; s < kRsItems; ++s) {
+    for (int s = 0; s < kOsItems; ++s) {
         const int64_t i = wbase + s * 32 + lane;
         if (i < seg_end) {
             const uint32_t d = (uint32_t)(key[s] >> shift) & 255u;
@@ -229,7 +250,7 @@ __global__ void __launch_bounds__(kRsThreads) rs_onesweep_kernel(const uint64_t*
     // coalesced writes: consecutive threads own consecutive positions of a digit's run
     const uint64_t idx_mask = (1ull << ib) - 1ull;
     const uint64_t high = (uint64_t)seg << low_bits;
-    for (int k = threadIdx.x; k < tile_count; k += kRsThreads) {
+    for (int k = threadIdx.x; k < tile_count; k += kOsThreads) {
         const uint64_t kk = skeys[k];
         const uint32_t d = (uint32_t)(kk >> shift) & 255u;
         const uint32_t pos = digit_base[d] + ((uint32_t)k - digit_start[d]);
@@ -506,7 +527,7 @@ int radix_sort_keys(b3d_ctx* ctx, const uint64_t* keys_in, int64_t n, int low_bi
     if (passes > kRsMaxPasses) return set_error(B3D_E_RANGE, "radix_sort_keys: %d key bits need more than %d passes", low_bits, kRsMaxPasses);
     // tiles never straddle segments
     std::vector<int32_t> tile_first(B + 1, 0);
-    for (int b = 0; b < B; ++b) tile_first[b + 1] = tile_first[b] + (int32_t)(((int64_t)seg_off_h[b + 1] - seg_off_h[b] + kRsTile - 1) / kRsTile);
+    for (int b = 0; b < B; ++b) tile_first[b + 1] = tile_first[b] + (int32_t)(((int64_t)seg_off_h[b + 1] - seg_off_h[b] + kOsTile - 1) / kOsTile);
     const int n_tiles = tile_first[B];
     DevBuf<int32_t> tile_first_d;
     B3D_TRY(tile_first_d.alloc(ctx, (size_t)B + 1));
@@ -534,7 +555,7 @@ int radix_sort_keys(b3d_ctx* ctx, const uint64_t* keys_in, int64_t n, int low_bi
     DevBuf<uint64_t> buf_a, buf_b;
     if (passes >= 2) B3D_TRY(buf_a.alloc(ctx, (size_t)n));
     if (passes >= 3) B3D_TRY(buf_b.alloc(ctx, (size_t)n));
-    const size_t smem = (size_t)kRsTile * sizeof(uint64_t);
+    const size_t smem = (size_t)kOsTile * sizeof(uint64_t);
     B3D_CUDA(cudaFuncSetAttribute((rs_onesweep_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B3D_CUDA(cudaFuncSetAttribute((rs_onesweep_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B3D_CUDA(cudaFuncSetAttribute((rs_onesweep_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -546,13 +567,13 @@ int radix_sort_keys(b3d_ctx* ctx, const uint64_t* keys_in, int64_t n, int low_bi
         uint32_t* st = status.p + (size_t)p * n_tiles * 256;
         unsigned int* tk = tickets.p + p;
         if (first && last) {
-            B3D_LAUNCH(ctx, (rs_onesweep_kernel<true, true>), n_tiles, kRsThreads, smem, in, out, order_out, sv, low_bits, ib, p, passes, ghist.p, st, tk);
+            B3D_LAUNCH(ctx, (rs_onesweep_kernel<true, true>), n_tiles, kOsThreads, smem, in, out, order_out, sv, low_bits, ib, p, passes, ghist.p, st, tk);
         } else if (first) {
-            B3D_LAUNCH(ctx, (rs_onesweep_kernel<true, false>), n_tiles, kRsThreads, smem, in, out, order_out, sv, low_bits, ib, p, passes, ghist.p, st, tk);
+            B3D_LAUNCH(ctx, (rs_onesweep_kernel<true, false>), n_tiles, kOsThreads, smem, in, out, order_out, sv, low_bits, ib, p, passes, ghist.p, st, tk);
         } else if (last) {
-            B3D_LAUNCH(ctx, (rs_onesweep_kernel<false, true>), n_tiles, kRsThreads, smem, in, out, order_out, sv, low_bits, ib, p, passes, ghist.p, st, tk);
+            B3D_LAUNCH(ctx, (rs_onesweep_kernel<false, true>), n_tiles, kOsThreads, smem, in, out, order_out, sv, low_bits, ib, p, passes, ghist.p, st, tk);
         } else {
-            B3D_LAUNCH(ctx, (rs_onesweep_kernel<false, false>), n_tiles, kRsThreads, smem, in, out, order_out, sv, low_bits, ib, p, passes, ghist.p, st, tk);
+            B3D_LAUNCH(ctx, (rs_onesweep_kernel<false, false>), n_tiles, kOsThreads, smem, in, out, order_out, sv, low_bits, ib, p, passes, ghist.p, st, tk);
         }
         ctx->prof_bytes((last ? 20 : 16) * n);  // packed words in, packed words (or keys + order) out
         in = out;
