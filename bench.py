@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture of
 # this command at 64 pairs (profiles/, see profiles/README.md for the file the figure comes from)
 NCU_TRAFFIC_PER_LAUNCH = {"icp_pass_kernel": 17.628067e9 / 10.0,                  # round 1 (profiles/r01n_ncu_icp_pass_p64_step_digest.txt)
-                          "icp_pass2_kernel": (17.390319e9 + 1.772061e9) / 10.0}  # profiles/r02c_ncu_icp_pass2_p64_digest.txt: ten passes of one step
+                          "icp_pass2_kernel": (19.127729e9 + 2.125340e9) / 10.0}  # profiles/r02g_ncu_icp_pass2_p64_digest.txt: ten passes of one step (read + write)
 
 WORKLOAD = "config2: D435 848x480 depth pairs -> deproject + tensor voxel 5mm + hybrid normals(0.01,30) + point-to-plane ICP(0.02, 30 it)"
 PIPE = dict(voxel_size=0.005, normals_max_nn=30, normals_radius=0.01, icp_kind=1, icp_max_dist=0.02, icp_max_iter=30)
