@@ -145,9 +145,10 @@ struct DispEmit {
     float* xyz;
     int32_t* src_px;  // optional: batch-global pixel index of every emitted point
     __device__ __forceinline__ void operator()(int64_t i, int64_t slot) const {
-        const int64_t px = i % frame_px;
-        const int64_t row = px / w;
-        const double x = (double)(int)(px - row * w), y = (double)row;
+        // 32-bit divisions: a batch holds fewer than 2^31 pixels (checked by the callers), and a 64-bit division costs ~4x as much
+        const uint32_t px = (uint32_t)i % (uint32_t)frame_px;
+        const uint32_t row = px / (uint32_t)w;
+        const double x = (double)(int)(px - row * (uint32_t)w), y = (double)(int)row;
         const double d = (double)((float)disp[i] / 16.0f);
         double v[4];
 #pragma unroll
@@ -182,6 +183,7 @@ int reproject_disparity_valid_batch(b3d_ctx* ctx, const int16_t* disp, int w, in
     const int64_t frame_px = (int64_t)w * h, n = frame_px * frames;
     off_h->assign((size_t)frames + 1, 0);
     if (n == 0) return B3D_OK;
+    B3D_REQUIRE(n < (int64_t)INT32_MAX, "%d frames x %lld pixels exceed 2^31-1 points", frames, (long long)frame_px);  // pixel indices are 32-bit below
     QMat Q;
     for (int i = 0; i < 16; ++i) Q.q[i] = Q_h[i];
     DevBuf<int64_t> total;

@@ -15,74 +15,76 @@ constexpr unsigned long long kScanFlagAgg = 1ull << 62;
 constexpr unsigned long long kScanFlagPrefix = 2ull << 62;
 constexpr unsigned long long kScanValueMask = (1ull << 62) - 1;
 
+// Items are dealt to the threads STRIPED (item k of thread t is tile_base + k * kScanBlock + t): every load of the predicate and
+// every store of the emitter is a coalesced access of 32 consecutive indices / 32 consecutive output slots. (The first version
+// gave each thread kScanItems CONSECUTIVE indices: order-preserving for free, but every warp access was strided by kScanItems
+// elements and the emitters' stores touched one sector per lane -- the run-head and disparity compactions ran at a fifth of the
+// copy bandwidth.) Output order = index order: the (k, warp) ballots are counted and scanned in tile order.
 template <typename Pred, typename Emit>
 __global__ void __launch_bounds__(kScanBlock) compact_kernel(Pred pred, Emit emit, int64_t n, unsigned long long* __restrict__ status,
                                                              unsigned int* __restrict__ ticket, int64_t* __restrict__ total) {
+    constexpr int kWarps = kScanBlock / 32;
+    constexpr int kCells = kScanItems * kWarps;  // (k, warp) groups of 32 consecutive indices, in tile order
+    static_assert(kCells == 64, "the scan below takes two values per lane of one warp");
     __shared__ unsigned int s_tile;
-    __shared__ int s_warp[kScanBlock / 32];
+    __shared__ int s_cnt[kCells];  // counts, then exclusive offsets
     __shared__ long long s_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const unsigned int tile = s_tile;
-    const int64_t base = (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
-    // each thread owns kScanItems consecutive indices (keeps the output order = index order)
-    unsigned int flags = 0;
-    int cnt = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        const int64_t i = base + k;
-        if (i < n && pred(i)) {
-            flags |= 1u << k;
-            ++cnt;
-        }
-    }
-    // block exclusive scan of cnt
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    int warp_base = 0, tile_total = 0;
-#pragma unroll
-    for (int w = 0; w < kScanBlock / 32; ++w) {
-        const int v = s_warp[w];
-        if (w < warp) warp_base += v;
-        tile_total += v;
-    }
-    const int excl = warp_base + incl - cnt;
-    if (threadIdx.x == 0) {
-        long long prefix = 0;
-        volatile unsigned long long* st = status;
-        if (tile == 0) {
-            st[0] = kScanFlagPrefix | (unsigned long long)tile_total;
-        } else {
-            st[tile] = kScanFlagAgg | (unsigned long long)tile_total;
-            __threadfence();
-            long long look = (long long)tile - 1;
-            while (true) {
-                unsigned long long v = st[look];
-                if (v == 0) continue;  // predecessor not published yet
-                prefix += (long long)(v & kScanValueMask);
-                if (v & kScanFlagPrefix) break;
-                --look;
-            }
-            st[tile] = kScanFlagPrefix | (unsigned long long)(prefix + tile_total);
-        }
-        s_prefix = prefix;
-        if ((int64_t)(tile + 1) * kScanTile >= n) *total = prefix + tile_total;
-    }
-    __syncthreads();
-    int64_t slot = s_prefix + excl;
+    const int64_t base = (int64_t)tile * kScanTile + threadIdx.x;
+    unsigned int flags = 0;
+    int rank[kScanItems];  // flagged items of the same (k, warp) group before this lane
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        if (flags & (1u << k)) {
-            emit(base + k, slot);
-            ++slot;
+        const int64_t i = base + (int64_t)k * kScanBlock;
+        const bool f = i < n && pred(i);
+        const unsigned int b = __ballot_sync(0xffffffffu, f);
+        flags |= f ? 1u << k : 0u;
+        rank[k] = __popc(b & ((1u << lane) - 1u));
+        if (lane == 0) s_cnt[k * kWarps + warp] = __popc(b);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // exclusive scan of the 64 group counts (lane l holds groups 2l and 2l + 1), the tile's total, the look-back
+        const int a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1];
+        int incl = a + b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
+        const int tile_total = __shfl_sync(0xffffffffu, incl, 31);
+        s_cnt[2 * lane] = incl - a - b;
+        s_cnt[2 * lane + 1] = incl - b;
+        if (lane == 0) {
+            long long prefix = 0;
+            volatile unsigned long long* st = status;
+            if (tile == 0) {
+                st[0] = kScanFlagPrefix | (unsigned long long)tile_total;
+            } else {
+                st[tile] = kScanFlagAgg | (unsigned long long)tile_total;
+                __threadfence();
+                long long look = (long long)tile - 1;
+                while (true) {
+                    unsigned long long v = st[look];
+                    if (v == 0) continue;  // predecessor not published yet
+                    prefix += (long long)(v & kScanValueMask);
+                    if (v & kScanFlagPrefix) break;
+                    --look;
+                }
+                st[tile] = kScanFlagPrefix | (unsigned long long)(prefix + tile_total);
+            }
+            s_prefix = prefix;
+            if ((int64_t)(tile + 1) * kScanTile >= n) *total = prefix + tile_total;
+        }
+    }
+    __syncthreads();
+    const int64_t tile_slot = s_prefix;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (flags & (1u << k)) emit(base + (int64_t)k * kScanBlock, tile_slot + s_cnt[k * kWarps + warp] + rank[k]);
     }
 }
 
