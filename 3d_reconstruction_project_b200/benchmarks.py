@@ -241,11 +241,21 @@ def micro_voxel_leg(device=0, steps=20, n=10_000_000, voxel=0.05, peak_gbs=None)
     run = lambda: ops.voxel_down_sample_tensor(pts, voxel, device=device, as_tensor=True)
     for _ in range(3):
         out = run()
-    ms, out = _timed(ctx, run, steps)
+    # per-call device times (one event between calls): the leg reports the MEDIAN call; the mean of a 0.7 ms call is at the mercy of a
+    # single host hiccup (the mean and the slowest call are reported next to it)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    torch.cuda.synchronize()
+    ev[0].record(ctx.stream)
+    for k in range(steps):
+        out = run()
+        ev[k + 1].record(ctx.stream)
+    torch.cuda.synchronize()
+    per_call = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(steps))
+    ms, ms_mean, ms_max = per_call[steps // 2], sum(per_call) / steps, per_call[-1]
     m = int(out["points"].shape[0])
     b = 12 * n + 12 * m
     gbps = b / (ms * 1e-3) / 1e9
     return {"workload": "micro: 10M uniform [0,1)^3 float32 points, tensor voxel_down_sample(0.05) (test/gpu-performance.py:13-26)", "ms": ms,
-            "mpoints_per_sec": n / (ms * 1e-3) / 1e6, "voxels": m,
+            "ms_mean": ms_mean, "ms_slowest_call": ms_max, "calls": steps, "mpoints_per_sec": n / (ms * 1e-3) / 1e6, "voxels": m,
             "roofline": {"bound": "hbm", "achieved": gbps, "peak": peak_gbs, "unit": "GB/s", "frac": (gbps / peak_gbs) if peak_gbs else None,
                          "algorithmic_bytes": b}}
