@@ -356,6 +356,37 @@ def test_icp_known_answer_and_oracle(ops, kind):
     assert np.array_equal(res["corr"], ref["corr"])
 
 
+def test_gicp_normal_equations_vs_numpy(ops):
+    """The generalized-ICP pass accumulates G^T M^-1 G and G^T M^-1 (p - q) through the inverse Cholesky factor of M. An
+    independent numpy statement with the plain inverse of M (cKDTree correspondences, no factor at all) must give the same 27 sums,
+    the same count and the same sum of squared distances."""
+    from scipy.spatial import cKDTree
+    from b200recon import distributed as dist
+    tgt, nrm = golden_cloud("output_00094")
+    T = small_rigid()
+    src, sn, _ = oracle.transform(np.linalg.inv(T), tgt, nrm)
+    sc = oracle.covariances_from_normals(sn).reshape(-1, 3, 3)
+    tc = oracle.covariances_from_normals(nrm).reshape(-1, 3, 3)
+    sh = dist.ShardedICP(2, src, len(src), tgt, 0.02, src_cov=sc.reshape(-1, 9), tgt_cov=tc.reshape(-1, 9), max_iter=1)
+    sums = sh.accumulate().cpu().numpy().copy()
+    sh.update()
+    sh.finish()
+    d, j = cKDTree(tgt).query(src, k=1)
+    keep = d < 0.02
+    p, q = src[keep], tgt[j[keep]]
+    A = np.linalg.inv(tc[j[keep]] + sc[keep])  # R = I at the identity start
+    G = np.zeros((len(p), 3, 6))
+    G[:, 0, 1], G[:, 0, 2] = p[:, 2], -p[:, 1]
+    G[:, 1, 0], G[:, 1, 2] = -p[:, 2], p[:, 0]
+    G[:, 2, 0], G[:, 2, 1] = p[:, 1], -p[:, 0]
+    G[:, :, 3:] = np.eye(3)
+    JTJ = np.einsum("nki,nkl,nlj->ij", G, A, G)
+    JTr = np.einsum("nki,nkl,nl->i", G, A, p - q)
+    ref = np.concatenate([JTJ[np.triu_indices(6)], JTr, [keep.sum(), (d[keep] ** 2).sum()]])
+    assert sums[27] == keep.sum()
+    assert np.allclose(sums[:29], ref, rtol=1e-9, atol=1e-9 * np.abs(ref[:27]).max()), np.abs(sums[:29] - ref).max()
+
+
 def test_icp_partial_overlap_with_init(ops):
     tgt, nrm = golden_cloud("output_00050")
     other, _ = golden_cloud("output_00008")
