@@ -189,7 +189,7 @@ def config5_leg(world, rank, local, points_per_rank=10_000_000, iters=10, dmax=0
         for name, (r, ms_v, p_v, _, _, per_rank) in runs.items():
             per_pass = ms_v / p_v
             gb = bytes_per_pass / (per_pass * 1e-3) / 1e9
-            out["variants"][name] = {"exchange": "all-reduce inside the pass kernel over peer memory (NVLink)" if name == "fused" else ("nccl all_reduce" if world > 1 else "none (one rank)"),
+            out["variants"][name] = {"exchange": "all-reduce inside the pass kernel over peer memory (NVLink)" if name == "fused" else ("nccl all_gather of the 29 sums + sum in rank order" if world > 1 else "none (one rank)"),
                                      "ms_per_pass": per_pass, "mpoints_per_sec": n / (per_pass * 1e-3) / 1e6, "algorithmic_gbps": gb,
                                      "frac_of_n_x_peak": (gb / (peak_gbs * world)) if peak_gbs else None,
                                      # per rank: the whole loop; for the NCCL variant also the shard's own pass kernel and its time in the

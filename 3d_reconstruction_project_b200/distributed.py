@@ -3,8 +3,8 @@
 1. Independent frame pairs (BASELINE config 4): pair i belongs to rank i mod world -- no data-path collective, one
    gather of the per-pair results at the end.
 2. One oversized cloud (BASELINE config 5): every rank holds a contiguous slice of the SOURCE and a replica of the target;
-   per ICP pass the 29 normal-equation sums (21 JtJ + 6 Jtr + |C| + sum d2) are all-reduced (NCCL over NVLink on GPUs, gloo
-   in the CPU tests) and every rank applies the same 6x6 solve.
+   per ICP pass the 29 normal-equation sums (21 JtJ + 6 Jtr + |C| + sum d2) are all-reduced in rank order (an NCCL all-gather
+   over NVLink on GPUs, gloo in the CPU tests, then a fixed-order sum) and every rank applies the same 6x6 solve.
 """
 import ctypes as C
 
@@ -46,10 +46,20 @@ def gather_pair_results(local, n_pairs, rank, world, group=None):
 
 
 def all_reduce_sums(sums, group=None):
-    """In-place sum of the 29-double tensor over the ranks (no-op without an initialised process group)."""
+    """In-place sum of the 29-double tensor over the ranks (no-op without an initialised process group), added IN RANK ORDER:
+    an all-gather of the ranks' vectors (232 bytes each) and `((r0 + r1) + r2) + ...` on every rank. A library all-reduce adds in
+    the order of its ring / tree, which changes with the world size and the algorithm NCCL picks; the fixed order makes the
+    result independent of both and bit-identical to the exchange fused into the pass kernel (b3d_icp_pass_peers adds the
+    peers' slots in rank order too) -- at 4 ranks a plain all_reduce differed from it in the last bit."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        world = dist.get_world_size(group)
+        parts = [torch.empty_like(sums) for _ in range(world)]
+        dist.all_gather(parts, sums, group=group)
+        acc = parts[0]
+        for r in range(1, world):
+            acc = acc + parts[r]
+        sums.copy_(acc)
     return sums
 
 

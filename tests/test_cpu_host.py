@@ -259,6 +259,45 @@ def test_two_rank_gloo_sharding(built, tmp_path):
         assert f"rank {r} ok" in o
 
 
+_ORDER_WORKER = r'''
+import os, sys
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["B3D_ROOT"])
+from b200recon import distributed as D
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["B3D_PORT"], rank=int(os.environ["RANK"]), world_size=3)
+rank = dist.get_rank()
+# three addends whose float64 sum depends on the association: ((1e16 + 1) + -1e16) = 0, ((1e16 + -1e16) + 1) = 1
+vals = [[1.0e16, 3.0], [1.0, 1.0e-16], [-1.0e16, 1.0]]
+t = torch.tensor(vals[rank] + [float(rank)] * 27, dtype=torch.float64)
+D.all_reduce_sums(t)
+want0 = (1.0e16 + 1.0) + -1.0e16     # rank order: 0.0 (the 1 is absorbed); r1 + r2 first would give 0.0 as well, r0 + r2 first gives 1.0
+want1 = (3.0 + 1.0e-16) + 1.0        # 4.0 in any order at this precision
+assert t[0].item() == want0 and t[1].item() == want1 and t[2].item() == 3.0, t[:3]
+g = [torch.zeros_like(t) for _ in range(3)]
+dist.all_gather(g, t)
+assert torch.equal(g[0], g[1]) and torch.equal(g[0], g[2])
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_three_rank_sum_in_rank_order(built, tmp_path):
+    """all_reduce_sums adds the ranks' vectors as ((r0 + r1) + r2): every rank gets the same bits, and they are the bits of that order
+    ((1e16 + 1) - 1e16 = 0, whereas (1e16 - 1e16) + 1 = 1)."""
+    script = tmp_path / "order_worker.py"
+    script.write_text(_ORDER_WORKER)
+    port = str(29900 + os.getpid() % 90)
+    procs = []
+    for r in range(3):
+        env = dict(os.environ, RANK=str(r), B3D_ROOT=ROOT, B3D_PORT=port, OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{o}"
+        assert f"rank {r} ok" in o
+
+
 def test_shims_resolve_reference_main(built):
     """With shims/ first on sys.path the reference's unchanged main.py imports b200recon's classes (SURVEY.md 8f rank 1)."""
     ref = "/root/reference"

@@ -109,7 +109,7 @@ def main():
         per_pass = total_ms / passes  # device time of the whole loop (updates and flag reads included), max over ranks
         fused = a.fused and world > 1
         print(json.dumps({"config": "config5: one cloud sharded by source points, point-to-plane, all-reduce of 29 doubles per pass",
-                          "n_points": n, "n_gpus": world, "exchange": ("peer-memory, fused in the pass kernel" if fused else "nccl all_reduce"),
+                          "n_points": n, "n_gpus": world, "exchange": ("peer-memory, fused in the pass kernel" if fused else "nccl all_gather + sum in rank order"),
                           "passes": passes, "ms_per_pass": per_pass, "accumulate_ms_per_pass": None if fused else acc_ms / passes,
                           "allreduce_ms_per_pass": None if fused else red_ms / passes,
                           "allreduce_share": None if fused else red_ms / (acc_ms + red_ms),
