@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(kNrmBlock) normals_staged_kernel(GridView<doub
 //    the covariance goes to global memory (48 bytes per point). No float64 copy of the candidates in shared memory.
 //  normals_eig2_kernel: one thread per point, closed-form eigenvector + orientation against the prior, every lane busy.
 // Points that need the k-nearest cut (more than k in-radius neighbours, or more than 32), or whose box takes more than one
-// staging batch, are queued for the per-lane kernel exactly as before (their covariance slot is marked).
+// staging batch, are queued (their covariance slot is marked) for normals_queue2_kernel below: one warp per queued point.
 #ifndef B3D_NRM2_CAP
 #define B3D_NRM2_CAP 472  // + 8 padding slots = 15 groups of 32: four blocks of four warps still fit one SM's shared memory
 #endif
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(kNrmBlock, B3D_NRM2_MIN_BLOCKS) normals_cov2_k
         const double ux = unit_coord_of_query(qx, F.ox, F.per_m), uy = unit_coord_of_query(qy, F.oy, F.per_m), uz = unit_coord_of_query(qz, F.oz, F.per_m);
         // The chunk is searched as one group of 32 lanes; a group whose box does not fit ONE staging batch (dense clouds: the
         // neighbour lists refer to slots of the batch) is split in halves and retried, down to groups of four lanes; what still
-        // does not fit goes to the per-lane kernel.
+        // does not fit is queued (normals_queue2_kernel).
         unsigned int pending = __ballot_sync(0xffffffffu, valid);
         int width = 32;
         while (pending != 0u) {
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(256) normals_eig2_kernel(const double* __restr
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double* c = cov6 + 6 * i;
         const double a00 = c[0];
-        if (__double_as_longlong(a00) == 0x7ff8000000000b3dll) continue;  // queued for the per-lane kernel
+        if (__double_as_longlong(a00) == 0x7ff8000000000b3dll) continue;  // queued: normals_queue2_kernel writes this normal
         Sym3<double> C{a00, c[1], c[2], c[3], c[4], c[5]};
         Vec3<double> nrm = sym3_smallest_eigvec<double>(C);
         const double len = sqrt(nrm.x * nrm.x + nrm.y * nrm.y + nrm.z * nrm.z);
@@ -853,7 +853,7 @@ int estimate_normals_batch(b3d_ctx* ctx, const T* xyz, const Segments& seg, int 
     int blocks = (n + 127) / 128;
     if constexpr (std::is_same<T, double>::value && !TENSOR) {
         if (use_radius && max_nn <= kNrmList) {
-            // staged fast path; the per-lane kernel below only redoes the queued points
+            // staged fast path; the queued points are redone by normals_queue2_kernel (round-2 kernels) or by the per-lane kernel below (round-1 kernel)
             QueryChunks qc;
             B3D_TRY(chunks_from_grid(ctx, *grid, seg.off, seg.off_h, &qc));
             B3D_TRY(todo_buf.alloc(ctx, (size_t)n));
