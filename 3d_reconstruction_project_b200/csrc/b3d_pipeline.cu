@@ -20,16 +20,12 @@ int reproject_disparity_valid_batch(b3d_ctx* ctx, const int16_t* disp, int w, in
                                     std::vector<int32_t>* off_h);
 template <typename T, typename IndexT>
 int voxel_downsample_batch(b3d_ctx* ctx, const T* xyz, const T* a0, const T* a1, const Segments& seg, double voxel, int flavour, T* o_xyz,
-                           T* o_a0, T* o_a1, IndexT* o_index, int32_t* o_count, SpatialSort* out_sort, const std::vector<double>* bounds_in);
+                           T* o_a0, T* o_a1, IndexT* o_index, int32_t* o_count, SpatialSort* out_sort, const std::vector<double>* bounds_in,
+                           double* o_xyz64);
 template <typename T, bool TENSOR>
 int estimate_normals_batch(b3d_ctx* ctx, const T* xyz, const Segments& seg, int max_nn, double radius, const T* prior, T* normals,
                            Grid<T>* reuse_grid, int reuse_rmax);
 
-namespace {
-__global__ void __launch_bounds__(256) widen_kernel(const float* __restrict__ in, int64_t n, double* __restrict__ out) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
-}
-}  // namespace
 
 }  // namespace b3d
 
@@ -44,19 +40,14 @@ struct BackParams {
     int icp_max_iter;
 };
 
-// Everything after the voxel down-sampling: vox holds the 2P down-sampled float32 clouds back to back (P sources, then P
-// targets), voff their offsets ([2P + 1]); raw_off the offsets of the raw clouds (for the result records).
-static int register_voxels_f32(b3d_ctx* ctx, DevBuf<float>& vox, const std::vector<int32_t>& voff, const std::vector<int32_t>& raw_off, int P,
+// Everything after the voxel down-sampling: vox64 holds the 2P down-sampled clouds back to back (P sources, then P targets), the
+// float32 voxel means widened to float64 by the reduction itself (to_legacy(): exact), voff their offsets ([2P + 1]); raw_off the
+// offsets of the raw clouds (for the result records).
+static int register_voxels_f32(b3d_ctx* ctx, DevBuf<double>& vox64, const std::vector<int32_t>& voff, const std::vector<int32_t>& raw_off, int P,
                                const BackParams* pr, b3d_pair_result* results_h) {
     const int F = 2 * P;
     const int64_t M = voff[F];
     const int32_t Ms = voff[P], Mt = (int32_t)M - voff[P];
-
-    // 3. to_legacy: float32 -> float64 (exact)
-    DevBuf<double> vox64;
-    B3D_TRY(vox64.alloc(ctx, (size_t)(3 * M)));
-    B3D_LAUNCH(ctx, widen_kernel, ctx->grid_for(3 * M, 256, 1, 8), 256, 0, vox.p, 3 * M, vox64.p);
-    vox.release();
     const double* src_pts = vox64.p;
     const double* tgt_pts = vox64.p + 3 * (int64_t)voff[P];
     std::vector<int32_t> soff(P + 1), toff(P + 1);
@@ -149,7 +140,7 @@ static int register_voxels_f32(b3d_ctx* ctx, DevBuf<float>& vox, const std::vect
 }
 
 // tensor voxel down-sampling of the frames [f0, f1) of xyz (raw offsets raw_off) into vox at row *m_done; appends their offsets
-static int voxel_group(b3d_ctx* ctx, const float* xyz, const std::vector<int32_t>& raw_off, int f0, int f1, float voxel_size, DevBuf<float>& vox,
+static int voxel_group(b3d_ctx* ctx, const float* xyz, const std::vector<int32_t>& raw_off, int f0, int f1, float voxel_size, DevBuf<double>& vox,
                        std::vector<int32_t>* voff, int64_t* m_done) {
     std::vector<int32_t> goff(f1 - f0 + 1);
     for (int f = f0; f <= f1; ++f) goff[f - f0] = raw_off[f] - raw_off[f0];
@@ -158,7 +149,7 @@ static int voxel_group(b3d_ctx* ctx, const float* xyz, const std::vector<int32_t
     B3D_TRY(upload_segments(ctx, goff, &goff_d, &gseg));
     SpatialSort vs;
     B3D_TRY((voxel_downsample_batch<float, int64_t>(ctx, xyz + 3 * (int64_t)raw_off[f0], nullptr, nullptr, gseg, (double)voxel_size, kLatTensorVoxel,
-                                                     vox.p + 3 * *m_done, nullptr, nullptr, nullptr, nullptr, &vs, nullptr)));
+                                                     nullptr, nullptr, nullptr, nullptr, nullptr, &vs, nullptr, vox.p + 3 * *m_done)));
     for (int f = f0; f < f1; ++f) (*voff)[f + 1] = (int32_t)(*m_done + vs.run_off_h[f - f0 + 1]);
     *m_done += vs.n_runs;
     return B3D_OK;
@@ -168,7 +159,7 @@ static int voxel_group(b3d_ctx* ctx, const float* xyz, const std::vector<int32_t
 static int register_clouds_f32(b3d_ctx* ctx, DevBuf<float>& xyz, const std::vector<int32_t>& raw_off, int P, const BackParams* pr,
                                b3d_pair_result* results_h) {
     const int F = 2 * P;
-    DevBuf<float> vox;
+    DevBuf<double> vox;
     B3D_TRY(vox.alloc(ctx, (size_t)(3 * (int64_t)raw_off[F])));
     std::vector<int32_t> voff(F + 1, 0);
     int64_t m_done = 0;
@@ -235,7 +226,7 @@ int b3d_register_depth_pairs(b3d_ctx* ctx, const b3d_pair_params* pr, const uint
         B3D_CUDA(cudaMemcpyAsync(depth_d.p + N * G.f0, host, (size_t)(N * (G.f1 - G.f0)) * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->copy_stream));
         B3D_CUDA(cudaEventRecord(ev[g], ctx->copy_stream));
     }
-    DevBuf<float> vox;
+    DevBuf<double> vox;
     B3D_TRY(vox.alloc(ctx, (size_t)(3 * N * F)));
     std::vector<int32_t> voff(F + 1, 0);
     int64_t m_done = 0;

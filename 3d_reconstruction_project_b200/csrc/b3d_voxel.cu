@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) voxel_reduce_short_kernel(const T* __rest
                                                                  const Lattice* __restrict__ lat, int shift, T* __restrict__ o_xyz,
                                                                  T* __restrict__ o_a0, T* __restrict__ o_a1, IndexT* __restrict__ o_index,
                                                                  int32_t* __restrict__ o_count, int32_t* __restrict__ long_list,
-                                                                 int32_t* __restrict__ long_count) {
+                                                                 int32_t* __restrict__ long_count, double* __restrict__ o_xyz64) {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_runs; r += (int64_t)gridDim.x * blockDim.x) {
         const int32_t s = run_start[r], e = run_start[r + 1];
         const uint64_t key = keys[s];
@@ -54,7 +54,12 @@ __global__ void __launch_bounds__(256) voxel_reduce_short_kernel(const T* __rest
             if (a1 != nullptr) { s1[0] += a1[3 * p]; s1[1] += a1[3 * p + 1]; s1[2] += a1[3 * p + 2]; }
         }
         const T cnt = (T)(e - s);
-        o_xyz[3 * r] = sp[0] / cnt; o_xyz[3 * r + 1] = sp[1] / cnt; o_xyz[3 * r + 2] = sp[2] / cnt;
+        // o_xyz64: the means widened to float64 (exact) instead of the flavour's own type -- the registration pipeline's to_legacy()
+        if (o_xyz64 != nullptr) {
+            o_xyz64[3 * r] = (double)(sp[0] / cnt); o_xyz64[3 * r + 1] = (double)(sp[1] / cnt); o_xyz64[3 * r + 2] = (double)(sp[2] / cnt);
+        } else {
+            o_xyz[3 * r] = sp[0] / cnt; o_xyz[3 * r + 1] = sp[1] / cnt; o_xyz[3 * r + 2] = sp[2] / cnt;
+        }
         if (a0 != nullptr && o_a0 != nullptr) { o_a0[3 * r] = s0[0] / cnt; o_a0[3 * r + 1] = s0[1] / cnt; o_a0[3 * r + 2] = s0[2] / cnt; }
         if (a1 != nullptr && o_a1 != nullptr) { o_a1[3 * r] = s1[0] / cnt; o_a1[3 * r + 1] = s1[1] / cnt; o_a1[3 * r + 2] = s1[2] / cnt; }
     }
@@ -68,7 +73,8 @@ template <typename T>
 __global__ void __launch_bounds__(kLongBlock) voxel_reduce_long_kernel(const T* __restrict__ xyz, const T* __restrict__ a0, const T* __restrict__ a1,
                                                                        const uint32_t* __restrict__ order, const int32_t* __restrict__ run_start,
                                                                        const int32_t* __restrict__ long_list, const int32_t* __restrict__ long_count,
-                                                                       T* __restrict__ o_xyz, T* __restrict__ o_a0, T* __restrict__ o_a1) {
+                                                                       T* __restrict__ o_xyz, T* __restrict__ o_a0, T* __restrict__ o_a1,
+                                                                       double* __restrict__ o_xyz64) {
     __shared__ T sm[9][kLongBlock + 1];
     const int n_long = *long_count;
     const int n_comp = 3 + (a0 != nullptr ? 3 : 0) + (a1 != nullptr ? 3 : 0);
@@ -107,7 +113,8 @@ __global__ void __launch_bounds__(kLongBlock) voxel_reduce_long_kernel(const T* 
             const T m = acc / (T)(e - s);
             const int c = threadIdx.x;
             if (c < 3) {
-                o_xyz[3 * (int64_t)r + c] = m;
+                if (o_xyz64 != nullptr) o_xyz64[3 * (int64_t)r + c] = (double)m;
+                else o_xyz[3 * (int64_t)r + c] = m;
             } else if (a0 != nullptr && c < 6) {
                 if (o_a0 != nullptr) o_a0[3 * (int64_t)r + (c - 3)] = m;
             } else {
@@ -123,7 +130,8 @@ __global__ void __launch_bounds__(kLongBlock) voxel_reduce_long_kernel(const T* 
 // (run offsets per cloud = down-sampled cloud offsets).
 template <typename T, typename IndexT>
 int voxel_downsample_batch(b3d_ctx* ctx, const T* xyz, const T* a0, const T* a1, const Segments& seg, double voxel, int flavour, T* o_xyz,
-                           T* o_a0, T* o_a1, IndexT* o_index, int32_t* o_count, SpatialSort* out_sort, const std::vector<double>* bounds_in) {
+                           T* o_a0, T* o_a1, IndexT* o_index, int32_t* o_count, SpatialSort* out_sort, const std::vector<double>* bounds_in,
+                           double* o_xyz64) {
     std::vector<double> bounds_local;
     const std::vector<double>* bounds = bounds_in;
     if (!bounds) {
@@ -139,17 +147,17 @@ int voxel_downsample_batch(b3d_ctx* ctx, const T* xyz, const T* a0, const T* a1,
     B3D_TRY(long_count.alloc(ctx, 1));
     B3D_CUDA(cudaMemsetAsync(long_count.p, 0, sizeof(int32_t), ctx->stream));
     B3D_LAUNCH(ctx, (voxel_reduce_short_kernel<T, IndexT>), ctx->grid_for(ss->n_runs, 256, 1, 16), 256, 0, xyz, a0, a1, ss->keys.p, ss->order.p,
-               ss->run_start.p, ss->n_runs, ss->lat.p, ss->shift, o_xyz, o_a0, o_a1, o_index, o_count, long_list.p, long_count.p);
+               ss->run_start.p, ss->n_runs, ss->lat.p, ss->shift, o_xyz, o_a0, o_a1, o_index, o_count, long_list.p, long_count.p, o_xyz64);
     const int long_grid = (int)std::min<int64_t>(max_long, (int64_t)ctx->sm_count * 8);
     B3D_LAUNCH(ctx, voxel_reduce_long_kernel<T>, long_grid, kLongBlock, 0, xyz, a0, a1, ss->order.p, ss->run_start.p, long_list.p, long_count.p,
-               o_xyz, o_a0, o_a1);
+               o_xyz, o_a0, o_a1, o_xyz64);
     return B3D_OK;
 }
 
 template int voxel_downsample_batch<float, int64_t>(b3d_ctx*, const float*, const float*, const float*, const Segments&, double, int, float*,
-                                                    float*, float*, int64_t*, int32_t*, SpatialSort*, const std::vector<double>*);
+                                                    float*, float*, int64_t*, int32_t*, SpatialSort*, const std::vector<double>*, double*);
 template int voxel_downsample_batch<double, int32_t>(b3d_ctx*, const double*, const double*, const double*, const Segments&, double, int, double*,
-                                                     double*, double*, int32_t*, int32_t*, SpatialSort*, const std::vector<double>*);
+                                                     double*, double*, int32_t*, int32_t*, SpatialSort*, const std::vector<double>*, double*);
 
 }  // namespace b3d
 
@@ -177,7 +185,7 @@ int b3d_voxel_downsample_legacy(b3d_ctx* ctx, const double* xyz, const double* c
     const double* a1 = colors ? normals : nullptr;
     double* o1 = colors ? out_normals : nullptr;
     B3D_TRY((voxel_downsample_batch<double, int32_t>(ctx, xyz, a0, a1, seg, voxel_size, kLatLegacyVoxel, out_xyz, o0, o1, out_index, out_count, &ss,
-                                                      nullptr)));
+                                                      nullptr, nullptr)));
     *m_h = ss.n_runs;
     return ctx->sync();
 }
@@ -197,7 +205,7 @@ int b3d_voxel_downsample_tensor(b3d_ctx* ctx, const float* xyz, const float* att
     B3D_TRY(single_segment(ctx, n, &off, &seg));
     SpatialSort ss;
     B3D_TRY((voxel_downsample_batch<float, int64_t>(ctx, xyz, attr, nullptr, seg, (double)voxel_size, kLatTensorVoxel, out_xyz, out_attr, nullptr,
-                                                     out_index, out_count, &ss, nullptr)));
+                                                     out_index, out_count, &ss, nullptr, nullptr)));
     *m_h = ss.n_runs;
     return ctx->sync();
 }
